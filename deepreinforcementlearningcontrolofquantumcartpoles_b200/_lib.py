@@ -1,0 +1,85 @@
+"""ctypes binding of libqcart.so (include/qcart.h).  No CPU fallback: a missing library or device raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqcart.so")
+
+QC_HARMONIC, QC_INV_HARMONIC, QC_QUARTIC = 0, 1, 2
+QC_FLAG_FAIL, QC_FLAG_ESCAPED = 1, 2
+QC_AUX_ENERGY, QC_AUX_XMEAN, QC_AUX_OUTSIDE, QC_AUX_NORM, QC_AUX_COUNT = 0, 1, 2, 3, 4
+QC_ERR_ARG, QC_ERR_CUDA, QC_ERR_PIVOT, QC_ERR_UNSUPPORTED, QC_ERR_STATE = -1, -2, -3, -4, -5
+
+
+class QcConfig(C.Structure):
+    _fields_ = [("variant", C.c_int32), ("n", C.c_int32), ("x_max", C.c_double), ("grid_size", C.c_double),
+                ("lambda_", C.c_double), ("mass", C.c_double), ("omega", C.c_double), ("dt", C.c_double),
+                ("gamma", C.c_double), ("n_sub", C.c_int32), ("f_max", C.c_double), ("n_levels", C.c_int32),
+                ("moment_order", C.c_int32), ("x_threshold", C.c_double), ("herm_mode", C.c_int32),
+                ("device", C.c_int32)]
+
+
+class QcartError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libqcart error %d: %s" % (code, msg))
+        self.code = code
+
+
+# every symbol include/qcart.h declares: (name, restype, argtypes)
+_vp, _dp, _ip, _i64 = C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64
+SYMBOLS = [
+    ("qc_last_error", C.c_char_p, []),
+    ("qc_version", C.c_char_p, []),
+    ("qc_create", C.c_int, [C.POINTER(QcConfig), C.POINTER(_vp)]),
+    ("qc_destroy", C.c_int, [_vp]),
+    ("qc_get_config", C.c_int, [_vp, C.POINTER(QcConfig)]),
+    ("qc_state_len", C.c_int, [_vp]),
+    ("qc_num_moments", C.c_int, [_vp]),
+    ("qc_num_aux", C.c_int, [_vp]),
+    ("qc_set_batch", C.c_int, [_vp, _i64]),
+    ("qc_batch", _i64, [_vp]),
+    ("qc_set_state", C.c_int, [_vp, _dp, C.c_int, _vp]),
+    ("qc_get_state", C.c_int, [_vp, _dp, C.c_int, _vp]),
+    ("qc_state_ptr", C.c_void_p, [_vp]),
+    ("qc_set_seed", C.c_int, [_vp, C.c_uint64, _i64]),
+    ("qc_clear_flags", C.c_int, [_vp, _vp]),
+    ("qc_init_packets", C.c_int, [_vp, _dp, _dp, C.c_double, C.c_int, _vp]),
+    ("qc_init_fock", C.c_int, [_vp, _dp, C.c_int, _vp]),
+    ("qc_step", C.c_int, [_vp, _ip, _dp, C.c_int, _ip, _dp, _dp, _vp, _dp, _dp, _vp]),
+    ("qc_step_forces", C.c_int, [_vp, _dp, _dp, C.c_int, _ip, _dp, _dp, _vp, _dp, _dp, _vp]),
+    ("qc_step_host", C.c_int, [_vp, _ip, _dp, C.c_int, _dp, _dp, _vp]),
+    ("qc_get_moments", C.c_int, [_vp, _dp, _dp, _vp]),
+    ("qc_level_force", C.c_double, [_vp, C.c_int]),
+    ("qc_step1", C.c_int, [_vp, _dp, C.c_double, C.c_double, C.c_double, _dp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    ("qc_simulate_10_steps1", C.c_int, [_vp, _dp, C.c_double, C.c_double, C.c_double, _dp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    ("qc_get_moments1", C.c_int, [_vp, _dp, _dp]),
+    ("qc_x_expectation1", C.c_int, [_vp, _dp, C.POINTER(C.c_double)]),
+    ("qc_philox_normals", None, [C.c_uint64, C.c_uint64, C.c_uint64, _dp]),
+    ("qc_measure_fp64_peak", C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    ("qc_measure_smem_peak", C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    ("qc_launch_count", _i64, [_vp]),
+    ("qc_kernel_info", C.c_char_p, [_vp]),
+]
+
+_lib = None
+
+
+def load():
+    """Load libqcart.so; raises if it has not been built (python __graft_entry__.py / csrc/build.sh)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libqcart.so is not built (run deepreinforcementlearningcontrolofquantumcartpoles_b200/csrc/build.sh); "
+                              "there is no CPU fallback for the SSE hot path")
+        lib = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise QcartError(rc, load().qc_last_error().decode())

@@ -1,0 +1,433 @@
+// C-ABI of libqcart.so (see include/qcart.h).  Handles, device memory, per-force factor tables, launches.
+#include "qc_internal.h"
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <new>
+
+using namespace qc;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define QC_CUDA(call)                                                                                              \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaGetLastError();                                      \
+        return fail(QC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+
+struct BatchView {
+    int64_t B = 0;
+    double2* psi = nullptr;
+    long long* step = nullptr;
+    unsigned char* flags = nullptr;
+    LaunchPlan plan; int plan_nsub = -1, plan_W = -1; int64_t plan_B = -1;
+};
+
+struct qc_sim {
+    Model model;
+    int device = 0;
+    cudaStream_t stream = nullptr;          // private stream of the host-buffer entry points
+    // operator tables (device, zero padded by 8 doubles on both sides)
+    double *raw_x = nullptr, *raw_hd = nullptr, *raw_h2 = nullptr;
+    // factor tables
+    double2* d_fac = nullptr; double* d_slot_force = nullptr; double* d_herm = nullptr;
+    int n_slots = 0, cap_slots = 0; std::vector<double> slot_force;
+    int W_needed = 0;
+    // resident batch
+    BatchView batch;
+    uint64_t seed = 0; int64_t traj_offset = 0;
+    // staging for qc_step_host / qc_step_forces
+    int32_t* d_action = nullptr; int64_t action_cap = 0;
+    double* d_noise = nullptr; size_t noise_cap = 0;
+    double* d_mom = nullptr; double* d_aux = nullptr; unsigned char* d_flagout = nullptr; int64_t out_cap = 0;
+    // single-trajectory shim state
+    BatchView one; int32_t* d_slot1 = nullptr; double* d_noise1 = nullptr; double* d_out1 = nullptr;  // d_out1: moments[20] aux[4] q[16] xm[16]
+    unsigned char* d_flag1 = nullptr;
+    int64_t launches = 0;
+    std::string info;
+};
+
+extern "C" const char* qc_last_error(void) { return g_err.c_str(); }
+extern "C" const char* qc_version(void) { return "qcart 0.1 sm_100a"; }
+
+static int use_device(const qc_sim* s) {
+    if (!s) return fail(QC_ERR_ARG, "null handle");
+    QC_CUDA(cudaSetDevice(s->device));
+    return QC_OK;
+}
+
+static int upload_padded(const std::vector<double>& v, int n, double** raw) {
+    std::vector<double> tmp(n + 16, 0.0);
+    for (int i = 0; i < n && i < (int)v.size(); i++) tmp[8 + i] = v[i];
+    QC_CUDA(cudaMalloc(raw, sizeof(double) * (n + 16)));
+    QC_CUDA(cudaMemcpy(*raw, tmp.data(), sizeof(double) * (n + 16), cudaMemcpyHostToDevice));
+    return QC_OK;
+}
+
+// add one force to the factor tables (device + host mirror)
+static int add_slot(qc_sim* s, double F, int* slot_out) {
+    const Model& m = s->model;
+    if (s->n_slots >= s->cap_slots) return fail(QC_ERR_UNSUPPORTED, "too many distinct force values (factor-table capacity)");
+    std::vector<zc> tab;
+    int rc = m.factor(F, tab);
+    if (rc == QC_ERR_PIVOT) return fail(rc, "implicit matrix would need row pivoting for this force (outside the reference's stable parameter range)");
+    if (rc) return fail(rc, "factorisation failed");
+    const int W = m.decay_width(tab, 1e-18);
+    if (W > s->W_needed) { s->W_needed = W; s->batch.plan_nsub = -1; s->one.plan_nsub = -1; }
+    const size_t row = (size_t)m.n * (m.ba + 1);
+    QC_CUDA(cudaMemcpy(s->d_fac + row * s->n_slots, tab.data(), sizeof(zc) * row, cudaMemcpyHostToDevice));
+    QC_CUDA(cudaMemcpy(s->d_slot_force + s->n_slots, &F, sizeof(double), cudaMemcpyHostToDevice));
+    if (s->d_herm) { std::vector<double> ht; m.herm_table(F, ht); QC_CUDA(cudaMemcpy(s->d_herm + (size_t)m.n * 11 * s->n_slots, ht.data(), sizeof(double) * ht.size(), cudaMemcpyHostToDevice)); }
+    s->slot_force.push_back(F);
+    *slot_out = s->n_slots++;
+    return QC_OK;
+}
+
+extern "C" int qc_create(const qc_config* cfg, qc_sim** out) {
+    if (!cfg || !out) return fail(QC_ERR_ARG, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) { cudaGetLastError(); return fail(QC_ERR_CUDA, "no usable CUDA device: libqcart has no CPU fallback"); }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(QC_ERR_ARG, "device ordinal out of range");
+    qc_sim* s = new (std::nothrow) qc_sim();
+    if (!s) return fail(QC_ERR_ARG, "out of host memory");
+    std::string err;
+    int rc = build_model(*cfg, s->model, err);
+    if (rc) { delete s; return fail(rc, err); }
+    s->device = cfg->device;
+    s->model.cfg.n = s->model.n;
+    const Model& m = s->model;
+    rc = use_device(s); if (rc) { delete s; return rc; }
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail(QC_ERR_CUDA, "cudaStreamCreate failed"); }
+    if ((rc = upload_padded(m.x, m.n, &s->raw_x)) || (rc = upload_padded(m.hdiag, m.n, &s->raw_hd))) { qc_destroy(s); return rc; }
+    if (m.cfg.variant == QC_INV_HARMONIC && (rc = upload_padded(m.hoff, m.n, &s->raw_h2))) { qc_destroy(s); return rc; }
+    s->cap_slots = cfg->n_levels + 256;
+    const size_t row = (size_t)m.n * (m.ba + 1);
+    if (cudaMalloc(&s->d_fac, sizeof(double2) * row * s->cap_slots) != cudaSuccess || cudaMalloc(&s->d_slot_force, sizeof(double) * s->cap_slots) != cudaSuccess) {
+        qc_destroy(s); return fail(QC_ERR_CUDA, "cudaMalloc(factor tables) failed");
+    }
+    if (m.cfg.variant == QC_INV_HARMONIC && m.cfg.herm_mode != 2 && cudaMalloc(&s->d_herm, sizeof(double) * (size_t)m.n * 11 * s->cap_slots) != cudaSuccess) {
+        qc_destroy(s); return fail(QC_ERR_CUDA, "cudaMalloc(herm table) failed");
+    }
+    for (int a = 0; a < cfg->n_levels; a++) {            // the 21 forces of the controller (Q/RL.py:108-112)
+        int slot; rc = add_slot(s, qc_level_force(s, a), &slot);
+        if (rc) { qc_destroy(s); return rc; }
+    }
+    // single-trajectory shim buffers
+    if (cudaMalloc(&s->one.psi, sizeof(double2) * m.n) != cudaSuccess || cudaMalloc(&s->one.step, sizeof(long long)) != cudaSuccess ||
+        cudaMalloc(&s->one.flags, 1) != cudaSuccess || cudaMalloc(&s->d_slot1, sizeof(int32_t)) != cudaSuccess ||
+        cudaMalloc(&s->d_noise1, sizeof(double) * 32) != cudaSuccess || cudaMalloc(&s->d_out1, sizeof(double) * 64) != cudaSuccess ||
+        cudaMalloc(&s->d_flag1, 1) != cudaSuccess) { qc_destroy(s); return fail(QC_ERR_CUDA, "cudaMalloc(shim buffers) failed"); }
+    cudaMemset(s->one.step, 0, sizeof(long long)); cudaMemset(s->one.flags, 0, 1);
+    s->one.B = 1;
+    *out = s;
+    return QC_OK;
+}
+
+extern "C" int qc_destroy(qc_sim* s) {
+    if (!s) return QC_OK;
+    cudaSetDevice(s->device);
+    cudaFree(s->raw_x); cudaFree(s->raw_hd); cudaFree(s->raw_h2); cudaFree(s->d_fac); cudaFree(s->d_slot_force); cudaFree(s->d_herm);
+    cudaFree(s->batch.psi); cudaFree(s->batch.step); cudaFree(s->batch.flags);
+    cudaFree(s->d_action); cudaFree(s->d_noise); cudaFree(s->d_mom); cudaFree(s->d_aux); cudaFree(s->d_flagout);
+    cudaFree(s->one.psi); cudaFree(s->one.step); cudaFree(s->one.flags); cudaFree(s->d_slot1); cudaFree(s->d_noise1); cudaFree(s->d_out1); cudaFree(s->d_flag1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    cudaGetLastError();
+    delete s;
+    return QC_OK;
+}
+
+extern "C" int qc_get_config(const qc_sim* s, qc_config* out) { if (!s || !out) return fail(QC_ERR_ARG, "null argument"); *out = s->model.cfg; return QC_OK; }
+extern "C" int qc_state_len(const qc_sim* s) { return s ? s->model.n : 0; }
+extern "C" int qc_num_moments(const qc_sim* s) { return s ? s->model.K : 0; }
+extern "C" int qc_num_aux(const qc_sim*) { return QC_AUX_COUNT; }
+extern "C" int64_t qc_batch(const qc_sim* s) { return s ? s->batch.B : 0; }
+extern "C" double* qc_state_ptr(qc_sim* s) { return s ? reinterpret_cast<double*>(s->batch.psi) : nullptr; }
+extern "C" int64_t qc_launch_count(const qc_sim* s) { return s ? s->launches : 0; }
+extern "C" const char* qc_kernel_info(const qc_sim* s) { return s ? s->info.c_str() : ""; }
+
+extern "C" double qc_level_force(const qc_sim* s, int level) {
+    const qc_config& c = s->model.cfg;
+    const int half = (c.n_levels - 1) / 2;
+    if (half == 0) return 0.0;
+    return (double)(level - half) * c.f_max / (double)half;          // convert_to_force, Q/RL.py:108-112
+}
+
+extern "C" int qc_set_batch(qc_sim* s, int64_t B) {
+    int rc = use_device(s); if (rc) return rc;
+    if (B <= 0 || B > (int64_t)1 << 30) return fail(QC_ERR_ARG, "batch size out of range");
+    BatchView& b = s->batch;
+    if (b.B != B) {
+        cudaFree(b.psi); cudaFree(b.step); cudaFree(b.flags); b = BatchView();
+        QC_CUDA(cudaMalloc(&b.psi, sizeof(double2) * (size_t)B * s->model.n));
+        QC_CUDA(cudaMalloc(&b.step, sizeof(long long) * B));
+        QC_CUDA(cudaMalloc(&b.flags, (size_t)B));
+        b.B = B;
+    }
+    QC_CUDA(cudaMemset(b.psi, 0, sizeof(double2) * (size_t)B * s->model.n));
+    QC_CUDA(cudaMemset(b.step, 0, sizeof(long long) * B));
+    QC_CUDA(cudaMemset(b.flags, 0, (size_t)B));
+    return QC_OK;
+}
+
+extern "C" int qc_set_state(qc_sim* s, const double* psi, int on_device, void* stream) {
+    int rc = use_device(s); if (rc) return rc;
+    if (!s->batch.psi) return fail(QC_ERR_STATE, "qc_set_batch first");
+    if (!psi) return fail(QC_ERR_ARG, "null state");
+    const size_t bytes = sizeof(double2) * (size_t)s->batch.B * s->model.n;
+    QC_CUDA(cudaMemcpyAsync(s->batch.psi, psi, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    QC_CUDA(cudaMemsetAsync(s->batch.flags, 0, (size_t)s->batch.B, (cudaStream_t)stream));
+    if (!on_device) QC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return QC_OK;
+}
+extern "C" int qc_get_state(const qc_sim* s, double* psi, int on_device, void* stream) {
+    int rc = use_device(s); if (rc) return rc;
+    if (!s->batch.psi) return fail(QC_ERR_STATE, "qc_set_batch first");
+    if (!psi) return fail(QC_ERR_ARG, "null state");
+    const size_t bytes = sizeof(double2) * (size_t)s->batch.B * s->model.n;
+    QC_CUDA(cudaMemcpyAsync(psi, s->batch.psi, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    if (!on_device) QC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return QC_OK;
+}
+extern "C" int qc_set_seed(qc_sim* s, uint64_t seed, int64_t traj_offset) {
+    int rc = use_device(s); if (rc) return rc;
+    s->seed = seed; s->traj_offset = traj_offset;
+    if (s->batch.step) QC_CUDA(cudaMemset(s->batch.step, 0, sizeof(long long) * s->batch.B));
+    QC_CUDA(cudaMemset(s->one.step, 0, sizeof(long long)));
+    return QC_OK;
+}
+extern "C" int qc_clear_flags(qc_sim* s, void* stream) {
+    int rc = use_device(s); if (rc) return rc;
+    if (!s->batch.flags) return fail(QC_ERR_STATE, "qc_set_batch first");
+    QC_CUDA(cudaMemsetAsync(s->batch.flags, 0, (size_t)s->batch.B, (cudaStream_t)stream));
+    return QC_OK;
+}
+
+static int stage_in(qc_sim* s, const double* host, size_t count, double** dev_out, cudaStream_t st) {
+    // small helper for nullable per-trajectory host arrays
+    if (!host) { *dev_out = nullptr; return QC_OK; }
+    if (s->noise_cap < count) { cudaFree(s->d_noise); s->d_noise = nullptr; s->noise_cap = 0; QC_CUDA(cudaMalloc(&s->d_noise, sizeof(double) * count)); s->noise_cap = count; }
+    QC_CUDA(cudaMemcpyAsync(s->d_noise, host, sizeof(double) * count, cudaMemcpyHostToDevice, st));
+    *dev_out = s->d_noise;
+    return QC_OK;
+}
+
+extern "C" int qc_init_packets(qc_sim* s, const double* wavenumber, const double* mean, double stdv, int on_device, void* stream) {
+    int rc = use_device(s); if (rc) return rc;
+    if (s->model.cfg.variant != QC_QUARTIC) return fail(QC_ERR_ARG, "qc_init_packets is for grid handles");
+    if (!s->batch.psi) return fail(QC_ERR_STATE, "qc_set_batch first");
+    const int64_t B = s->batch.B;
+    const double *dk = wavenumber, *dm = mean;
+    if (!on_device && (wavenumber || mean)) {
+        std::vector<double> tmp(2 * (size_t)B, 0.0);
+        if (wavenumber) std::copy(wavenumber, wavenumber + B, tmp.begin());
+        if (mean) std::copy(mean, mean + B, tmp.begin() + B);
+        double* d = nullptr; rc = stage_in(s, tmp.data(), tmp.size(), &d, (cudaStream_t)stream); if (rc) return rc;
+        QC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        dk = wavenumber ? d : nullptr; dm = mean ? d + B : nullptr;
+    }
+    rc = launch_init_packets(s->batch.psi, (int)B, s->model.n, s->model.cfg.grid_size, s->model.half, dk, dm, stdv, stream);
+    if (rc) return fail(rc, "init kernel launch failed");
+    s->launches++;
+    QC_CUDA(cudaMemsetAsync(s->batch.flags, 0, (size_t)B, (cudaStream_t)stream));
+    return QC_OK;
+}
+extern "C" int qc_init_fock(qc_sim* s, const double* alpha, int on_device, void* stream) {
+    int rc = use_device(s); if (rc) return rc;
+    if (s->model.cfg.variant == QC_QUARTIC) return fail(QC_ERR_ARG, "qc_init_fock is for Fock handles");
+    if (!s->batch.psi) return fail(QC_ERR_STATE, "qc_set_batch first");
+    const double* da = alpha;
+    if (alpha && !on_device) { double* d = nullptr; rc = stage_in(s, alpha, 2 * (size_t)s->batch.B, &d, (cudaStream_t)stream); if (rc) return rc; da = d; }
+    rc = launch_init_fock(s->batch.psi, (int)s->batch.B, s->model.n, da, stream);
+    if (rc) return fail(rc, "init kernel launch failed");
+    s->launches++;
+    QC_CUDA(cudaMemsetAsync(s->batch.flags, 0, (size_t)s->batch.B, (cudaStream_t)stream));
+    return QC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* noise, int n_sub, const int32_t* nsub_traj,
+               double* moments, double* aux, uint8_t* flags, double* q_out, double* xmean_out, int moments_only, void* stream) {
+    const Model& m = s->model;
+    if (n_sub <= 0 && !moments_only) n_sub = m.cfg.n_sub;
+    if (moments_only) n_sub = 0;
+    if (n_sub > 4096) return fail(QC_ERR_ARG, "n_sub > 4096 per launch: split the call");
+    if (b.plan_nsub != n_sub || b.plan_B != b.B || b.plan_W != s->W_needed) {
+        std::string err;
+        int rc = plan_launch(m, n_sub, (int)b.B, s->W_needed, b.plan, err);
+        if (rc) return fail(rc, err);
+        b.plan_nsub = n_sub; b.plan_B = b.B; b.plan_W = s->W_needed;
+        if (&b == &s->batch) s->info = b.plan.info;
+    }
+    const LaunchPlan& pl = b.plan;
+    StepParams p; memset(&p, 0, sizeof(p));
+    p.n = m.n; p.B = (int)b.B; p.T = pl.T; p.G = pl.G; p.P = pl.P; p.chunk = pl.chunk; p.W = pl.W; p.NP = pl.NP; p.n_sub = n_sub;
+    p.K = m.K; p.M = m.cfg.moment_order; p.tstride = pl.tstride; p.variant = m.cfg.variant; p.ba = m.ba; p.herm_mode = m.cfg.herm_mode;
+    p.half = m.half; p.fail_len = m.fail_len; p.cen_lo = m.cen_lo; p.cen_hi = m.cen_hi;
+    p.w = m.w; p.kappa = m.kappa; p.dt = m.cfg.dt; p.gamma = m.cfg.gamma; p.fail_thr2 = m.fail_thr * m.fail_thr; p.h = m.cfg.grid_size;
+    for (int k = 0; k < 4; k++) { p.tk[k] = (m.cfg.variant == QC_QUARTIC) ? m.hoff[k] : 0.0; p.pk[k] = m.pk[k]; }
+    p.x = s->raw_x + 8; p.hdiag = s->raw_hd + 8; p.h2 = s->raw_h2 ? s->raw_h2 + 8 : nullptr;
+    p.fac = s->d_fac; p.slot_force = s->d_slot_force; p.slot = slot_dev; p.order = nullptr; p.n_slots = s->n_slots; p.herm_tab = s->d_herm;
+    p.psi = b.psi; p.noise = noise; p.seed = s->seed; p.traj_offset = s->traj_offset; p.step_count = b.step; p.nsub_traj = nsub_traj;
+    p.moments = moments; p.aux = aux; p.flags_out = flags; p.flags_latch = b.flags; p.q_out = q_out; p.xmean_out = xmean_out;
+    p.moments_only = moments_only;
+    std::string err;
+    int rc = launch_step(pl, p, stream, err);
+    if (rc) return fail(rc, err);
+    s->launches++;
+    return QC_OK;
+}
+
+extern "C" int qc_step(qc_sim* s, const int32_t* action, const double* noise, int n_sub, const int32_t* nsub_traj,
+                       double* moments, double* aux, uint8_t* flags, double* q_out, double* xmean_out, void* stream) {
+    int rc = use_device(s); if (rc) return rc;
+    if (!s->batch.psi) return fail(QC_ERR_STATE, "qc_set_batch first");
+    if (!action) return fail(QC_ERR_ARG, "null action array");
+    return run(s, s->batch, action, noise, n_sub, nsub_traj, moments, aux, flags, q_out, xmean_out, 0, stream);
+}
+
+static int ensure_out(qc_sim* s) {
+    const int64_t B = s->batch.B;
+    if (s->out_cap < B) {
+        cudaFree(s->d_mom); cudaFree(s->d_aux); cudaFree(s->d_flagout); cudaFree(s->d_action);
+        s->d_mom = s->d_aux = nullptr; s->d_flagout = nullptr; s->d_action = nullptr; s->out_cap = 0;
+        QC_CUDA(cudaMalloc(&s->d_mom, sizeof(double) * B * s->model.K));
+        QC_CUDA(cudaMalloc(&s->d_aux, sizeof(double) * B * QC_AUX_COUNT));
+        QC_CUDA(cudaMalloc(&s->d_flagout, (size_t)B));
+        QC_CUDA(cudaMalloc(&s->d_action, sizeof(int32_t) * B));
+        s->out_cap = B;
+    }
+    return QC_OK;
+}
+
+extern "C" int qc_step_forces(qc_sim* s, const double* force_host, const double* noise, int n_sub, const int32_t* nsub_traj,
+                              double* moments, double* aux, uint8_t* flags, double* q_out, double* xmean_out, void* stream) {
+    int rc = use_device(s); if (rc) return rc;
+    if (!s->batch.psi) return fail(QC_ERR_STATE, "qc_set_batch first");
+    if (!force_host) return fail(QC_ERR_ARG, "null force array");
+    rc = ensure_out(s); if (rc) return rc;
+    const int64_t B = s->batch.B;
+    std::vector<int32_t> slots(B);
+    for (int64_t i = 0; i < B; i++) {
+        const double F = force_host[i];
+        int slot = -1;
+        for (int k = 0; k < s->n_slots; k++) if (s->slot_force[k] == F) { slot = k; break; }
+        if (slot < 0) { rc = add_slot(s, F, &slot); if (rc) return rc; }
+        slots[i] = slot;
+    }
+    QC_CUDA(cudaMemcpyAsync(s->d_action, slots.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    QC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));       // `slots` is a temporary
+    return run(s, s->batch, s->d_action, noise, n_sub, nsub_traj, moments, aux, flags, q_out, xmean_out, 0, stream);
+}
+
+extern "C" int qc_step_host(qc_sim* s, const int32_t* action, const double* noise, int n_sub, double* moments, double* aux, uint8_t* flags) {
+    int rc = use_device(s); if (rc) return rc;
+    if (!s->batch.psi) return fail(QC_ERR_STATE, "qc_set_batch first");
+    if (!action) return fail(QC_ERR_ARG, "null action array");
+    rc = ensure_out(s); if (rc) return rc;
+    const int64_t B = s->batch.B; const int K = s->model.K;
+    if (n_sub <= 0) n_sub = s->model.cfg.n_sub;
+    cudaStream_t st = s->stream;
+    QC_CUDA(cudaMemcpyAsync(s->d_action, action, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
+    double* dn = nullptr;
+    rc = stage_in(s, noise, (size_t)B * n_sub * 2, &dn, st); if (rc) return rc;
+    rc = run(s, s->batch, s->d_action, dn, n_sub, nullptr, moments ? s->d_mom : nullptr, aux ? s->d_aux : nullptr, flags ? s->d_flagout : nullptr, nullptr, nullptr, 0, st);
+    if (rc) return rc;
+    if (moments) QC_CUDA(cudaMemcpyAsync(moments, s->d_mom, sizeof(double) * B * K, cudaMemcpyDeviceToHost, st));
+    if (aux) QC_CUDA(cudaMemcpyAsync(aux, s->d_aux, sizeof(double) * B * QC_AUX_COUNT, cudaMemcpyDeviceToHost, st));
+    if (flags) QC_CUDA(cudaMemcpyAsync(flags, s->d_flagout, (size_t)B, cudaMemcpyDeviceToHost, st));
+    QC_CUDA(cudaStreamSynchronize(st));
+    return QC_OK;
+}
+
+extern "C" int qc_get_moments(qc_sim* s, double* moments, double* aux, void* stream) {
+    int rc = use_device(s); if (rc) return rc;
+    if (!s->batch.psi) return fail(QC_ERR_STATE, "qc_set_batch first");
+    rc = ensure_out(s); if (rc) return rc;
+    QC_CUDA(cudaMemsetAsync(s->d_action, 0, sizeof(int32_t) * s->batch.B, (cudaStream_t)stream));
+    BatchView mv = s->batch; mv.plan_nsub = -1;                         // separate plan (n_sub = 0) without disturbing the step plan
+    return run(s, mv, s->d_action, nullptr, 0, nullptr, moments, aux, nullptr, nullptr, nullptr, 1, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// single-trajectory shims
+
+static int find_or_add_slot(qc_sim* s, double F, int* slot) {
+    for (int k = 0; k < s->n_slots; k++) if (s->slot_force[k] == F) { *slot = k; return QC_OK; }
+    return add_slot(s, F, slot);
+}
+
+static int step1_common(qc_sim* s, double* psi, double dt, double F, double gamma, const double* normals, int nsteps,
+                        double* q, double* x_mean, int* fail_out, bool fail_final_only) {
+    int rc = use_device(s); if (rc) return rc;
+    if (!psi) return fail(QC_ERR_ARG, "The input object cannot be identified as an array of complex128");
+    const Model& m = s->model;
+    if (dt != m.cfg.dt || gamma != m.cfg.gamma) return fail(QC_ERR_ARG, "dt / gamma differ from the handle's configuration (create a handle per (dt, gamma))");
+    int slot; rc = find_or_add_slot(s, F, &slot); if (rc) return rc;
+    cudaStream_t st = s->stream;
+    QC_CUDA(cudaMemcpyAsync(s->one.psi, psi, sizeof(double2) * m.n, cudaMemcpyHostToDevice, st));
+    QC_CUDA(cudaMemcpyAsync(s->d_slot1, &slot, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    QC_CUDA(cudaMemsetAsync(s->one.flags, 0, 1, st));
+    if (normals) QC_CUDA(cudaMemcpyAsync(s->d_noise1, normals, sizeof(double) * 2 * nsteps, cudaMemcpyHostToDevice, st));
+    double* dq = s->d_out1 + 32; double* dxm = s->d_out1 + 48;
+    rc = run(s, s->one, s->d_slot1, normals ? s->d_noise1 : nullptr, nsteps, nullptr, nullptr, nullptr, s->d_flag1, dq, dxm, 0, st);
+    if (rc) return rc;
+    double hq[16], hxm[16]; unsigned char hf = 0;
+    QC_CUDA(cudaMemcpyAsync(psi, s->one.psi, sizeof(double2) * m.n, cudaMemcpyDeviceToHost, st));
+    QC_CUDA(cudaMemcpyAsync(hq, dq, sizeof(double) * nsteps, cudaMemcpyDeviceToHost, st));
+    QC_CUDA(cudaMemcpyAsync(hxm, dxm, sizeof(double) * nsteps, cudaMemcpyDeviceToHost, st));
+    QC_CUDA(cudaMemcpyAsync(&hf, s->d_flag1, 1, cudaMemcpyDeviceToHost, st));
+    QC_CUDA(cudaStreamSynchronize(st));
+    if (q) *q = hq[nsteps - 1];
+    if (x_mean) *x_mean = hxm[nsteps - 1];
+    if (fail_out) {
+        if (!fail_final_only) *fail_out = (hf & QC_FLAG_FAIL) ? 1 : 0;
+        else {   // simulate_10_steps checks the boundary once, on the final state (Q:555-556)
+            auto nrm = [&](int lo, int hi) { double a = 0; for (int i = lo; i < hi; i++) a += psi[2 * i] * psi[2 * i] + psi[2 * i + 1] * psi[2 * i + 1]; return std::sqrt(a); };
+            int f = nrm(m.n - m.fail_len, m.n) > m.fail_thr;
+            if (m.cfg.variant == QC_QUARTIC) f = f || (nrm(0, m.fail_len) > m.fail_thr);
+            *fail_out = f;
+        }
+    }
+    return QC_OK;
+}
+
+extern "C" int qc_step1(qc_sim* s, double* psi, double dt, double F, double gamma, const double* normals, double* q, double* x_mean, int* fail_out) {
+    return step1_common(s, psi, dt, F, gamma, normals, 1, q, x_mean, fail_out, false);
+}
+extern "C" int qc_simulate_10_steps1(qc_sim* s, double* psi, double dt, double F, double gamma, const double* normals, double* q, double* x_mean, int* fail_out) {
+    return step1_common(s, psi, dt, F, gamma, normals, 10, q, x_mean, fail_out, true);
+}
+
+static int moments1_common(qc_sim* s, const double* psi, double* mom_out, double* xmean_out) {
+    int rc = use_device(s); if (rc) return rc;
+    if (!psi) return fail(QC_ERR_ARG, "The input state cannot be identified as an array of complex128");
+    const Model& m = s->model;
+    cudaStream_t st = s->stream;
+    int32_t zero = 0;
+    QC_CUDA(cudaMemcpyAsync(s->one.psi, psi, sizeof(double2) * m.n, cudaMemcpyHostToDevice, st));
+    QC_CUDA(cudaMemcpyAsync(s->d_slot1, &zero, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    BatchView mv = s->one; mv.plan_nsub = -1;
+    rc = run(s, mv, s->d_slot1, nullptr, 0, nullptr, s->d_out1, s->d_out1 + 24, nullptr, nullptr, nullptr, 1, st);
+    if (rc) return rc;
+    double h[28];
+    QC_CUDA(cudaMemcpyAsync(h, s->d_out1, sizeof(double) * 28, cudaMemcpyDeviceToHost, st));
+    QC_CUDA(cudaStreamSynchronize(st));
+    if (mom_out) for (int k = 0; k < m.K; k++) mom_out[k] = h[k];
+    if (xmean_out) *xmean_out = h[24 + QC_AUX_XMEAN];
+    return QC_OK;
+}
+extern "C" int qc_get_moments1(qc_sim* s, const double* psi, double* out) {
+    if (!out) return fail(QC_ERR_ARG, "The moment data array is missing");
+    return moments1_common(s, psi, out, nullptr);
+}
+extern "C" int qc_x_expectation1(qc_sim* s, const double* psi, double* out) {
+    if (!out) return fail(QC_ERR_ARG, "null output");
+    return moments1_common(s, psi, nullptr, out);
+}
+
+// ------------------------------------------------------------------------------------------------------
+extern "C" void qc_philox_normals(uint64_t seed, uint64_t traj, uint64_t step, double* out2) { philox_normals_host(seed, traj, step, out2); }
+extern "C" int qc_measure_fp64_peak(int device, double* v) { int rc = measure_fp64_peak(device, v); return rc ? fail(rc, "fp64 peak micro-benchmark failed") : QC_OK; }
+extern "C" int qc_measure_smem_peak(int device, double* v) { int rc = measure_smem_peak(device, v); return rc ? fail(rc, "smem peak micro-benchmark failed") : QC_OK; }

@@ -1,0 +1,95 @@
+// Internal declarations shared by qc_model.cpp (host precompute), qc_kernels.cu (device code) and qc_api.cu (C-ABI).
+#pragma once
+#include <stdint.h>
+#include <vector_types.h>
+#include <complex>
+#include <string>
+#include <vector>
+#include "../../include/qcart.h"
+
+namespace qc {
+
+typedef std::complex<double> zc;
+
+// ------------------------------------------------------------------------------------------------------
+// Host-side model of one system: operators of the reference's Set_World constructors and the per-force
+// factorisation that replaces reset_ab (Q:394-432).
+struct Model {
+    qc_config cfg;
+    int n = 0;          // state length
+    int bx = 0;         // half bandwidth of x_hat (0 grid, 1 Fock)
+    int bh = 0;         // half bandwidth of H (4 grid, 0 harmonic, 2 inverted harmonic)
+    int ba = 0;         // half bandwidth of A = I + i dt/2 (H - kappa F x)
+    double w = 1.0;     // inner-product weight (grid_size or 1)
+    double kappa = 0.0; // force coupling (pi grid, omega Fock)
+    int half = 0;       // grid: index of x = 0
+    std::vector<double> x;      // grid x[i] (Q:48); Fock: xl[i] = sqrt((i+1)/2), i < n-1, else 0 (H:65-72)
+    std::vector<double> hdiag;  // H[i][i]
+    std::vector<double> hoff;   // grid: 4 uniform off-diagonal constants t_k; inverted harmonic: h2[i] = H[i][i+2] (n values); harmonic: empty
+    double pk[4] = {0, 0, 0, 0};  // grid: first-derivative coefficients c_k / h (Q:59-70)
+    double fail_thr = 0.0;      // threshold of check_boundary_error (Q:561, H:404, I:423)
+    int fail_len = 0;           // number of boundary amplitudes tested (6 both sides grid; 5 top levels Fock)
+    int cen_lo = 0, cen_hi = 0; // inverted quartic: index window of |x| < x_th (IQ/main_parallel.py:78-81); empty = off
+    int K = 0;                  // moments per trajectory
+
+    // A = L D L^T for one force; returns QC_ERR_PIVOT when LAPACK's partial pivoting (zgbtf2) would have swapped rows.
+    // tab: n*(ba+1) complex, row i = { l[i][i-1], ..., l[i][i-ba], 1/d[i] }.
+    int factor(double F, std::vector<zc>& tab) const;
+    // Smallest warm-up length such that a substitution started W points early (zero history) reproduces the
+    // exact one to < tol relative (measured on impulse responses of both sweeps).
+    int decay_width(const std::vector<zc>& tab, double tol) const;
+    // inverted harmonic: K = Im(C) = -dt^4/24 H0^3 + dt^6/360 H0^5 (real symmetric, half bandwidth 10); tab[i*11] = K_ii, tab[i*11+k] = K[i][i-k].
+    // Needed to reproduce the HERMITIAN-descriptor application of the complex-symmetric C (I:23,551):  C_herm = C - 2i strict_lower(K).
+    void herm_table(double F, std::vector<double>& tab) const;
+};
+
+int build_model(const qc_config& cfg, Model& m, std::string& err);
+
+// ------------------------------------------------------------------------------------------------------
+// Kernel parameters (passed by value).
+struct StepParams {
+    // geometry
+    int n, B, T, G, P, chunk, W, NP, n_sub, K, M;
+    int tstride;             // bytes of shared memory per trajectory slot
+    int variant, ba, herm_mode;
+    int half, fail_len, cen_lo, cen_hi;
+    // physics
+    double w, kappa, dt, gamma, fail_thr2, h;
+    double tk[4], pk[4];
+    // tables (device)
+    const double* x;         // [n + 16] zero padded by 8 on both sides (pointer to element 0)
+    const double* hdiag;     // [n + 16] same padding
+    const double* h2;        // [n + 16] inverted harmonic, same padding (else null)
+    const double2* fac;      // [slots][n][ba+1]
+    const double* slot_force;// [slots]
+    const int32_t* slot;     // [B] slot per trajectory
+    const int32_t* order;    // [B] work list (null = identity)
+    const double* herm_tab;  // inverted harmonic, herm_mode 0/1: [slots][n][11] = {K_ii, K[i][i-1..i-10]}, K = Im(C)
+    int n_slots;
+    // state
+    double2* psi;            // [B][n]
+    const double* noise;     // [B][n_sub][2] or null
+    unsigned long long seed; long long traj_offset;
+    long long* step_count;   // [B]
+    const int32_t* nsub_traj;// [B] or null
+    // outputs
+    double* moments; double* aux; unsigned char* flags_out; unsigned char* flags_latch; double* q_out; double* xmean_out;
+    int moments_only;        // 1: skip the substep loop, only compute moments/aux of the resident state
+};
+
+struct LaunchPlan {
+    int L, T, G, P, chunk, W, NP, threads, smem_bytes, tstride, maxt;
+    bool multi;
+    char info[192];
+};
+
+int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan, std::string& err);
+int launch_step(const LaunchPlan& plan, const StepParams& p, void* stream, std::string& err);
+int launch_init_packets(double2* psi, int B, int n, double h, int half, const double* k, const double* mean, double stdv, void* stream);
+int launch_init_fock(double2* psi, int B, int n, const double* alpha, void* stream);
+int measure_fp64_peak(int device, double* flops);
+int measure_smem_peak(int device, double* bps);
+
+void philox_normals_host(uint64_t seed, uint64_t traj, uint64_t step, double* out2);
+
+}  // namespace qc
