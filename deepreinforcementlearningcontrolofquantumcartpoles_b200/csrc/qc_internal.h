@@ -79,8 +79,8 @@ struct StepParams {
 
 struct LaunchPlan {
     int L, T, G, P, chunk, W, NP, threads, smem_bytes, tstride, maxt;
-    bool multi;
-    char info[192];
+    bool multi, tabs;
+    char info[224];
 };
 
 int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan, std::string& err);

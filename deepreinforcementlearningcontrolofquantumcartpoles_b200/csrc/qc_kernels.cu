@@ -172,38 +172,44 @@ __device__ __forceinline__ void sweep_h0(const LaneOps<VAR, L>& ops, double2* __
 }
 
 // ------------------------------------------------------------------------------------------------------
-// The implicit solve by the solver lanes of warp 0 (see file header).  rhs in U, scratch z in V, result in U.
-template <int VAR, int L>
-__device__ __forceinline__ void solver_phase(const StepParams& p, unsigned char* smem, int tid, bool active_any) {
-    constexpr int BA = VarTraits<VAR>::BA;
-    const int G = p.G, P = p.P, n = p.n;
-    const int ts = tid / P, cs = tid - ts * P;
-    const bool sol = (tid < p.T * P);
-    unsigned char* base = smem + (size_t)(sol ? ts : 0) * p.tstride;
-    double2* U = reinterpret_cast<double2*>(base);
-    double2* V = U + p.NP;
-    double* scal = reinterpret_cast<double*>(base + p.tstride - 128);
-    int* iflag = reinterpret_cast<int*>(scal + 8);
-    const bool act = sol && (iflag[1] != 0);                 // trajectory present and still stepping
-    const int s0 = cs * p.chunk, e0 = min(s0 + p.chunk, n);
-    const bool work = act && (s0 < n);
-    const double2* __restrict__ fac = p.fac + (size_t)(act ? iflag[2] : 0) * n * (BA + 1);
+// The implicit solve (I + i dt/2 H0) psi' = psi~, done by the first warp of the trajectory (see file header).
+// rhs in U, scratch z in V, result in U.  Lane c owns points [c*chunk, (c+1)*chunk) and starts both substitutions W points
+// outside its chunk with zero history.  Every lane runs the same trip count (chunk + W); out-of-range points read as zero rows.
+// Factor rows {l_1..l_BA, 1/d, (xl,0)} come from the shared-memory copy `tab` ([line index][CS], TABS) or from global memory.
+template <int VAR> struct SolveTraits { static constexpr int BA = VarTraits<VAR>::BA; static constexpr int CS = (BA == 4) ? 5 : ((BA == 1) ? 3 : 5); };
 
-    if (work) {   // forward: L y = rhs, z = D^{-1} y
-        const int start = max(0, s0 - p.W);
+template <int VAR, int L, bool TABS>
+__device__ __forceinline__ void solve_traj(const StepParams& p, double2* __restrict__ U, double2* __restrict__ V, const double2* __restrict__ tab,
+                                           const double2* __restrict__ fac, double* scal, int* iflag, int lane) {
+    constexpr int BA = SolveTraits<VAR>::BA, CS = SolveTraits<VAR>::CS;
+    const int G = p.G, n = p.n, chunk = p.chunk, W = p.W;
+    const int s0 = lane * chunk, e0 = min(s0 + chunk, n);
+    const int trips = chunk + W;
+    // ---- forward: L y = rhs, z = D^{-1} y ------------------------------------------------------------------
+    {
         double2 y[BA];
 #pragma unroll
         for (int k = 0; k < BA; k++) y[k] = mk2(0.0, 0.0);
-        double2 cf[BA + 1];
+        int i = s0 - W;
+        // line position of i (for i < 0 the loads are predicated off, the position is only advanced)
+        int jj = ((i % L) + L) % L, ll = (i - jj) / L;
+#pragma unroll 4
+        for (int t = 0; t < trips; t++) {
+            const bool ok = (i >= 0) && (i < e0);
+            const int li = jj * G + ll;
+            double2 rhs = mk2(0.0, 0.0), cf[BA + 1];
 #pragma unroll
-        for (int k = 0; k <= BA; k++) cf[k] = __ldg(&fac[(size_t)start * (BA + 1) + k]);
-        double2 rhs = U[lidx<L>(start, G)];
-        for (int i = start; i < e0; i++) {
-            double2 cfn[BA + 1]; double2 rhsn = mk2(0.0, 0.0);
-            const int in = (i + 1 < e0) ? i + 1 : i;
+            for (int k = 0; k <= BA; k++) cf[k] = mk2(0.0, 0.0);
+            if (ok) {
+                rhs = U[li];
+                if (TABS) {
 #pragma unroll
-            for (int k = 0; k <= BA; k++) cfn[k] = __ldg(&fac[(size_t)in * (BA + 1) + k]);
-            rhsn = U[lidx<L>(in, G)];
+                    for (int k = 0; k <= BA; k++) cf[k] = tab[li * CS + k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k <= BA; k++) cf[k] = __ldg(&fac[(size_t)i * (BA + 1) + k]);
+                }
+            }
             double re = rhs.x, im = rhs.y;
 #pragma unroll
             for (int k = BA - 1; k >= 0; k--) {   // far history first: the newest value (k = 0) closes the dependency chain
@@ -213,30 +219,40 @@ __device__ __forceinline__ void solver_phase(const StepParams& p, unsigned char*
 #pragma unroll
             for (int k = BA - 1; k > 0; k--) y[k] = y[k - 1];
             y[0] = mk2(re, im);
-            if (i >= s0) V[lidx<L>(i, G)] = mk2(re * cf[BA].x - im * cf[BA].y, re * cf[BA].y + im * cf[BA].x);
-#pragma unroll
-            for (int k = 0; k <= BA; k++) cf[k] = cfn[k];
-            rhs = rhsn;
+            if (ok && i >= s0) V[li] = mk2(re * cf[BA].x - im * cf[BA].y, re * cf[BA].y + im * cf[BA].x);
+            i++; jj++; if (jj == L) { jj = 0; ll++; }
         }
     }
     __syncwarp();
-    double nrm = 0.0, sx = 0.0, bl = 0.0, br = 0.0, cen = 0.0;
-    if (work) {   // backward: L^T x = z, column oriented (uses row i of L again)
-        const int end = min(n, e0 + p.W);
+    // ---- backward: L^T x = z, column oriented (row i of L again) ------------------------------------------
+    double nrm = 0.0, sx = 0.0, cen = 0.0;
+    {
         double2 pend[BA];
 #pragma unroll
         for (int k = 0; k < BA; k++) pend[k] = mk2(0.0, 0.0);
-        double2 cf[BA];
-#pragma unroll
-        for (int k = 0; k < BA; k++) cf[k] = __ldg(&fac[(size_t)(end - 1) * (BA + 1) + k]);
-        double2 z = V[lidx<L>(end - 1, G)];
+        int i = s0 + trips - 1;
+        int jj = i % L, ll = i / L;
         double2 xprev = mk2(0.0, 0.0);
-        for (int i = end - 1; i >= s0; i--) {
-            double2 cfn[BA]; double2 zn;
-            const int in = (i - 1 >= s0) ? i - 1 : i;
+        const bool do_cen = (VAR == QC_QUARTIC) && (p.cen_hi > p.cen_lo);
+#pragma unroll 4
+        for (int t = 0; t < trips; t++) {
+            const bool ok = (i < n);
+            const int li = jj * G + ll;
+            double2 z = mk2(0.0, 0.0), cf[BA + 2];
 #pragma unroll
-            for (int k = 0; k < BA; k++) cfn[k] = __ldg(&fac[(size_t)in * (BA + 1) + k]);
-            zn = V[lidx<L>(in, G)];
+            for (int k = 0; k < BA + 2; k++) cf[k] = mk2(0.0, 0.0);
+            if (ok) {
+                z = V[li];
+                if (TABS) {
+#pragma unroll
+                    for (int k = 0; k < BA; k++) cf[k] = tab[li * CS + k];
+                    if (VAR != QC_QUARTIC) cf[BA + 1] = tab[li * CS + BA + 1];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < BA; k++) cf[k] = __ldg(&fac[(size_t)i * (BA + 1) + k]);
+                    if (VAR != QC_QUARTIC) cf[BA + 1] = mk2(__ldg(&p.x[i]), 0.0);
+                }
+            }
             const double xr = z.x + pend[0].x, xi = z.y + pend[0].y;
 #pragma unroll
             for (int k = 0; k < BA; k++) {
@@ -244,44 +260,42 @@ __device__ __forceinline__ void solver_phase(const StepParams& p, unsigned char*
                 pend[k].x = fma(-xr, cf[k].x, fma(xi, cf[k].y, pr));
                 pend[k].y = fma(-xr, cf[k].y, fma(-xi, cf[k].x, pi));
             }
-            if (i < e0) {
-                U[lidx<L>(i, G)] = mk2(xr, xi);
+            if (ok && i < e0) {
+                U[li] = mk2(xr, xi);
                 const double a2 = xr * xr + xi * xi;
                 nrm += a2;
-                if constexpr (VAR == QC_QUARTIC) {
+                if (VAR == QC_QUARTIC) {
                     sx = fma(p.h * (double)(i - p.half), a2, sx);
-                    if (i < p.fail_len) bl += a2;
-                    if (i >= p.cen_lo && i < p.cen_hi) cen += a2;
+                    if (do_cen && i >= p.cen_lo && i < p.cen_hi) cen += a2;
                 } else {
-                    sx = fma(2.0 * __ldg(&p.x[i]), xr * xprev.x + xi * xprev.y, sx);
+                    sx = fma(2.0 * cf[BA + 1].x, xr * xprev.x + xi * xprev.y, sx);     // 2 xl_i Re(conj(x_i) x_{i+1})
                 }
-                if (i >= n - p.fail_len) br += a2;
             }
             xprev = mk2(xr, xi);
-#pragma unroll
-            for (int k = 0; k < BA; k++) cf[k] = cfn[k];
-            z = zn;
+            i--; jj--; if (jj < 0) { jj = L - 1; ll--; }
         }
     }
-    // combine the P chunks of a trajectory (P is a power of two, lanes contiguous)
-    for (int o = P >> 1; o > 0; o >>= 1) {
-        nrm += __shfl_xor_sync(0xffffffffu, nrm, o); sx += __shfl_xor_sync(0xffffffffu, sx, o);
-        bl += __shfl_xor_sync(0xffffffffu, bl, o); br += __shfl_xor_sync(0xffffffffu, br, o);
-        cen += __shfl_xor_sync(0xffffffffu, cen, o);
-    }
-    if (act && cs == 0) {
+    nrm = warp_sum(nrm); sx = warp_sum(sx); cen = warp_sum(cen);
+    __syncwarp();
+    if (lane == 0) {
         const double s = 1.0 / sqrt(nrm) / sqrt(p.w);          // normalize(): Q:259-263, H:197-201
         const double s2 = s * s;
+        // check_boundary_error (Q:559-565, H:403-407, I:422-426) on the normalised state
+        double bl = 0.0, br = 0.0;
+        for (int k = 0; k < p.fail_len; k++) {
+            const double2 hi = U[lidx<L>(n - 1 - k, G)]; br += hi.x * hi.x + hi.y * hi.y;
+            if (VAR == QC_QUARTIC) { const double2 lo = U[lidx<L>(k, G)]; bl += lo.x * lo.x + lo.y * lo.y; }
+        }
         scal[0] = s; scal[1] = p.w * sx * s2;
         int f = iflag[0];
-        if (bl * s2 > p.fail_thr2 || br * s2 > p.fail_thr2) f |= QC_FLAG_FAIL;      // check_boundary_error
+        if (bl * s2 > p.fail_thr2 || br * s2 > p.fail_thr2) f |= QC_FLAG_FAIL;
         if (VAR == QC_QUARTIC && p.cen_hi > p.cen_lo) { if (1.0 - p.w * cen * s2 > 0.5) f |= QC_FLAG_ESCAPED; }
         iflag[0] = f;
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
-template <int VAR, int L, bool MULTI, int MAXT>
+template <int VAR, int L, bool MULTI, int MAXT, bool TABS>
 __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     constexpr int HB = VarTraits<VAR>::HB;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -297,10 +311,13 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     double2* U = reinterpret_cast<double2*>(base);
     double2* V = U + p.NP;
     double2* X3 = V + p.NP;                                              // Fock only (plan allocates it)
-    double* nz = reinterpret_cast<double*>(base + (size_t)((VAR == QC_QUARTIC) ? 2 : 3) * p.NP * sizeof(double2));
+    constexpr int NBUF = (VAR == QC_QUARTIC) ? 2 : 3;
+    constexpr int CS = SolveTraits<VAR>::CS, BAs = SolveTraits<VAR>::BA;
+    double2* tab = U + (size_t)NBUF * p.NP;                              // [NP][CS] factor rows of this trajectory's force (TABS)
+    double* nz = reinterpret_cast<double*>(base + (size_t)(NBUF + (TABS ? CS : 0)) * p.NP * sizeof(double2));
     double* red = reinterpret_cast<double*>(base + p.tstride - 128 - 2 * QC_MAXRED * nwarps * sizeof(double));
     double* scal = reinterpret_cast<double*>(base + p.tstride - 128);
-    int* iflag = reinterpret_cast<int*>(scal + 8);   // [0] latched flags, [1] active this substep, [2] factor slot
+    int* iflag = reinterpret_cast<int*>(scal + 8);   // [0] latched flags
     int red_phase = 0;
 
     const int slot = have ? min(max(p.slot[traj], 0), p.n_slots - 1) : 0;
@@ -352,7 +369,19 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
         else philox_normals_dev(p.seed, (uint64_t)(p.traj_offset + traj), (uint64_t)(step0 + s), &r0, &r1);
         nz[2 * s] = r0; nz[2 * s + 1] = r1;
     }
-    if (g == 0) { iflag[0] = have ? (int)p.flags_latch[traj] : 0; iflag[1] = 0; iflag[2] = slot; }
+    if (g == 0) iflag[0] = have ? (int)p.flags_latch[traj] : 0;
+    const double2* __restrict__ fac = p.fac + (size_t)slot * n * (BAs + 1);
+    if (TABS) {
+        for (int i = g; i < p.NP; i += G) {
+            const int li = lidx<L>(i, G);
+#pragma unroll
+            for (int k = 0; k < CS; k++) {
+                double2 v = mk2(0.0, 0.0);
+                if (have && i < n) { if (k <= BAs) v = __ldg(&fac[(size_t)i * (BAs + 1) + k]); else if (k == BAs + 1 && VAR != QC_QUARTIC) v = mk2(__ldg(&p.x[i]), 0.0); }
+                tab[li * CS + k] = v;
+            }
+        }
+    }
     traj_sync<MULTI>(bar_id, G);
 
     double sc = 1.0, xbar;
@@ -386,7 +415,6 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     // ---- substep loop ---------------------------------------------------------------------------------------
     for (int s = 0; s < p.n_sub; s++) {
         const bool active = s < my_nsub;
-        if (g == 0) iflag[1] = active ? 1 : 0;
         if (active) {
             const double r0 = nz[2 * s], r1 = nz[2 * s + 1];
             const double dW = r0 * sdt, dZ = sdt * dt * 0.5 * (r0 + r1 / sqrt(3.0));       // Q:573
@@ -574,10 +602,12 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
 #pragma unroll
             for (int j = 0; j < L; j++) U[j * G + g] = valid[j] ? mk2(acc[j].x + hw[j].x, acc[j].y + hw[j].y) : mk2(0.0, 0.0);
         }
-        __syncthreads();
-        if (tid < 32) solver_phase<VAR, L>(p, smem, tid, true);
-        __syncthreads();
-        if (active) { sc = scal[0]; xbar = scal[1]; }
+        if (active) {
+            traj_sync<MULTI>(bar_id, G);                       // psi~ complete in U
+            if (g < 32) solve_traj<VAR, L, TABS>(p, U, V, tab, fac, scal, iflag, g);
+            traj_sync<MULTI>(bar_id, G);
+            sc = scal[0]; xbar = scal[1];
+        }
     }
 
     // ---- epilogue: normalised state back to HBM, moments, reward terms, flags -------------------------------------
@@ -743,19 +773,19 @@ typedef void (*kern_t)(const StepParams);
 
 // Instantiations.  maxt = __launch_bounds__ of the instance (caps registers: 512 -> 128, 384 -> 168, 256 -> 255, 1024 -> 64
 // with spills to local memory: the "large grid" instances whose state no longer fits the register file).
-struct KernEntry { int var, L; bool multi; int maxt; kern_t fn; };
-#define QC_KE(VAR, L, MULTI, MAXT) {VAR, L, MULTI, MAXT, sse_step_kernel<VAR, L, MULTI, MAXT>}
+struct KernEntry { int var, L; bool multi; int maxt; bool tabs; kern_t fn; };
+#define QC_KE(VAR, L, MULTI, MAXT) {VAR, L, MULTI, MAXT, true, sse_step_kernel<VAR, L, MULTI, MAXT, true>}, {VAR, L, MULTI, MAXT, false, sse_step_kernel<VAR, L, MULTI, MAXT, false>}
 static const KernEntry g_kernels[] = {
-    QC_KE(QC_QUARTIC, 2, true, 512), QC_KE(QC_QUARTIC, 3, true, 512), QC_KE(QC_QUARTIC, 5, true, 384), QC_KE(QC_QUARTIC, 6, true, 384),
+    QC_KE(QC_QUARTIC, 3, true, 512), QC_KE(QC_QUARTIC, 5, true, 384), QC_KE(QC_QUARTIC, 6, true, 384),
     QC_KE(QC_QUARTIC, 6, false, 384), QC_KE(QC_QUARTIC, 9, true, 256), QC_KE(QC_QUARTIC, 5, true, 1024), QC_KE(QC_QUARTIC, 9, true, 1024),
     QC_KE(QC_HARMONIC, 1, true, 512), QC_KE(QC_HARMONIC, 2, true, 512), QC_KE(QC_HARMONIC, 3, true, 384), QC_KE(QC_HARMONIC, 3, false, 384),
-    QC_KE(QC_INV_HARMONIC, 1, true, 512), QC_KE(QC_INV_HARMONIC, 2, true, 512), QC_KE(QC_INV_HARMONIC, 3, true, 384), QC_KE(QC_INV_HARMONIC, 3, false, 384),
+    QC_KE(QC_INV_HARMONIC, 1, true, 512), QC_KE(QC_INV_HARMONIC, 2, true, 512), QC_KE(QC_INV_HARMONIC, 3, true, 384), QC_KE(QC_INV_HARMONIC, 6, false, 256),
 };
 
-static const KernEntry* find_kernel(int var, int L, bool multi, int threads_needed) {
+static const KernEntry* find_kernel(int var, int L, bool multi, int threads_needed, bool tabs) {
     const KernEntry* best = nullptr;
     for (const KernEntry& e : g_kernels)
-        if (e.var == var && e.L == L && e.multi == multi && e.maxt >= threads_needed && (!best || e.maxt < best->maxt)) best = &e;
+        if (e.var == var && e.L == L && e.multi == multi && e.tabs == tabs && e.maxt >= threads_needed && (!best || e.maxt < best->maxt)) best = &e;
     return best;
 }
 
@@ -772,6 +802,8 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
     // candidate points-per-lane, preferred first
     const int candG[] = {3, 5, 6, 9, 2}; const int candF[] = {2, 3, 1};
     const int* cand = (var == QC_QUARTIC) ? candG : candF; const int ncand = (var == QC_QUARTIC) ? 5 : 3;
+    const int forceTabs = env_int("QCART_TABS", -1);
+    const int ba = m.ba, CS = (ba == 4) ? 5 : ((ba == 1) ? 3 : 5);
     for (int c = 0; c < ncand; c++) {
         const int L = cand[c];
         if (forceL && L != forceL) continue;
@@ -779,37 +811,42 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
         if (G > 1024) continue;
         bool multi = G > 32;
         if (!multi && forceMulti == 1) multi = true;
-        const KernEntry* ke = find_kernel(var, L, multi, G);
-        if (!ke && !multi) { multi = true; ke = find_kernel(var, L, true, G); }    // bar.sync with 32 threads is fine too
-        if (!ke) continue;
-        cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, (const void*)ke->fn) != cudaSuccess) { err = std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(cudaGetLastError()); return QC_ERR_CUDA; }
-        const int NP = G * L;
-        int tstride = nbuf * NP * 16 + n_sub * 16 + 2 * QC_MAXRED * (G / 32) * 8 + 128;
-        tstride = (tstride + 15) / 16 * 16;
-        int Tmax = ke->maxt / G;
-        Tmax = std::min(Tmax, 65536 / std::max(1, fa.numRegs * G));
-        Tmax = std::min(Tmax, (smem_max - 1024) / tstride);
-        Tmax = std::min(Tmax, 15);
-        if (Tmax < 1) continue;
-        int T = forceT;
-        if (T <= 0) { const int per_sm = (B + n_sm - 1) / n_sm; T = std::max(1, std::min(per_sm, 8)); }   // small batch: one even wave
-        T = std::min(T, Tmax);
-        int P = forceP;
-        if (P <= 0) { P = 1; while (P * 2 * T <= 32 && (n + P * 2 - 1) / (P * 2) >= W_needed) P *= 2; }
-        while (P > 1 && (P * T > 32 || (n + P - 1) / P < W_needed || (P & (P - 1)))) P--;
-        plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = (n + P - 1) / P; plan.W = (P == 1) ? 0 : W_needed;
-        plan.NP = NP; plan.threads = T * G; plan.tstride = tstride; plan.smem_bytes = T * tstride; plan.multi = multi; plan.maxt = ke->maxt;
-        snprintf(plan.info, sizeof(plan.info), "sse_step_kernel<var=%d,L=%d,multi=%d,maxt=%d> T=%d G=%d P=%d chunk=%d W=%d threads=%d smem=%d regs=%d lmem=%d",
-                 var, L, (int)multi, ke->maxt, T, G, P, plan.chunk, plan.W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
-        return QC_OK;
+        for (int tabs = 1; tabs >= 0; tabs--) {
+            if (forceTabs >= 0 && tabs != forceTabs) continue;
+            const KernEntry* ke = find_kernel(var, L, multi, G, tabs != 0);
+            if (!ke && !multi) ke = find_kernel(var, L, true, G, tabs != 0);    // bar.sync with 32 threads is fine too
+            if (!ke) continue;
+            cudaFuncAttributes fa;
+            if (cudaFuncGetAttributes(&fa, (const void*)ke->fn) != cudaSuccess) { err = std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(cudaGetLastError()); return QC_ERR_CUDA; }
+            const int NP = G * L;
+            int tstride = (nbuf + (tabs ? CS : 0)) * NP * 16 + n_sub * 16 + 2 * QC_MAXRED * (G / 32) * 8 + 128;
+            tstride = (tstride + 15) / 16 * 16;
+            int Tmax = ke->maxt / G;
+            Tmax = std::min(Tmax, 65536 / std::max(1, fa.numRegs * G));
+            Tmax = std::min(Tmax, (smem_max - 1024) / tstride);
+            Tmax = std::min(Tmax, 15);
+            if (Tmax < 1) continue;
+            int T = forceT;
+            if (T <= 0) { const int per_sm = (B + n_sm - 1) / n_sm; T = std::max(1, std::min(per_sm, 8)); }   // small batch: one even wave
+            if (tabs && Tmax < std::min(T, 3) && forceTabs < 0) continue;     // tables would squeeze the CTA too much: use the global-table variant
+            T = std::min(T, Tmax);
+            int P = forceP > 0 ? std::min(forceP, 32) : 32;
+            int chunk = (n + P - 1) / P;
+            chunk = (chunk + L - 1) / L * L;
+            P = (n + chunk - 1) / chunk;
+            plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = chunk; plan.W = (P == 1) ? 0 : W_needed;
+            plan.NP = NP; plan.threads = T * G; plan.tstride = tstride; plan.smem_bytes = T * tstride; plan.multi = ke->multi; plan.maxt = ke->maxt; plan.tabs = tabs != 0;
+            snprintf(plan.info, sizeof(plan.info), "sse_step_kernel<var=%d,L=%d,multi=%d,maxt=%d,tabs=%d> T=%d G=%d P=%d chunk=%d W=%d threads=%d smem=%d regs=%d lmem=%d",
+                     var, L, (int)ke->multi, ke->maxt, tabs, T, G, P, plan.chunk, plan.W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
+            return QC_OK;
+        }
     }
     err = "no resident-kernel configuration fits this state length (n > 9216, or QCART_L override invalid)";
     return QC_ERR_UNSUPPORTED;
 }
 
 int launch_step(const LaunchPlan& plan, const StepParams& p, void* stream, std::string& err) {
-    const KernEntry* ke = find_kernel(p.variant, plan.L, plan.multi, plan.maxt);
+    const KernEntry* ke = find_kernel(p.variant, plan.L, plan.multi, plan.maxt, plan.tabs);
     if (!ke) { err = "kernel not found"; return QC_ERR_UNSUPPORTED; }
     kern_t fn = ke->fn;
     if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess) {

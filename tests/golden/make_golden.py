@@ -1,0 +1,140 @@
+#!/usr/bin/env python3
+"""Generates the committed golden fixtures under tests/golden/ (run in the authoring container, where /root/reference exists).
+
+Two kinds of vectors:
+ (A) outputs of the REFERENCE'S OWN PYTHON code, executed here:
+     * `space_def.set_global` (quartic oscillator/space_def.py:5-88) is imported as is -> grid x, Hamiltonian bands, p_hat;
+     * the pure functions of the task scripts that define the observation / reward (`cal_energy`, `Gaussian_packet`,
+       `calculate_outside_probability`, `adjust_n_max`, `get_data_xp`, `phonon_number`, ...) are extracted from main_parallel.py by
+       AST (the scripts themselves run argparse / CUDA set-up at import and cannot be imported) and executed unmodified.
+ (B) frozen outputs of the CPU oracle (oracle/sse_oracle.c) on seeded inputs (numpy PCG64), so that any later change of the oracle or
+     of the CUDA path is caught on the GPU box, where /root/reference does not exist.
+ (C) if oracle/_ref/ was built (the reference .cpp compiled against the MKL-API shim), its step()/get_moments() outputs on the same
+     seeded inputs -- the strongest pin of the oracle.
+"""
+import ast
+import warnings
+import os
+import sys
+import types
+
+import numpy as np
+from math import pi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+REF = "/root/reference/implementation codes"
+
+
+def extract_functions(path, names, namespace):
+    """Compile the named top-level (or nested-in-nothing) function definitions of a reference script into `namespace`."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tree = ast.parse(open(path).read())
+    picked = [node for node in tree.body if isinstance(node, ast.FunctionDef) and node.name in names]
+    mod = ast.Module(body=picked, type_ignores=[])
+    exec(compile(mod, path, "exec"), namespace)
+    missing = set(names) - set(n.name for n in picked)
+    assert not missing, missing
+    return namespace
+
+
+def grid_reference(task_dir, x_max, x_n, lambda_, mass, xth=None):
+    sys.path.insert(0, os.path.join(REF, task_dir))
+    for m in ("space_def",):
+        sys.modules.pop(m, None)
+    import space_def
+    g = space_def.set_global(x_max=x_max, x_n_=x_n, lambda_=lambda_, mass=mass)
+    sys.path.pop(0)
+    ns = {"np": np, "pi": pi, "sqrt": np.sqrt, "x": g["x"], "grid_size": g["grid_size"], "x_n": x_n, "linalg": __import__("scipy.linalg").linalg}
+    names = ["probability", "x_expct", "cal_energy", "Gaussian_packet", "p_expct"]
+    ns["p_hat"] = g["p_hat"]
+    if xth is not None:
+        names.append("calculate_outside_probability")
+    extract_functions(os.path.join(REF, task_dir, "main_parallel.py"), names, ns)
+    return g, ns
+
+
+def make_grid_fixture(name, task_dir, params):
+    n = 2 * int(params["x_max"] / params["grid_size"] + 0.5) + 1
+    g, ns = grid_reference(task_dir, params["x_max"], n, params["lambda_"], params["mass"], params.get("x_threshold"))
+    H = g["quartic_Hamil"].toarray()
+    rng = np.random.default_rng(11)
+    states, energies, xs, ps, outs = [], [], [], [], []
+    for b in range(4):
+        k = rng.uniform(-0.3, 0.3)
+        mean = rng.uniform(-2, 2)
+        psi = ns["Gaussian_packet"](wavelength=(float("inf") if b == 0 else 1. / k), mean=(0. if b == 0 else mean), std=1.)
+        states.append(psi)
+        energies.append(ns["cal_energy"](psi, g["Hamil"]))
+        xs.append(ns["x_expct"](psi))
+        ps.append(ns["p_expct"](psi))
+        if params.get("x_threshold"):
+            outs.append(ns["calculate_outside_probability"](psi, params["x_threshold"]))
+    np.savez_compressed(os.path.join(HERE, name), x=g["x"], grid_size=g["grid_size"],
+                        H_bands=np.stack([np.concatenate([np.diag(H, k), np.zeros(k)]) for k in range(5)]),
+                        p_hat_dense_untruncated=g["p_hat"].toarray(), states=np.array(states), energy=np.array(energies),
+                        x_mean=np.array(xs), p_mean_untruncated=np.array(ps), outside=np.array(outs))
+    print("wrote", name)
+
+
+def make_fock_fixture():
+    from common import initial_states
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200 import configs
+    out = {}
+    for task, task_dir in (("harmonic", "harmonic oscillator"), ("inverted_harmonic", "inverted harmonic oscillator")):
+        params = configs.PRESETS[task]()
+        from scipy.sparse import csr_matrix
+        from math import sqrt, factorial
+        ns = {"np": np, "csr": csr_matrix, "sqrt": sqrt, "factorial": factorial, "pi": pi, "omega": params["omega"], "n_max": params["n_max"],
+              "__name__": "reference_fragment", "linalg": __import__("scipy.linalg").linalg}
+        names = ["probability", "adjust_n_max", "x_expct", "p_expct", "expct", "get_data_xp"] + (["phonon_number"] if task == "harmonic" else [])
+        extract_functions(os.path.join(REF, task_dir, "main_parallel.py"), names, ns)
+        ns["adjust_n_max"](params["n_max"])
+        psi = initial_states(params, 6, seed=21)
+        rng = np.random.default_rng(5)
+        psi = psi + 1e-3 * (rng.standard_normal(psi.shape) + 1j * rng.standard_normal(psi.shape)) * np.exp(-np.arange(psi.shape[1]) / 8.0)
+        psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+        out[task + "_states"] = psi
+        out[task + "_obs_float32"] = np.array([ns["get_data_xp"](s) for s in psi])
+        if task == "harmonic":
+            out[task + "_phonon"] = np.array([ns["phonon_number"](s) for s in psi])
+        out[task + "_x"] = np.array([ns["x_expct"](s) for s in psi])
+    np.savez_compressed(os.path.join(HERE, "fock_reference_python.npz"), **out)
+    print("wrote fock_reference_python.npz")
+
+
+def make_oracle_fixture():
+    from common import TASKS, oracle_for, initial_states, oracle_control_step, level_force
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200 import configs
+    out = {}
+    for task in TASKS:
+        params = configs.PRESETS[task]()
+        B = 3
+        rng = np.random.Generator(np.random.PCG64(2024))
+        psi0 = initial_states(params, B, seed=4)
+        actions = np.array([0, 10, 17], np.int32)
+        noise = rng.standard_normal((B, params["n_sub"], 2))
+        orc = oracle_for(params)
+        ref, fails, qs = oracle_control_step(orc, params, psi0, actions, noise, want_q=True)
+        out[task + "_psi0"] = psi0
+        out[task + "_actions"] = actions
+        out[task + "_noise"] = noise
+        out[task + "_psi1"] = ref
+        out[task + "_fail"] = fails
+        out[task + "_q"] = np.array([q for q, _ in qs])
+        out[task + "_xmean"] = np.array([xm for _, xm in qs])
+        if "quartic" in task:
+            out[task + "_moments"] = np.array([orc.get_moments(ref[b]) for b in range(B)])
+    np.savez_compressed(os.path.join(HERE, "oracle_control_step.npz"), **out)
+    print("wrote oracle_control_step.npz")
+
+
+if __name__ == "__main__":
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200 import configs
+    make_grid_fixture("grid_reference_python_quartic.npz", "quartic oscillator", configs.quartic())
+    make_grid_fixture("grid_reference_python_inverted_quartic.npz", "inverted quartic oscillator", configs.inverted_quartic())
+    make_fock_fixture()
+    make_oracle_fixture()
