@@ -132,9 +132,48 @@ def make_oracle_fixture():
     print("wrote oracle_control_step.npz")
 
 
+def make_reference_build_fixture():
+    """(C) the reference's own simulation*.cpp (compiled against oracle/mkl_shim by oracle/build_ref.sh): one full control step per task."""
+    from common import TASKS, initial_states, level_force
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200 import configs
+    from oracle.ref_module import RefModule, available
+    out = {}
+    for task in TASKS:
+        if not available(task):
+            print("oracle/_ref/%s missing: run oracle/build_ref.sh first" % task)
+            return
+        params = configs.PRESETS[task]()
+        ref = RefModule(task)
+        B = 2
+        rng = np.random.Generator(np.random.PCG64(777))
+        psi0 = initial_states(params, B, seed=31)
+        actions = np.array([4, 18], np.int32)
+        noise = rng.standard_normal((B, params["n_sub"], 2))
+        psi1 = psi0.copy()
+        q = np.zeros((B, params["n_sub"])); xm = np.zeros((B, params["n_sub"])); fail = np.zeros(B, np.int32)
+        for b in range(B):
+            st = psi1[b].copy()
+            for s in range(params["n_sub"]):         # the reference's call pattern: one Python->C call per substep (Q/main_parallel.py:226)
+                q[b, s], xm[b, s], f = ref.step(st, params["dt"], level_force(params, int(actions[b])), params["gamma"], noise[b, s])
+                fail[b] |= f
+            psi1[b] = st
+        out[task + "_psi0"], out[task + "_actions"], out[task + "_noise"] = psi0, actions, noise
+        out[task + "_psi1"], out[task + "_q"], out[task + "_xmean"], out[task + "_fail"] = psi1, q, xm, fail
+        out[task + "_xexp"] = np.array([ref.x_expectation(np.ascontiguousarray(psi1[b])) for b in range(B)])
+        out[task + "_settings"] = np.array(ref.check_settings(), dtype=np.float64)
+        if "quartic" in task:
+            mom = np.zeros((B, 20))
+            for b in range(B):
+                ref.get_moments(np.ascontiguousarray(psi1[b]), mom[b])
+            out[task + "_moments"] = mom
+    np.savez_compressed(os.path.join(HERE, "reference_build_control_step.npz"), **out)
+    print("wrote reference_build_control_step.npz")
+
+
 if __name__ == "__main__":
     from deepreinforcementlearningcontrolofquantumcartpoles_b200 import configs
     make_grid_fixture("grid_reference_python_quartic.npz", "quartic oscillator", configs.quartic())
     make_grid_fixture("grid_reference_python_inverted_quartic.npz", "inverted quartic oscillator", configs.inverted_quartic())
     make_fock_fixture()
     make_oracle_fixture()
+    make_reference_build_fixture()

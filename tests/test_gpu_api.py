@@ -1,0 +1,176 @@
+"""GPU tests of the boundary: the `simulation`-module mirror (reference signatures and error behaviour), host-buffer entry point,
+flags, and the env API."""
+import numpy as np
+import pytest
+from math import pi
+
+from common import oracle_for, initial_states, level_force
+from deepreinforcementlearningcontrolofquantumcartpoles_b200 import configs, BatchedSim, QuantumCartpoleEnv, simulation, _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def test_simulation_module_mirror_quartic():
+    params = configs.quartic()
+    simulation.configure(params)
+    assert simulation.check_settings() == (171, 0.1, params["lambda_"], params["mass"], 5)       # Q:652-654
+    orc = oracle_for(params)
+    psi = initial_states(params, 1, 4)[0]
+    ref = psi.copy()
+    rng = np.random.default_rng(2)
+    for F in (0.0, 2.5, 2.5, -5.0, 0.37):
+        r = rng.standard_normal(2)
+        q, xm, fail = simulation.step(psi, params["dt"], F, params["gamma"], normals=r)           # in place, like the reference
+        q2, xm2, fail2 = orc.step(ref, params["dt"], F, params["gamma"], r)
+        assert np.linalg.norm(psi - ref) / np.linalg.norm(ref) < 1e-10
+        assert abs(q - q2) < 1e-10 * max(1, abs(q2)) and abs(xm - xm2) < 1e-10 and fail == fail2
+    out = np.empty(20)
+    assert simulation.get_moments(psi, out) is None
+    mref = orc.get_moments(ref)
+    assert np.max(np.abs(out - mref) / np.maximum(np.abs(mref), 1e-3)) < 1e-9
+    assert abs(simulation.x_expectation(psi) - orc.x_expectation(ref)) < 1e-10
+    # simulate_10_steps (Q:526-558)
+    r10 = rng.standard_normal((10, 2))
+    q, xm, fail = simulation.simulate_10_steps(psi, params["dt"], 1.5, params["gamma"], normals=r10)
+    f2, qs, xms = orc.run(ref, params["dt"], 1.5, params["gamma"], r10, want_q=True)
+    assert np.linalg.norm(psi - ref) / np.linalg.norm(ref) < 1e-10 and abs(q - qs[-1]) < 1e-9 * max(1, abs(qs[-1])) and abs(xm - xms[-1]) < 1e-10
+    # seeded internal stream is reproducible
+    a, b = initial_states(params, 1, 4)[0], initial_states(params, 1, 4)[0]
+    simulation.set_seed(99); simulation.step(a, params["dt"], 0.0, params["gamma"])
+    simulation.set_seed(99); simulation.step(b, params["dt"], 0.0, params["gamma"])
+    assert np.array_equal(a, b)
+
+
+def test_simulation_module_error_behaviour():
+    """check_type / check_moment_data_array of the reference (Q:288-323): TypeError for non-arrays, ValueError for shape/dtype."""
+    params = configs.quartic()
+    simulation.configure(params)
+    good = initial_states(params, 1, 0)[0]
+    with pytest.raises(TypeError):
+        simulation.step([0j] * 171, params["dt"], 0.0, params["gamma"])
+    with pytest.raises(ValueError, match="one-dimensional"):
+        simulation.step(np.zeros((1, 171), np.complex128), params["dt"], 0.0, params["gamma"])
+    with pytest.raises(ValueError, match="required size 171"):
+        simulation.step(np.zeros(170, np.complex128), params["dt"], 0.0, params["gamma"])
+    with pytest.raises(ValueError, match="Complex128"):
+        simulation.step(np.zeros(171, np.float64), params["dt"], 0.0, params["gamma"])
+    with pytest.raises(ValueError, match="required size 20"):
+        simulation.get_moments(good, np.empty(19))
+    with pytest.raises(ValueError, match="Float64"):
+        simulation.get_moments(good, np.empty(20, np.float32))
+    with pytest.raises(TypeError):
+        simulation.step(good, "dt", 0.0, params["gamma"])
+
+
+def test_simulation_module_mirror_fock():
+    for task in ("harmonic", "inverted_harmonic"):
+        params = configs.PRESETS[task]()
+        simulation.configure(params)
+        assert simulation.check_settings() == (params["n_max"], params["omega"])                 # H:562-564
+        orc = oracle_for(params)
+        psi = initial_states(params, 1, 3)[0]
+        ref = psi.copy()
+        rng = np.random.default_rng(5)
+        for F in (0.0, 4.0, -2.5):
+            r = rng.standard_normal(2)
+            q, xm, fail = simulation.step(psi, params["dt"], F, params["gamma"], normals=r)
+            q2, xm2, fail2 = orc.step(ref, params["dt"], F, params["gamma"], r)
+            assert np.linalg.norm(psi - ref) / np.linalg.norm(ref) < 1e-10 and abs(xm - xm2) < 1e-10 and fail == fail2
+        assert abs(simulation.x_expectation(psi) - orc.x_expectation(ref)) < 1e-10
+
+
+def test_host_buffer_entry_point_equals_device_entry_point():
+    torch = _torch()
+    params = configs.quartic(n_sub=8)
+    B = 64
+    psi0 = initial_states(params, B, 1)
+    act = np.random.default_rng(0).integers(0, 21, B).astype(np.int32)
+    a = BatchedSim(params, batch=B, seed=3); a.set_state(psi0)
+    b = BatchedSim(params, batch=B, seed=3); b.set_state(psi0)
+    out = a.step(torch.as_tensor(act, device="cuda"))
+    mom, aux, flags = b.step_host(act)
+    assert np.array_equal(out["moments"].cpu().numpy(), mom) and np.array_equal(out["aux"].cpu().numpy(), aux)
+    assert np.array_equal(out["flags"].cpu().numpy(), flags)
+    assert np.array_equal(a.get_state(), b.get_state())
+
+
+def test_fail_and_escape_flags():
+    torch = _torch()
+    # numerical Fail: amplitude at the grid boundary (Q:559-565); oracle decides
+    params = configs.quartic(n_sub=4)
+    orc = oracle_for(params)
+    x = orc.x_array()
+    psi = np.exp(-(x - 7.9) ** 2 / 0.5).astype(np.complex128)
+    psi /= np.sqrt(np.sum(np.abs(psi) ** 2) * params["grid_size"])
+    ok = initial_states(params, 1, 0)[0]
+    batch = np.stack([psi, ok])
+    noise = np.zeros((2, 4, 2))
+    sim = BatchedSim(params, batch=2); sim.set_state(batch)
+    out = sim.step(torch.as_tensor(np.array([10, 10], np.int32), device="cuda"), noise=torch.as_tensor(noise, device="cuda"))
+    st = psi.copy(); f_ref, _, _ = orc.run(st, params["dt"], 0.0, params["gamma"], noise[0])
+    flags = out["flags"].cpu().numpy()
+    assert f_ref == 1 and (flags[0] & L.QC_FLAG_FAIL) and not (flags[1] & L.QC_FLAG_FAIL)
+    # latched until cleared
+    out = sim.step(torch.as_tensor(np.array([10, 10], np.int32), device="cuda"), noise=torch.as_tensor(noise, device="cuda"))
+    assert out["flags"].cpu().numpy()[0] & L.QC_FLAG_FAIL
+    # escape: inverted quartic, packet far outside |x| < x_th = 5 (IQ/main_parallel.py:78-81,199-200)
+    p2 = configs.inverted_quartic(n_sub=2)
+    sim2 = BatchedSim(p2, batch=2)
+    sim2.init_packets(mean=np.array([0.0, 7.0]))
+    out2 = sim2.step(torch.zeros(2, dtype=torch.int32, device="cuda") + 10)
+    f2 = out2["flags"].cpu().numpy()
+    aux2 = out2["aux"].cpu().numpy()
+    assert not (f2[0] & L.QC_FLAG_ESCAPED) and (f2[1] & L.QC_FLAG_ESCAPED)
+    assert aux2[0, L.QC_AUX_OUTSIDE] < 0.01 and aux2[1, L.QC_AUX_OUTSIDE] > 0.9
+
+
+def test_initial_state_builders_match_reference_formulas():
+    params = configs.quartic()
+    sim = BatchedSim(params, batch=3)
+    k = np.array([0.0, 0.2, -0.3]); mean = np.array([0.0, 1.0, -0.5])
+    sim.init_packets(wavenumber=k, mean=mean, std=1.0)
+    got = sim.get_state()
+    x = sim.x_grid()
+    for b in range(3):       # Gaussian_packet, Q/main_parallel.py:75-76 with wavelength = 1/k
+        ref = np.exp(2j * pi * (x - mean[b]) * k[b]) * np.exp(-(x - mean[b]) ** 2 / 4) / np.sqrt(np.sqrt(2 * pi))
+        assert np.max(np.abs(got[b] - ref)) < 1e-14
+    f = BatchedSim(configs.harmonic(), batch=2)
+    f.init_fock(None)
+    s = f.get_state()
+    assert np.all(s[:, 0] == 1.0) and np.all(s[:, 1:] == 0)
+
+
+@pytest.mark.parametrize("task", ["quartic", "inverted_quartic", "harmonic", "inverted_harmonic"])
+def test_env_reset_step_protocol(task):
+    torch = _torch()
+    kw = {"batch": 16, "seed": 1}
+    env = QuantumCartpoleEnv(task, **kw)
+    if task == "quartic":
+        # shorten the 15-20 time-unit warm-up for the test by monkeypatching the rng range is not needed: 16 trajectories, ~28 launches
+        pass
+    obs = env.reset()
+    assert obs.shape == (16, env.observation_size()) and obs.dtype == torch.float32 and torch.isfinite(obs).all()
+    zero = torch.full((16,), env.zero_action, dtype=torch.int64, device=env.dev)
+    for _ in range(3):
+        obs, reward, done, info = env.step(zero)
+    assert reward.shape == (16,) and done.shape == (16,) and done.dtype == torch.bool
+    if task == "quartic":
+        assert torch.all(info["energy"] < 7.6 + 5) and torch.allclose(reward.double(), -info["energy"], atol=1e-5)
+        assert abs(float(env.t[0]) - 3 * 80 / 1440) < 1e-9
+    if task == "harmonic":
+        assert torch.allclose(reward.double(), -10 * info["energy"], atol=1e-4)
+    if task in ("inverted_quartic", "inverted_harmonic"):
+        assert set(reward.cpu().numpy().tolist()) <= {1.0, -1.0}
+    # pushing hard in one direction eventually terminates the inverted tasks
+    if task == "inverted_quartic":
+        push = torch.full((16,), 20, dtype=torch.int64, device=env.dev)
+        for _ in range(40):
+            obs, reward, done, info = env.step(push)
+            if bool(done.all()):
+                break
+        assert bool(done.all()) and float(reward.max()) == -1.0

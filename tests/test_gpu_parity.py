@@ -75,3 +75,210 @@ def test_q_and_xmean_streams(task):
     for b in range(B):
         assert np.max(np.abs(xm[b] - qs[b][1])) < 1e-10
         assert np.max(np.abs(q[b] - qs[b][0]) / np.maximum(1.0, np.abs(qs[b][0]))) < 1e-10
+
+
+@pytest.mark.parametrize("task", ["quartic", "inverted_harmonic"])
+def test_many_trajectories_per_cta(task):
+    """Batch large enough that the planner packs several trajectories per CTA (T > 1) and several CTAs per SM."""
+    B = 1500 if task == "quartic" else 1300
+    params, sim, out, psi_gpu, orc, psi_ref, fails, _ = run_case(task, B, n_sub=12)
+    assert " T=1 " not in sim.kernel_info()
+    assert rel_err(psi_gpu, psi_ref) < TOL_STEP
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_frozen_golden_vectors_through_the_abi(task):
+    """tests/golden/oracle_control_step.npz (committed): same psi0 / actions / noise through the CUDA path."""
+    import os
+    torch = _torch()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_control_step.npz"))
+    params = configs.PRESETS[task]()
+    sim = BatchedSim(params, batch=3)
+    sim.set_state(g[task + "_psi0"])
+    out = sim.step(torch.as_tensor(g[task + "_actions"], device="cuda"), noise=torch.as_tensor(g[task + "_noise"], device="cuda"), want_q=True)
+    torch.cuda.synchronize()
+    assert rel_err(sim.get_state(), g[task + "_psi1"]) < TOL_STEP
+    assert np.array_equal((out["flags"].cpu().numpy() & L.QC_FLAG_FAIL) != 0, g[task + "_fail"] != 0)
+    q = out["q"].cpu().numpy()
+    assert np.max(np.abs(q - g[task + "_q"]) / np.maximum(1, np.abs(g[task + "_q"]))) < 1e-10
+    if "quartic" in task:
+        m = out["moments"].cpu().numpy()
+        assert np.max(np.abs(m - g[task + "_moments"]) / np.maximum(np.abs(g[task + "_moments"]), 1e-3)) < TOL_STEP
+
+
+@pytest.mark.parametrize("task", ["quartic", "harmonic"])
+def test_in_kernel_philox_noise(task):
+    """noise = NULL: the kernel draws (r0, r1) from Philox4x32-10 keyed by (seed, global trajectory id, substep counter);
+    feeding the host restatement of the same stream to the oracle must reproduce the trajectory."""
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200 import philox_normals
+    torch = _torch()
+    params = configs.PRESETS[task](n_sub=10)
+    B, seed, off = 6, 1234, 1000
+    psi0 = initial_states(params, B, 3)
+    sim = BatchedSim(params, batch=B, seed=seed, traj_offset=off)
+    sim.set_state(psi0)
+    actions = np.array([0, 5, 10, 15, 20, 7], np.int32)
+    act = torch.as_tensor(actions, device="cuda")
+    orc = oracle_for(params)
+    ref = psi0
+    for cstep in range(2):          # the substep counter continues across control steps
+        sim.step(act)
+        noise = np.array([[philox_normals(seed, off + b, cstep * 10 + s) for s in range(10)] for b in range(B)])
+        ref, _, _ = oracle_control_step(orc, params, ref, actions, noise)
+    torch.cuda.synchronize()
+    assert rel_err(sim.get_state(), ref) < TOL_STEP
+
+
+def test_result_is_independent_of_sharding():
+    """Philox is keyed by the GLOBAL trajectory id: one handle with 12 trajectories == two handles with 6 (traj_offset 0 and 6)."""
+    torch = _torch()
+    params = configs.quartic(n_sub=8)
+    psi0 = initial_states(params, 12, 9)
+    act = np.arange(12, dtype=np.int32)
+    full = BatchedSim(params, batch=12, seed=5)
+    full.set_state(psi0)
+    full.step(torch.as_tensor(act, device="cuda"))
+    parts = []
+    for r in range(2):
+        s = BatchedSim(params, batch=6, seed=5, traj_offset=6 * r)
+        s.set_state(psi0[6 * r: 6 * r + 6])
+        s.step(torch.as_tensor(act[6 * r: 6 * r + 6], device="cuda"))
+        parts.append(s.get_state())
+    assert np.array_equal(full.get_state(), np.concatenate(parts))
+
+
+def test_per_trajectory_substep_budget():
+    torch = _torch()
+    params = configs.quartic(n_sub=12)
+    B = 5
+    psi0 = initial_states(params, B, 2)
+    rng = np.random.default_rng(0)
+    noise = rng.standard_normal((B, 12, 2))
+    budget = np.array([12, 0, 5, 1, 9], np.int32)
+    actions = np.full(B, 13, np.int32)
+    sim = BatchedSim(params, batch=B)
+    sim.set_state(psi0)
+    sim.step(torch.as_tensor(actions, device="cuda"), noise=torch.as_tensor(noise, device="cuda"), nsub_traj=torch.as_tensor(budget, device="cuda"))
+    got = sim.get_state()
+    orc = oracle_for(params)
+    for b in range(B):
+        st = psi0[b].copy()
+        if budget[b]:
+            orc.run(st, params["dt"], level_force(params, 13), params["gamma"], noise[b, :budget[b]])
+        assert np.linalg.norm(got[b] - st) / np.linalg.norm(st) < TOL_STEP
+
+
+def test_arbitrary_force_values():
+    torch = _torch()
+    params = configs.quartic(n_sub=6)
+    B = 4
+    psi0 = initial_states(params, B, 2)
+    noise = np.random.default_rng(1).standard_normal((B, 6, 2))
+    forces = np.array([0.123, -4.9, 2.5, 0.123])
+    sim = BatchedSim(params, batch=B)
+    sim.set_state(psi0)
+    sim.step_forces(forces, noise=torch.as_tensor(noise, device="cuda"))
+    got = sim.get_state()
+    orc = oracle_for(params)
+    for b in range(B):
+        st = psi0[b].copy()
+        orc.run(st, params["dt"], float(forces[b]), params["gamma"], noise[b])
+        assert np.linalg.norm(got[b] - st) / np.linalg.norm(st) < TOL_STEP
+
+
+@pytest.mark.parametrize("npts,env", [(257, {}), (513, {}), (1025, {}), (2049, {}), (4097, {})])
+def test_grid_size_sweep(npts, env):
+    """BASELINE.json config 5: x_max 13, N points, dt ~ h^2; tolerance check vs the oracle at every N the resident kernel supports."""
+    torch = _torch()
+    params = configs.quartic_sweep(npts, n_sub=3)
+    B = 2
+    psi0 = initial_states(params, B, 1)
+    noise = np.random.default_rng(4).standard_normal((B, 3, 2))
+    actions = np.array([2, 19], np.int32)
+    sim = BatchedSim(params, batch=B)
+    assert sim.n == npts
+    sim.set_state(psi0)
+    out = sim.step(torch.as_tensor(actions, device="cuda"), noise=torch.as_tensor(noise, device="cuda"))
+    torch.cuda.synchronize()
+    orc = oracle_for(params)
+    ref, fails, _ = oracle_control_step(orc, params, psi0, actions, noise)
+    print(npts, sim.kernel_info())
+    assert rel_err(sim.get_state(), ref) < TOL_STEP
+    m = out["moments"].cpu().numpy()
+    mref = np.array([orc.get_moments(ref[b]) for b in range(B)])
+    assert np.max(np.abs(m[:, :5] - mref[:, :5]) / np.maximum(np.abs(mref[:, :5]), 1e-3)) < 1e-9
+
+
+def test_long_run_stays_within_episode_tolerance():
+    """North-star: <= 1e-6 after a full episode with identical noise.  Harmonic: the full 1800 control steps of an episode
+    (t_max = 100); quartic: 250 control steps (20 000 substeps)."""
+    torch = _torch()
+    for task, n_ctrl in (("harmonic", 1800), ("quartic", 250)):
+        params = configs.PRESETS[task]()
+        B = 2
+        rng = np.random.default_rng(12)
+        psi0 = initial_states(params, B, 5)
+        sim = BatchedSim(params, batch=B)
+        sim.set_state(psi0)
+        orc = oracle_for(params)
+        ref = psi0
+        for c in range(n_ctrl):
+            actions = rng.integers(6, 15, B).astype(np.int32)
+            noise = rng.standard_normal((B, params["n_sub"], 2))
+            sim.step(torch.as_tensor(actions, device="cuda"), noise=torch.as_tensor(noise, device="cuda"))
+            ref, _, _ = oracle_control_step(orc, params, ref, actions, noise)
+        err = rel_err(sim.get_state(), ref)
+        print(task, n_ctrl, "control steps: rel err", err)
+        assert err < 1e-6
+
+
+def test_full_size_properties_config2():
+    """BASELINE configs[1] at full size (1024 trajectories): normalisation, determinism, flags clear, and a random subset against
+    the oracle."""
+    torch = _torch()
+    params = configs.quartic()
+    B = 1024
+    psi0 = np.tile(initial_states(params, 128, 7), (8, 1))
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    act = torch.randint(0, 21, (B,), device="cuda", dtype=torch.int32, generator=g)
+    runs = []
+    for rep in range(2):
+        sim = BatchedSim(params, batch=B, seed=77)
+        sim.set_state(psi0)
+        out = sim.step(act)
+        torch.cuda.synchronize()
+        runs.append((sim.get_state(), out["moments"].cpu().numpy(), out["aux"].cpu().numpy(), out["flags"].cpu().numpy()))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])       # bitwise deterministic
+    psi, mom, aux, flags = runs[0]
+    assert np.max(np.abs(np.sum(np.abs(psi) ** 2, axis=1) * params["grid_size"] - 1)) < 1e-12
+    assert np.all(flags == 0) and np.all(np.isfinite(mom))
+    assert np.max(np.abs(mom[:, 0] - aux[:, L.QC_AUX_XMEAN])) < 1e-12
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200 import philox_normals
+    orc = oracle_for(params)
+    a = act.cpu().numpy()
+    for b in (0, 511, 1023):
+        noise = np.array([philox_normals(77, b, s) for s in range(params["n_sub"])])
+        st = psi0[b].copy()
+        orc.run(st, params["dt"], level_force(params, int(a[b])), params["gamma"], noise)
+        assert np.linalg.norm(psi[b] - st) / np.linalg.norm(st) < TOL_STEP
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_reference_build_fixture_through_the_abi(task):
+    """tests/golden/reference_build_control_step.npz: outputs of the REFERENCE'S OWN C++ (compiled against the MKL-API shim) for one
+    full control step; the CUDA path must reproduce them within the north-star tolerance (1e-10 relative per control step)."""
+    import os
+    torch = _torch()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_build_control_step.npz"))
+    params = configs.PRESETS[task]()
+    sim = BatchedSim(params, batch=g[task + "_psi0"].shape[0])
+    sim.set_state(g[task + "_psi0"])
+    out = sim.step(torch.as_tensor(g[task + "_actions"], device="cuda"), noise=torch.as_tensor(g[task + "_noise"], device="cuda"), want_q=True)
+    torch.cuda.synchronize()
+    assert rel_err(sim.get_state(), g[task + "_psi1"]) < TOL_STEP
+    assert np.array_equal((out["flags"].cpu().numpy() & L.QC_FLAG_FAIL) != 0, g[task + "_fail"] != 0)
+    assert np.max(np.abs(out["x_mean"].cpu().numpy() - g[task + "_xmean"])) < 1e-10
+    assert np.max(np.abs(out["q"].cpu().numpy() - g[task + "_q"]) / np.maximum(1, np.abs(g[task + "_q"]))) < 1e-10
+    if "quartic" in task:
+        m = out["moments"].cpu().numpy()
+        assert np.max(np.abs(m - g[task + "_moments"]) / np.maximum(np.abs(g[task + "_moments"]), 1e-3)) < TOL_STEP
