@@ -78,8 +78,8 @@ struct StepParams {
 };
 
 struct LaunchPlan {
-    int L, T, G, P, chunk, W, NP, threads, smem_bytes, tstride, maxt;
-    bool multi, tabs;
+    int L, T, G, P, chunk, W, NP, threads, smem_bytes, tstride, maxt, gc;
+    bool tabs;
     char info[224];
 };
 

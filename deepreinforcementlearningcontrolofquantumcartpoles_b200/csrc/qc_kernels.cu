@@ -1,78 +1,8 @@
-// Device code of libqcart: the persistent fused SSE control-step kernel for sm_100a.
-//
-// One launch advances every trajectory of the batch by one control step = n_sub substeps of the
-// order-1.5 strong scheme of the reference's go_one_step (Q:569-644; H:413-554; I:432-572), with the
-// implicit banded solve, renormalisation, Fail / escape latches and the moment extraction fused in.
-// (Q = quartic oscillator/simulation_quart.cpp, H = harmonic oscillator/simulation.cpp,
-//  I = inverted harmonic oscillator/simulation_i.cpp under /root/reference/implementation codes/.)
-//
-// Mapping:
-//   * a trajectory is owned by G lanes (G = 32*warps); lane g keeps points [g*L, g*L+L) of every live vector
-//     in REGISTERS for the whole control step; the wavefunction crosses HBM only at kernel entry/exit;
-//   * band operators (9-point kinetic stencil / ladder operators) read their halos from a j-major shared-memory
-//     line ( point i -> [(i % L) * G + i / L] ), bank-conflict free for every L, one barrier per sweep;
-//   * all linear terms of the scheme are merged into ONE Horner chain in H0 = H - kappa F x (5 sweeps):
-//       psi~ = acc + H0 ( v1 + H0 ( c2 a + H0 ( c3 a + H0 ( c4 a + H0 c5 a ) ) ) )
-//     which equals  k(aIm(Y+) - aIm(Y-)) + 2 k2 aIm(psi) + C a  of simple_sum_up because aIm is linear;
-//   * the implicit solve (I + i dt/2 H0) psi' = psi~ is the one serial recurrence: it is done by P "solver" lanes
-//     per trajectory, all T*P of them in warp 0, one lane per contiguous chunk, with the pivot-free L D L^T factors
-//     precomputed per force level.  A lane starts its substitution W points early with zero history: L^{-1} decays
-//     below 1e-18 within W points (measured at create time), so the result equals the sequential solve to round-off;
-//   * norm, <x>, boundary norms and the escape probability are accumulated by the solver lanes in the backward
-//     sweep; the only other reduction per substep is one warp-shuffle butterfly (deterministic, fixed shape).
-#include "qc_internal.h"
-#include <cuda_runtime.h>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <algorithm>
+// Launch plumbing, initial-state kernels and the roofline micro-benchmarks of libqcart.
+#include "qc_kernel_impl.cuh"
 
 namespace qc {
 
-#define QC_MAXRED 24
-
-// ------------------------------------------------------------------------------------------------------
-// small device helpers
-
-__device__ __forceinline__ double2 mk2(double a, double b) { double2 r; r.x = a; r.y = b; return r; }
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-template <bool MULTI>
-__device__ __forceinline__ void traj_sync(int bar_id, int nthreads) {
-    if constexpr (MULTI) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
-    else __syncwarp();
-}
-
-// Philox4x32-10 (Salmon et al.), counter = (traj_lo, traj_hi, step_lo, step_hi), key = (seed_lo, seed_hi)
-__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-    for (int r = 0; r < 10; r++) {
-        if (r > 0) { k0 += W0; k1 += W1; }
-        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
-        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-__host__ __device__ inline void philox_uniforms(uint64_t seed, uint64_t traj, uint64_t step, double* u1, double* u2) {
-    uint32_t o[4];
-    philox4x32_10((uint32_t)traj, (uint32_t)(traj >> 32), (uint32_t)step, (uint32_t)(step >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o);
-    const uint64_t a = ((uint64_t)o[1] << 32) | o[0], b = ((uint64_t)o[3] << 32) | o[2];
-    *u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-    *u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-}
-__device__ inline void philox_normals_dev(uint64_t seed, uint64_t traj, uint64_t step, double* r0, double* r1) {
-    double u1, u2; philox_uniforms(seed, traj, step, &u1, &u2);
-    const double rad = sqrt(-2.0 * log(u1));
-    double s, c; sincospi(2.0 * u2, &s, &c);
-    *r0 = rad * c; *r1 = rad * s;
-}
 void philox_normals_host(uint64_t seed, uint64_t traj, uint64_t step, double* out2) {
     double u1, u2; philox_uniforms(seed, traj, step, &u1, &u2);
     const double rad = std::sqrt(-2.0 * std::log(u1));
@@ -80,712 +10,33 @@ void philox_normals_host(uint64_t seed, uint64_t traj, uint64_t step, double* ou
     out2[1] = rad * std::sin(2.0 * 3.14159265358979323846 * u2);
 }
 
-// j-major line index of point i
-template <int L> __device__ __forceinline__ int lidx(int i, int G) { return (i % L) * G + i / L; }
+const KernEntry* qc_entries_grid_fast(int* count);
+const KernEntry* qc_entries_grid_fast2(int* count);
+const KernEntry* qc_entries_grid_gen(int* count);
+const KernEntry* qc_entries_grid_gen2(int* count);
+const KernEntry* qc_entries_grid_big(int* count);
+const KernEntry* qc_entries_fock_h(int* count);
+const KernEntry* qc_entries_fock_ih(int* count);
+const KernEntry* qc_entries_fock_ih2(int* count);
 
-// Load the value of relative point r (compile-time after unrolling; r in [-HB, L+HB)) of lane g from a line buffer.
-template <int L> __device__ __forceinline__ double2 ld_rel(const double2* __restrict__ buf, int g, int G, int r) {
-    if (r >= 0 && r < L) return buf[r * G + g];
-    if (r < 0) {
-        const int q = (-r + L - 1) / L, rr = q * L + r;
-        return (g - q >= 0) ? buf[rr * G + (g - q)] : mk2(0.0, 0.0);
-    }
-    const int q = r / L, rr = r - q * L;
-    return (g + q < G) ? buf[rr * G + (g + q)] : mk2(0.0, 0.0);
+static std::vector<KernEntry> all_kernels() {
+    std::vector<KernEntry> v;
+    typedef const KernEntry* (*getter)(int*);
+    const getter gs[] = {qc_entries_grid_fast, qc_entries_grid_fast2, qc_entries_grid_gen, qc_entries_grid_gen2, qc_entries_grid_big, qc_entries_fock_h, qc_entries_fock_ih, qc_entries_fock_ih2};
+    for (getter gfn : gs) { int c = 0; const KernEntry* e = gfn(&c); v.insert(v.end(), e, e + c); }
+    return v;
 }
 
-// ------------------------------------------------------------------------------------------------------
-// reductions over the lanes of one trajectory: warp butterfly, then (MULTI) fixed-order sum of per-warp partials
-template <int NV, bool MULTI>
-__device__ __forceinline__ void traj_reduce(double (&v)[NV], double* red, int& red_phase, int wq, int nwarps, int lane, int bar_id, int G) {
-#pragma unroll
-    for (int k = 0; k < NV; k++) v[k] = warp_sum(v[k]);
-    if constexpr (MULTI) {
-        double* rb = red + red_phase * (QC_MAXRED * nwarps);
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < NV; k++) rb[wq * QC_MAXRED + k] = v[k];
-        }
-        traj_sync<true>(bar_id, G);
-#pragma unroll
-        for (int k = 0; k < NV; k++) {
-            double s = 0.0;
-            for (int q = 0; q < nwarps; q++) s += rb[q * QC_MAXRED + k];
-            v[k] = s;
-        }
-        red_phase ^= 1;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// H0 application on the L own points of a lane.  `ext` holds the vector on relative points [-HB, L+HB) (index r+HB).
-template <int VAR> struct VarTraits;
-template <> struct VarTraits<QC_QUARTIC> { static constexpr int HB = 4, BA = 4; };
-template <> struct VarTraits<QC_HARMONIC> { static constexpr int HB = 1, BA = 1; };
-template <> struct VarTraits<QC_INV_HARMONIC> { static constexpr int HB = 2, BA = 2; };
-
-template <int VAR, int L>
-struct LaneOps {
-    static constexpr int HB = VarTraits<VAR>::HB;
-    // grid: dg[j] = H_jj - kappa F x_j, uniform off-diagonals tk.  Fock: hd[j] = H_jj, fxl[r+2] = -kappa F xl_r (r in [-2, L]),
-    // h2[r+2] = H[r][r+2] (r in [-2, L-1]).
-    double dg[L];
-    double fxl[(VAR == QC_QUARTIC) ? 1 : L + 3];
-    double h2[(VAR == QC_INV_HARMONIC) ? L + 2 : 1];
-    double tk[4];
-
-    __device__ __forceinline__ double2 h0(const double2* ext, int j) const {
-        const double2 c = ext[j + HB];
-        double re = dg[j] * c.x, im = dg[j] * c.y;
-        if constexpr (VAR == QC_QUARTIC) {
-#pragma unroll
-            for (int k = 1; k <= 4; k++) {
-                const double2 a = ext[j + HB - k], b = ext[j + HB + k];
-                re = fma(tk[k - 1], a.x + b.x, re); im = fma(tk[k - 1], a.y + b.y, im);
-            }
-        } else {
-            const double2 a = ext[j + HB - 1], b = ext[j + HB + 1];
-            re = fma(fxl[j + 2], b.x, re); im = fma(fxl[j + 2], b.y, im);
-            re = fma(fxl[j + 1], a.x, re); im = fma(fxl[j + 1], a.y, im);
-            if constexpr (VAR == QC_INV_HARMONIC) {
-                const double2 a2 = ext[j + HB - 2], b2 = ext[j + HB + 2];
-                re = fma(h2[j + 2], b2.x, re); im = fma(h2[j + 2], b2.y, im);
-                re = fma(h2[j], a2.x, re); im = fma(h2[j], a2.y, im);
-            }
-        }
-        return mk2(re, im);
-    }
-};
-
-// One Horner sweep: publish w (own points) into `buf`, barrier, gather halos, return H0 w on the own points.
-template <int VAR, int L, bool MULTI>
-__device__ __forceinline__ void sweep_h0(const LaneOps<VAR, L>& ops, double2* __restrict__ buf, const double2 (&w)[L], double2 (&hw)[L], int g, int G, int bar_id) {
-    constexpr int HB = VarTraits<VAR>::HB;
-#pragma unroll
-    for (int j = 0; j < L; j++) buf[j * G + g] = w[j];
-    traj_sync<MULTI>(bar_id, G);
-    double2 ext[L + 2 * HB];
-#pragma unroll
-    for (int r = -HB; r < L + HB; r++) ext[r + HB] = (r >= 0 && r < L) ? w[r] : ld_rel<L>(buf, g, G, r);
-#pragma unroll
-    for (int j = 0; j < L; j++) hw[j] = ops.h0(ext, j);
-}
-
-// ------------------------------------------------------------------------------------------------------
-// The implicit solve (I + i dt/2 H0) psi' = psi~, done by the first warp of the trajectory (see file header).
-// rhs in U, scratch z in V, result in U.  Lane c owns points [c*chunk, (c+1)*chunk) and starts both substitutions W points
-// outside its chunk with zero history.  Every lane runs the same trip count (chunk + W); out-of-range points read as zero rows.
-// Factor rows {l_1..l_BA, 1/d, (xl,0)} come from the shared-memory copy `tab` ([line index][CS], TABS) or from global memory.
-template <int VAR> struct SolveTraits { static constexpr int BA = VarTraits<VAR>::BA; static constexpr int CS = (BA == 4) ? 5 : ((BA == 1) ? 3 : 5); };
-
-template <int VAR, int L, bool TABS>
-__device__ __forceinline__ void solve_traj(const StepParams& p, double2* __restrict__ U, double2* __restrict__ V, const double2* __restrict__ tab,
-                                           const double2* __restrict__ fac, double* scal, int* iflag, int lane) {
-    constexpr int BA = SolveTraits<VAR>::BA, CS = SolveTraits<VAR>::CS;
-    const int G = p.G, n = p.n, chunk = p.chunk, W = p.W;
-    const int s0 = lane * chunk, e0 = min(s0 + chunk, n);
-    const int trips = chunk + W;
-    // ---- forward: L y = rhs, z = D^{-1} y ------------------------------------------------------------------
-    {
-        double2 y[BA];
-#pragma unroll
-        for (int k = 0; k < BA; k++) y[k] = mk2(0.0, 0.0);
-        int i = s0 - W;
-        // line position of i (for i < 0 the loads are predicated off, the position is only advanced)
-        int jj = ((i % L) + L) % L, ll = (i - jj) / L;
-#pragma unroll 4
-        for (int t = 0; t < trips; t++) {
-            const bool ok = (i >= 0) && (i < e0);
-            const int li = jj * G + ll;
-            double2 rhs = mk2(0.0, 0.0), cf[BA + 1];
-#pragma unroll
-            for (int k = 0; k <= BA; k++) cf[k] = mk2(0.0, 0.0);
-            if (ok) {
-                rhs = U[li];
-                if (TABS) {
-#pragma unroll
-                    for (int k = 0; k <= BA; k++) cf[k] = tab[li * CS + k];
-                } else {
-#pragma unroll
-                    for (int k = 0; k <= BA; k++) cf[k] = __ldg(&fac[(size_t)i * (BA + 1) + k]);
-                }
-            }
-            double re = rhs.x, im = rhs.y;
-#pragma unroll
-            for (int k = BA - 1; k >= 0; k--) {   // far history first: the newest value (k = 0) closes the dependency chain
-                re = fma(-cf[k].x, y[k].x, re); re = fma(cf[k].y, y[k].y, re);
-                im = fma(-cf[k].x, y[k].y, im); im = fma(-cf[k].y, y[k].x, im);
-            }
-#pragma unroll
-            for (int k = BA - 1; k > 0; k--) y[k] = y[k - 1];
-            y[0] = mk2(re, im);
-            if (ok && i >= s0) V[li] = mk2(re * cf[BA].x - im * cf[BA].y, re * cf[BA].y + im * cf[BA].x);
-            i++; jj++; if (jj == L) { jj = 0; ll++; }
-        }
-    }
-    __syncwarp();
-    // ---- backward: L^T x = z, column oriented (row i of L again) ------------------------------------------
-    double nrm = 0.0, sx = 0.0, cen = 0.0;
-    {
-        double2 pend[BA];
-#pragma unroll
-        for (int k = 0; k < BA; k++) pend[k] = mk2(0.0, 0.0);
-        int i = s0 + trips - 1;
-        int jj = i % L, ll = i / L;
-        double2 xprev = mk2(0.0, 0.0);
-        const bool do_cen = (VAR == QC_QUARTIC) && (p.cen_hi > p.cen_lo);
-#pragma unroll 4
-        for (int t = 0; t < trips; t++) {
-            const bool ok = (i < n);
-            const int li = jj * G + ll;
-            double2 z = mk2(0.0, 0.0), cf[BA + 2];
-#pragma unroll
-            for (int k = 0; k < BA + 2; k++) cf[k] = mk2(0.0, 0.0);
-            if (ok) {
-                z = V[li];
-                if (TABS) {
-#pragma unroll
-                    for (int k = 0; k < BA; k++) cf[k] = tab[li * CS + k];
-                    if (VAR != QC_QUARTIC) cf[BA + 1] = tab[li * CS + BA + 1];
-                } else {
-#pragma unroll
-                    for (int k = 0; k < BA; k++) cf[k] = __ldg(&fac[(size_t)i * (BA + 1) + k]);
-                    if (VAR != QC_QUARTIC) cf[BA + 1] = mk2(__ldg(&p.x[i]), 0.0);
-                }
-            }
-            const double xr = z.x + pend[0].x, xi = z.y + pend[0].y;
-#pragma unroll
-            for (int k = 0; k < BA; k++) {
-                const double pr = (k + 1 < BA) ? pend[k + 1].x : 0.0, pi = (k + 1 < BA) ? pend[k + 1].y : 0.0;
-                pend[k].x = fma(-xr, cf[k].x, fma(xi, cf[k].y, pr));
-                pend[k].y = fma(-xr, cf[k].y, fma(-xi, cf[k].x, pi));
-            }
-            if (ok && i < e0) {
-                U[li] = mk2(xr, xi);
-                const double a2 = xr * xr + xi * xi;
-                nrm += a2;
-                if (VAR == QC_QUARTIC) {
-                    sx = fma(p.h * (double)(i - p.half), a2, sx);
-                    if (do_cen && i >= p.cen_lo && i < p.cen_hi) cen += a2;
-                } else {
-                    sx = fma(2.0 * cf[BA + 1].x, xr * xprev.x + xi * xprev.y, sx);     // 2 xl_i Re(conj(x_i) x_{i+1})
-                }
-            }
-            xprev = mk2(xr, xi);
-            i--; jj--; if (jj < 0) { jj = L - 1; ll--; }
-        }
-    }
-    nrm = warp_sum(nrm); sx = warp_sum(sx); cen = warp_sum(cen);
-    __syncwarp();
-    if (lane == 0) {
-        const double s = 1.0 / sqrt(nrm) / sqrt(p.w);          // normalize(): Q:259-263, H:197-201
-        const double s2 = s * s;
-        // check_boundary_error (Q:559-565, H:403-407, I:422-426) on the normalised state
-        double bl = 0.0, br = 0.0;
-        for (int k = 0; k < p.fail_len; k++) {
-            const double2 hi = U[lidx<L>(n - 1 - k, G)]; br += hi.x * hi.x + hi.y * hi.y;
-            if (VAR == QC_QUARTIC) { const double2 lo = U[lidx<L>(k, G)]; bl += lo.x * lo.x + lo.y * lo.y; }
-        }
-        scal[0] = s; scal[1] = p.w * sx * s2;
-        int f = iflag[0];
-        if (bl * s2 > p.fail_thr2 || br * s2 > p.fail_thr2) f |= QC_FLAG_FAIL;
-        if (VAR == QC_QUARTIC && p.cen_hi > p.cen_lo) { if (1.0 - p.w * cen * s2 > 0.5) f |= QC_FLAG_ESCAPED; }
-        iflag[0] = f;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-template <int VAR, int L, bool MULTI, int MAXT, bool TABS>
-__global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
-    constexpr int HB = VarTraits<VAR>::HB;
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int tid = threadIdx.x, G = p.G, n = p.n;
-    const int t = tid / G, g = tid - t * G;
-    const int lane = tid & 31, wq = g >> 5, nwarps = G >> 5;
-    const int bar_id = 1 + t;
-    const int pos = blockIdx.x * p.T + t;
-    const bool have = pos < p.B;
-    const int traj = have ? (p.order ? p.order[pos] : pos) : 0;
-
-    unsigned char* base = smem + (size_t)t * p.tstride;
-    double2* U = reinterpret_cast<double2*>(base);
-    double2* V = U + p.NP;
-    double2* X3 = V + p.NP;                                              // Fock only (plan allocates it)
-    constexpr int NBUF = (VAR == QC_QUARTIC) ? 2 : 3;
-    constexpr int CS = SolveTraits<VAR>::CS, BAs = SolveTraits<VAR>::BA;
-    double2* tab = U + (size_t)NBUF * p.NP;                              // [NP][CS] factor rows of this trajectory's force (TABS)
-    double* nz = reinterpret_cast<double*>(base + (size_t)(NBUF + (TABS ? CS : 0)) * p.NP * sizeof(double2));
-    double* red = reinterpret_cast<double*>(base + p.tstride - 128 - 2 * QC_MAXRED * nwarps * sizeof(double));
-    double* scal = reinterpret_cast<double*>(base + p.tstride - 128);
-    int* iflag = reinterpret_cast<int*>(scal + 8);   // [0] latched flags
-    int red_phase = 0;
-
-    const int slot = have ? min(max(p.slot[traj], 0), p.n_slots - 1) : 0;
-    const double F = have ? p.slot_force[slot] : 0.0;
-    const int my_nsub = have ? (p.moments_only ? 0 : (p.nsub_traj ? min(p.nsub_traj[traj], p.n_sub) : p.n_sub)) : 0;
-    const long long step0 = have ? p.step_count[traj] : 0;
-
-    // ---- per-lane constants -------------------------------------------------------------------------------
-    LaneOps<VAR, L> ops;
-    double xs[(VAR == QC_QUARTIC) ? L : 1];      // grid: x_j
-    double xl[(VAR == QC_QUARTIC) ? 1 : L + 3];  // Fock: xl_r, r in [-2, L]  (index r+2)
-    bool valid[L];
-#pragma unroll
-    for (int j = 0; j < L; j++) {
-        const int i = g * L + j;
-        valid[j] = have && (i < n);
-        if constexpr (VAR == QC_QUARTIC) {
-            xs[j] = valid[j] ? __ldg(&p.x[i]) : 0.0;
-            ops.dg[j] = valid[j] ? (__ldg(&p.hdiag[i]) - p.kappa * F * xs[j]) : 0.0;
-        } else {
-            ops.dg[j] = valid[j] ? __ldg(&p.hdiag[i]) : 0.0;
-        }
-    }
-    if constexpr (VAR == QC_QUARTIC) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) ops.tk[k] = p.tk[k];
-    } else {
-#pragma unroll
-        for (int r = -2; r <= L; r++) {
-            const int i = g * L + r;                 // tables are zero padded by 8 on both sides
-            const double v = (i < n + 8) ? __ldg(&p.x[i]) : 0.0;
-            xl[r + 2] = v; ops.fxl[r + 2] = -p.kappa * F * v;
-        }
-        if constexpr (VAR == QC_INV_HARMONIC) {
-#pragma unroll
-            for (int r = -2; r < L; r++) { const int i = g * L + r; ops.h2[r + 2] = (i < n + 8) ? __ldg(&p.h2[i]) : 0.0; }
-        }
-    }
-
-    // ---- prologue: state -> shared line U, noise table, initial <x> ----------------------------------------
-    for (int i = g; i < p.NP; i += G) {
-        double2 v = mk2(0.0, 0.0);
-        if (have && i < n) v = p.psi[(size_t)traj * n + i];
-        U[lidx<L>(i, G)] = v;
-    }
-    for (int s = g; s < my_nsub; s += G) {
-        double r0, r1;
-        if (p.noise) { r0 = p.noise[((size_t)traj * p.n_sub + s) * 2]; r1 = p.noise[((size_t)traj * p.n_sub + s) * 2 + 1]; }
-        else philox_normals_dev(p.seed, (uint64_t)(p.traj_offset + traj), (uint64_t)(step0 + s), &r0, &r1);
-        nz[2 * s] = r0; nz[2 * s + 1] = r1;
-    }
-    if (g == 0) iflag[0] = have ? (int)p.flags_latch[traj] : 0;
-    const double2* __restrict__ fac = p.fac + (size_t)slot * n * (BAs + 1);
-    if (TABS) {
-        for (int i = g; i < p.NP; i += G) {
-            const int li = lidx<L>(i, G);
-#pragma unroll
-            for (int k = 0; k < CS; k++) {
-                double2 v = mk2(0.0, 0.0);
-                if (have && i < n) { if (k <= BAs) v = __ldg(&fac[(size_t)i * (BAs + 1) + k]); else if (k == BAs + 1 && VAR != QC_QUARTIC) v = mk2(__ldg(&p.x[i]), 0.0); }
-                tab[li * CS + k] = v;
-            }
-        }
-    }
-    traj_sync<MULTI>(bar_id, G);
-
-    double sc = 1.0, xbar;
-    {
-        double v[2] = {0.0, 0.0};
-#pragma unroll
-        for (int j = 0; j < L; j++) {
-            const double2 c = U[j * G + g];
-            if constexpr (VAR == QC_QUARTIC) {
-                const double a2 = c.x * c.x + c.y * c.y;
-                v[0] = fma(xs[j], a2, v[0]);
-                const int i = g * L + j;
-                if (i >= p.cen_lo && i < p.cen_hi) v[1] += a2;
-            } else {
-                const double2 nx = ld_rel<L>(U, g, G, j + 1);
-                v[0] = fma(2.0 * xl[j + 2], c.x * nx.x + c.y * nx.y, v[0]);
-            }
-        }
-        traj_reduce<2, MULTI>(v, red, red_phase, wq, nwarps, lane, bar_id, G);
-        xbar = p.w * v[0];
-        if (VAR == QC_QUARTIC && p.cen_hi > p.cen_lo && g == 0 && have && !p.moments_only) {
-            if (1.0 - p.w * v[1] > 0.5) iflag[0] |= QC_FLAG_ESCAPED;       // the check before the first substep (IQ/main_parallel.py:199)
-        }
-    }
-
-    // scheme constants
-    const double dt = p.dt, sdt = sqrt(dt), g4 = p.gamma / 4.0, gs = sqrt(p.gamma / 2.0), sig = sdt * gs;
-    const double e5 = dt * dt * dt * dt * dt * dt / 360.0, e4 = dt * dt * dt * dt * dt / 80.0, e3 = dt * dt * dt * dt / 24.0, e2 = dt * dt * dt / 12.0;
-    const double q_scale = 1.0 / sqrt(2.0 * p.gamma) / dt;
-
-    // ---- substep loop ---------------------------------------------------------------------------------------
-    for (int s = 0; s < p.n_sub; s++) {
-        const bool active = s < my_nsub;
-        if (active) {
-            const double r0 = nz[2 * s], r1 = nz[2 * s + 1];
-            const double dW = r0 * sdt, dZ = sdt * dt * 0.5 * (r0 + r1 / sqrt(3.0));       // Q:573
-            const double k1 = 0.5 / sdt * dZ, k2 = 0.25 * dt, k3 = 0.25 / sdt * (dW * dW - dt), k4 = 0.5 / dt * (dW * dt - dZ),
-                         k5 = 0.25 / dt * (dW * dW / 3 - dt) * dW, k6 = 0.25 * sdt * dW;   // Q:636-641
-            if (g == 0) {
-                if (p.q_out) p.q_out[(size_t)traj * p.n_sub + s] = xbar + dW * q_scale;   // Q:577
-                if (p.xmean_out) p.xmean_out[(size_t)traj * p.n_sub + s] = xbar;
-            }
-            double2 psi[L], a[L], acc[L], w[L], hw[L], v1[L];
-            if constexpr (VAR == QC_QUARTIC) {
-                // ===== position grid: x is diagonal, everything but H0 is pointwise ====================================
-                double2 ext[L + 8];
-#pragma unroll
-                for (int r = -4; r < L + 4; r++) { const double2 c = ld_rel<L>(U, g, G, r); ext[r + 4] = mk2(sc * c.x, sc * c.y); }
-                double m[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                for (int j = 0; j < L; j++) {
-                    psi[j] = ext[j + 4];
-                    const double2 h = ops.h0(ext, j);
-                    const double d = xs[j] - xbar, d2g = g4 * d * d;
-                    // a = -i H0 psi - gamma/4 (x-<x>)^2 psi      (D1, Q:434-449)
-                    a[j] = valid[j] ? mk2(h.y - d2g * psi[j].x, -h.x - d2g * psi[j].y) : mk2(0.0, 0.0);
-                    const double bx_ = gs * d * psi[j].x, by_ = gs * d * psi[j].y;         // b = sqrt(gamma/2)(x-<x>) psi   (D2, Q:473-486)
-                    const double ux = fma(dt, a[j].x, psi[j].x), uy = fma(dt, a[j].y, psi[j].y);
-                    const double ypx = fma(sdt, bx_, ux), ypy = fma(sdt, by_, uy), ymx = fma(-sdt, bx_, ux), ymy = fma(-sdt, by_, uy);   // Y+-  (Q:589-594)
-                    const double p2 = ypx * ypx + ypy * ypy, m2 = ymx * ymx + ymy * ymy;
-                    const double xp2 = xs[j] * p2;
-                    m[0] += xp2; m[1] = fma(xs[j], xp2, m[1]); m[2] = fma(xs[j] * xs[j], xp2, m[2]); m[3] = fma(xs[j], m2, m[3]);
-                }
-                traj_reduce<4, MULTI>(m, red, red_phase, wq, nwarps, lane, bar_id, G);
-                // un-normalised <x> of Y+, Y- (D1ImRe, Q:457-460) and of Phi+- = Y+ (1 +- sig (x - <x>_Y+)) (Q:605-615,479-482)
-                const double xbp = p.w * m[0], xbm = p.w * m[3];
-                const double t1 = m[1] - xbp * m[0], t2 = m[2] - 2.0 * xbp * m[1] + xbp * xbp * m[0];
-                const double xfp = p.w * (m[0] + 2.0 * sig * t1 + sig * sig * t2), xfm = p.w * (m[0] - 2.0 * sig * t1 + sig * sig * t2);
-                const double cvb = 2.0 * sdt * (k1 - k6) * gs, cvp = 2.0 * k2;
-#pragma unroll
-                for (int j = 0; j < L; j++) {
-                    const double x = xs[j], d = x - xbar, dp = x - xbp, dm = x - xbm;
-                    const double bx_ = gs * d * psi[j].x, by_ = gs * d * psi[j].y;
-                    const double ux = fma(dt, a[j].x, psi[j].x), uy = fma(dt, a[j].y, psi[j].y);
-                    const double ypx = fma(sdt, bx_, ux), ypy = fma(sdt, by_, uy), ymx = fma(-sdt, bx_, ux), ymy = fma(-sdt, by_, uy);
-                    // psi~ - (linear H0 terms) = cpsi psi + cP Y+ + cM Y-   (all multipliers real on the grid)
-                    const double cpsi = 1.0 + (dW - 2.0 * k4) * gs * d - 2.0 * k2 * g4 * d * d;
-                    const double php = 1.0 + sig * dp, phm = 1.0 - sig * dp;
-                    const double cP = -(k1 + k2) * g4 * dp * dp + (k3 + k4 - k5) * gs * dp + k5 * gs * ((x - xfp) * php - (x - xfm) * phm);
-                    const double cM = (k1 - k2) * g4 * dm * dm + (k4 - k3 + k5) * gs * dm;
-                    acc[j] = mk2(cpsi * psi[j].x + cP * ypx + cM * ymx, cpsi * psi[j].y + cP * ypy + cM * ymy);
-                    const double cv = cvb * d + cvp;                                       // v1 = -i (cvb b/gs... ) see header
-                    v1[j] = mk2(cv * psi[j].y, -cv * psi[j].x);
-                }
-            } else {
-                // ===== Fock basis: x is tridiagonal ====================================================================
-                double2 pe[L + 4];                       // psi on [-2, L+1]
-#pragma unroll
-                for (int r = -2; r < L + 2; r++) { const double2 c = ld_rel<L>(U, g, G, r); pe[r + 2] = mk2(sc * c.x, sc * c.y); }
-                double2 rel0[L + 2];                     // (x - <x>) psi on [-1, L]
-#pragma unroll
-                for (int r = -1; r <= L; r++) {
-                    const double xa = xl[r + 2], xb = xl[r + 1];     // xl_r, xl_{r-1}
-                    rel0[r + 1] = mk2(xa * pe[r + 3].x + xb * pe[r + 1].x - xbar * pe[r + 2].x, xa * pe[r + 3].y + xb * pe[r + 1].y - xbar * pe[r + 2].y);
-                }
-                double2 yp[L], ym[L], sq0[L];
-#pragma unroll
-                for (int j = 0; j < L; j++) {
-                    psi[j] = pe[j + 2];
-                    const double xa = xl[j + 2], xb = xl[j + 1];
-                    sq0[j] = mk2(xa * rel0[j + 2].x + xb * rel0[j].x - xbar * rel0[j + 1].x, xa * rel0[j + 2].y + xb * rel0[j].y - xbar * rel0[j + 1].y);
-                    // H0 psi on own points (halo HB <= 2)
-                    const double2 h = ops.h0(pe + (2 - HB), j);
-                    a[j] = mk2(h.y - g4 * sq0[j].x, -h.x - g4 * sq0[j].y);
-                    const double ux = fma(dt, a[j].x, psi[j].x), uy = fma(dt, a[j].y, psi[j].y);
-                    yp[j] = mk2(fma(sig, rel0[j + 1].x, ux), fma(sig, rel0[j + 1].y, uy));
-                    ym[j] = mk2(fma(-sig, rel0[j + 1].x, ux), fma(-sig, rel0[j + 1].y, uy));
-                }
-                // exchange Y+ (-> V) and Y- (-> X3) with halo 2
-#pragma unroll
-                for (int j = 0; j < L; j++) { V[j * G + g] = yp[j]; X3[j * G + g] = ym[j]; }
-                traj_sync<MULTI>(bar_id, G);
-                double2 ype[L + 4], yme[L + 4];
-#pragma unroll
-                for (int r = -2; r < L + 2; r++) {
-                    ype[r + 2] = (r >= 0 && r < L) ? yp[r] : ld_rel<L>(V, g, G, r);
-                    yme[r + 2] = (r >= 0 && r < L) ? ym[r] : ld_rel<L>(X3, g, G, r);
-                }
-                double2 xyp[L + 2], xym[L + 2];          // x Y+- on [-1, L]
-                double m[2] = {0.0, 0.0};
-#pragma unroll
-                for (int r = -1; r <= L; r++) {
-                    const double xa = xl[r + 2], xb = xl[r + 1];
-                    xyp[r + 1] = mk2(xa * ype[r + 3].x + xb * ype[r + 1].x, xa * ype[r + 3].y + xb * ype[r + 1].y);
-                    xym[r + 1] = mk2(xa * yme[r + 3].x + xb * yme[r + 1].x, xa * yme[r + 3].y + xb * yme[r + 1].y);
-                    if (r >= 0 && r < L) {
-                        m[0] += ype[r + 2].x * xyp[r + 1].x + ype[r + 2].y * xyp[r + 1].y;
-                        m[1] += yme[r + 2].x * xym[r + 1].x + yme[r + 2].y * xym[r + 1].y;
-                    }
-                }
-                traj_reduce<2, MULTI>(m, red, red_phase, wq, nwarps, lane, bar_id, G);
-                const double xbp = p.w * m[0], xbm = p.w * m[1];
-                double2 relp[L + 2], relm[L + 2], php[L + 2], phm[L + 2];
-#pragma unroll
-                for (int r = -1; r <= L; r++) {
-                    relp[r + 1] = mk2(xyp[r + 1].x - xbp * ype[r + 2].x, xyp[r + 1].y - xbp * ype[r + 2].y);
-                    relm[r + 1] = mk2(xym[r + 1].x - xbm * yme[r + 2].x, xym[r + 1].y - xbm * yme[r + 2].y);
-                    php[r + 1] = mk2(fma(sig, relp[r + 1].x, ype[r + 2].x), fma(sig, relp[r + 1].y, ype[r + 2].y));     // Phi+ (Q:612)
-                    phm[r + 1] = mk2(fma(-sig, relp[r + 1].x, ype[r + 2].x), fma(-sig, relp[r + 1].y, ype[r + 2].y));   // Phi- (Q:606-608)
-                }
-                double2 xfp_[L], xfm_[L];
-                double mf[2] = {0.0, 0.0};
-#pragma unroll
-                for (int j = 0; j < L; j++) {
-                    const double xa = xl[j + 2], xb = xl[j + 1];
-                    xfp_[j] = mk2(xa * php[j + 2].x + xb * php[j].x, xa * php[j + 2].y + xb * php[j].y);
-                    xfm_[j] = mk2(xa * phm[j + 2].x + xb * phm[j].x, xa * phm[j + 2].y + xb * phm[j].y);
-                    mf[0] += php[j + 1].x * xfp_[j].x + php[j + 1].y * xfp_[j].y;
-                    mf[1] += phm[j + 1].x * xfm_[j].x + phm[j + 1].y * xfm_[j].y;
-                }
-                traj_reduce<2, MULTI>(mf, red, red_phase, wq, nwarps, lane, bar_id, G);
-                const double xfp = p.w * mf[0], xfm = p.w * mf[1];
-                const double cvb = 2.0 * sdt * (k1 - k6) * gs, cvp = 2.0 * k2;
-#pragma unroll
-                for (int j = 0; j < L; j++) {
-                    const double xa = xl[j + 2], xb = xl[j + 1];
-                    // (x-<x>)^2 Y+-  -> aRe(Y+-) = -gamma/4 * that  (D1ImRe, Q:468-469)
-                    const double sqpx = xa * relp[j + 2].x + xb * relp[j].x - xbp * relp[j + 1].x, sqpy = xa * relp[j + 2].y + xb * relp[j].y - xbp * relp[j + 1].y;
-                    const double sqmx = xa * relm[j + 2].x + xb * relm[j].x - xbm * relm[j + 1].x, sqmy = xa * relm[j + 2].y + xb * relm[j].y - xbm * relm[j + 1].y;
-                    const double arpx = -g4 * sqpx, arpy = -g4 * sqpy, armx = -g4 * sqmx, army = -g4 * sqmy;
-                    const double ar0x = -g4 * sq0[j].x, ar0y = -g4 * sq0[j].y;
-                    const double b0x = gs * rel0[j + 1].x, b0y = gs * rel0[j + 1].y;
-                    const double bpx = gs * relp[j + 1].x, bpy = gs * relp[j + 1].y, bmx = gs * relm[j + 1].x, bmy = gs * relm[j + 1].y;
-                    const double bfpx = gs * (xfp_[j].x - xfp * php[j + 1].x), bfpy = gs * (xfp_[j].y - xfp * php[j + 1].y);
-                    const double bfmx = gs * (xfm_[j].x - xfm * phm[j + 1].x), bfmy = gs * (xfm_[j].y - xfm * phm[j + 1].y);
-                    acc[j] = mk2(psi[j].x + dW * b0x + k1 * (arpx - armx) + k2 * (arpx + armx + 2.0 * ar0x) + k3 * (bpx - bmx) + k4 * (bpx + bmx - 2.0 * b0x) + k5 * (bfpx - bfmx - bpx + bmx),
-                                 psi[j].y + dW * b0y + k1 * (arpy - army) + k2 * (arpy + army + 2.0 * ar0y) + k3 * (bpy - bmy) + k4 * (bpy + bmy - 2.0 * b0y) + k5 * (bfpy - bfmy - bpy + bmy));
-                    const double tvx = cvb * rel0[j + 1].x + cvp * psi[j].x, tvy = cvb * rel0[j + 1].y + cvp * psi[j].y;
-                    v1[j] = mk2(tvy, -tvx);
-                }
-            }
-            if constexpr (VAR == QC_INV_HARMONIC) {
-                // The reference applies the complex-symmetric correction matrix C with a HERMITIAN/UPPER descriptor (I:23,551):
-                // C_herm = C - 2i strict_lower(Im C).  herm_mode 0 reproduces that; 1 additionally drops Im(C_ii); 2 = symmetric (as H:532).
-                if (p.herm_mode != 2) {
-                    traj_sync<MULTI>(bar_id, G);
-#pragma unroll
-                    for (int j = 0; j < L; j++) V[j * G + g] = a[j];
-                    traj_sync<MULTI>(bar_id, G);
-                    double2 ah[L + 10];
-#pragma unroll
-                    for (int r = -10; r < L; r++) ah[r + 10] = (r >= 0) ? a[r] : ld_rel<L>(V, g, G, r);
-                    const double* __restrict__ kt = p.herm_tab + (size_t)slot * n * 11;
-#pragma unroll
-                    for (int j = 0; j < L; j++) {
-                        if (valid[j]) {
-                            const int i = g * L + j;
-                            double cr = 0.0, ci = 0.0;
-#pragma unroll
-                            for (int k = 1; k <= 10; k++) { const double c = __ldg(&kt[(size_t)i * 11 + k]); cr = fma(c, ah[j + 10 - k].x, cr); ci = fma(c, ah[j + 10 - k].y, ci); }
-                            acc[j].x += 2.0 * ci; acc[j].y -= 2.0 * cr;
-                            if (p.herm_mode == 1) { const double kd = __ldg(&kt[(size_t)i * 11]); acc[j].x += kd * a[j].y; acc[j].y -= kd * a[j].x; }
-                        }
-                    }
-                }
-            }
-            // ===== merged Horner chain in H0 (see header) ===============================================================
-#pragma unroll
-            for (int j = 0; j < L; j++) w[j] = mk2(-e5 * a[j].y, e5 * a[j].x);                    // c5 a,  c5 = +i dt^6/360
-            double2* b0 = (VAR == QC_QUARTIC) ? V : U;    // Fock: V/X3 were just used for Y+-, U is free (all lanes passed a barrier after reading it)
-            double2* b1 = (VAR == QC_QUARTIC) ? U : V;
-            sweep_h0<VAR, L, MULTI>(ops, b0, w, hw, g, G, bar_id);
-#pragma unroll
-            for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(-e4, a[j].x, hw[j].x), fma(-e4, a[j].y, hw[j].y)) : mk2(0.0, 0.0);      // c4 = -dt^5/80
-            sweep_h0<VAR, L, MULTI>(ops, b1, w, hw, g, G, bar_id);
-#pragma unroll
-            for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(e3, a[j].y, hw[j].x), fma(-e3, a[j].x, hw[j].y)) : mk2(0.0, 0.0);       // c3 = -i dt^4/24
-            sweep_h0<VAR, L, MULTI>(ops, b0, w, hw, g, G, bar_id);
-#pragma unroll
-            for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(e2, a[j].x, hw[j].x), fma(e2, a[j].y, hw[j].y)) : mk2(0.0, 0.0);        // c2 = dt^3/12
-            sweep_h0<VAR, L, MULTI>(ops, b1, w, hw, g, G, bar_id);
-#pragma unroll
-            for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(v1[j].x + hw[j].x, v1[j].y + hw[j].y) : mk2(0.0, 0.0);
-            sweep_h0<VAR, L, MULTI>(ops, b0, w, hw, g, G, bar_id);
-            // psi~ -> U (rhs of the implicit solve).  For the grid b0 == V so U's last readers (sweep 4) are behind a barrier;
-            // for Fock b0 == U: its halo readers must finish first.
-            if constexpr (VAR != QC_QUARTIC) traj_sync<MULTI>(bar_id, G);
-#pragma unroll
-            for (int j = 0; j < L; j++) U[j * G + g] = valid[j] ? mk2(acc[j].x + hw[j].x, acc[j].y + hw[j].y) : mk2(0.0, 0.0);
-        }
-        if (active) {
-            traj_sync<MULTI>(bar_id, G);                       // psi~ complete in U
-            if (g < 32) solve_traj<VAR, L, TABS>(p, U, V, tab, fac, scal, iflag, g);
-            traj_sync<MULTI>(bar_id, G);
-            sc = scal[0]; xbar = scal[1];
-        }
-    }
-
-    // ---- epilogue: normalised state back to HBM, moments, reward terms, flags -------------------------------------
-    traj_sync<MULTI>(bar_id, G);
-    double2 psi[L];
-#pragma unroll
-    for (int j = 0; j < L; j++) { const double2 c = U[j * G + g]; psi[j] = mk2(sc * c.x, sc * c.y); }
-    if (have && !p.moments_only) {
-        for (int i = g; i < n; i += G) { const double2 c = U[lidx<L>(i, G)]; p.psi[(size_t)traj * n + i] = mk2(sc * c.x, sc * c.y); }
-        if (g == 0) { p.step_count[traj] = step0 + my_nsub; p.flags_latch[traj] = (unsigned char)iflag[0]; }
-    }
-    if (have && g == 0 && p.flags_out) p.flags_out[traj] = (unsigned char)iflag[0];
-    if (p.moments == nullptr && p.aux == nullptr) return;
-
-    if constexpr (VAR == QC_QUARTIC) {
-        // compute_statistics (Q:325-362) + cal_energy (Q/main_parallel.py:63-64) + outside probability (IQ/main_parallel.py:78-81)
-        double2 ext[L + 8];
-#pragma unroll
-        for (int r = -4; r < L + 4; r++) { const double2 c = ld_rel<L>(U, g, G, r); ext[r + 4] = (r >= 0 && r < L) ? psi[r] : mk2(sc * c.x, sc * c.y); }
-        double2 tcur[L];
-        double v0[5] = {0.0, 0.0, 0.0, 0.0, 0.0};    // norm, sum x|psi|^2, Re<psi|H psi>, Re<psi|p psi>, centre probability
-#pragma unroll
-        for (int j = 0; j < L; j++) {
-            const int i = g * L + j;
-            const double a2 = psi[j].x * psi[j].x + psi[j].y * psi[j].y;
-            v0[0] += a2; v0[1] = fma(xs[j], a2, v0[1]);
-            if (i >= p.cen_lo && i < p.cen_hi) v0[4] += a2;
-            double hr = 0.0, hi = 0.0;
-            if (valid[j]) {
-                const double hd = __ldg(&p.hdiag[i]);
-                hr = hd * psi[j].x; hi = hd * psi[j].y;
-#pragma unroll
-                for (int k = 1; k <= 4; k++) { hr = fma(p.tk[k - 1], ext[j + 4 - k].x + ext[j + 4 + k].x, hr); hi = fma(p.tk[k - 1], ext[j + 4 - k].y + ext[j + 4 + k].y, hi); }
-            }
-            v0[2] += psi[j].x * hr + psi[j].y * hi;
-            // p_hat psi with the reference's truncated upper triangle mirrored (Q:59-70,181,239)
-            double pr = 0.0, pim = 0.0;
-#pragma unroll
-            for (int k = 1; k <= 4; k++) {
-                const bool mu = (i + 2 * k <= n - 1), ml = (i + k <= n - 1);
-                const double dx = (mu ? ext[j + 4 + k].x : 0.0) - (ml ? ext[j + 4 - k].x : 0.0);
-                const double dy = (mu ? ext[j + 4 + k].y : 0.0) - (ml ? ext[j + 4 - k].y : 0.0);
-                pr = fma(p.pk[k - 1], dy, pr); pim = fma(-p.pk[k - 1], dx, pim);
-            }
-            tcur[j] = mk2(pr, pim);
-            v0[3] += psi[j].x * pr + psi[j].y * pim;
-        }
-        traj_reduce<5, MULTI>(v0, red, red_phase, wq, nwarps, lane, bar_id, G);
-        const double xm = p.w * v0[1], pm = p.w * v0[3];
-        double S[20];
-#pragma unroll
-        for (int k = 0; k < 20; k++) S[k] = 0.0;
-        double xr[L];
-#pragma unroll
-        for (int j = 0; j < L; j++) xr[j] = xs[j] - xm;
-        const int M = p.M;
-        // power i = 0:  <xr^j>, j = 2..M
-#pragma unroll
-        for (int j = 0; j < L; j++) {
-            const double c = psi[j].x * psi[j].x + psi[j].y * psi[j].y;
-            double xp = xr[j] * xr[j];
-#pragma unroll
-            for (int jj = 2; jj <= 5; jj++) { if (jj <= M) S[jj * (jj + 1) / 2 - 1] = fma(c, xp, S[jj * (jj + 1) / 2 - 1]); xp *= xr[j]; }
-        }
-#pragma unroll
-        for (int j = 0; j < L; j++) tcur[j] = mk2(tcur[j].x - pm * psi[j].x, tcur[j].y - pm * psi[j].y);      // t1 = (p - <p>) psi
-        traj_sync<MULTI>(bar_id, G);     // every lane has read U (state store + halos) before it is reused below
-#pragma unroll
-        for (int ip = 1; ip <= 5; ip++) {
-            if (ip <= M) {
-                if (ip > 1) {
-                    double2* buf = (ip & 1) ? U : V;
-#pragma unroll
-                    for (int j = 0; j < L; j++) buf[j * G + g] = tcur[j];
-                    traj_sync<MULTI>(bar_id, G);
-                    double2 te[L + 8];
-#pragma unroll
-                    for (int r = -4; r < L + 4; r++) te[r + 4] = (r >= 0 && r < L) ? tcur[r] : ld_rel<L>(buf, g, G, r);
-#pragma unroll
-                    for (int j = 0; j < L; j++) {
-                        const int i = g * L + j;
-                        double pr = 0.0, pim = 0.0;
-#pragma unroll
-                        for (int k = 1; k <= 4; k++) {
-                            const bool mu = (i + 2 * k <= n - 1), ml = (i + k <= n - 1);
-                            const double dx = (mu ? te[j + 4 + k].x : 0.0) - (ml ? te[j + 4 - k].x : 0.0);
-                            const double dy = (mu ? te[j + 4 + k].y : 0.0) - (ml ? te[j + 4 - k].y : 0.0);
-                            pr = fma(p.pk[k - 1], dy, pr); pim = fma(-p.pk[k - 1], dx, pim);
-                        }
-                        tcur[j] = valid[j] ? mk2(pr - pm * te[j + 4].x, pim - pm * te[j + 4].y) : mk2(0.0, 0.0);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < L; j++) {
-                    const double c = psi[j].x * tcur[j].x + psi[j].y * tcur[j].y;
-                    double xp = 1.0;
-#pragma unroll
-                    for (int mm = 0; mm <= 4; mm++) {
-                        const int jj = ip + mm;
-                        if (jj >= 2 && jj <= 5 && jj <= M) S[jj * (jj + 1) / 2 - 1 + ip] = fma(c, xp, S[jj * (jj + 1) / 2 - 1 + ip]);
-                        xp *= xr[j];
-                    }
-                }
-            }
-        }
-        traj_reduce<20, MULTI>(S, red, red_phase, wq, nwarps, lane, bar_id, G);
-        if (have && g == 0) {
-            if (p.moments) {
-                double* out = p.moments + (size_t)traj * p.K;
-                out[0] = xm; out[1] = pm;
-#pragma unroll
-                for (int k = 2; k < 20; k++) if (k < p.K) out[k] = p.w * S[k];
-            }
-            if (p.aux) {
-                double* ax = p.aux + (size_t)traj * QC_AUX_COUNT;
-                ax[QC_AUX_ENERGY] = p.w * v0[2]; ax[QC_AUX_XMEAN] = xm;
-                ax[QC_AUX_OUTSIDE] = (p.cen_hi > p.cen_lo) ? 1.0 - p.w * v0[4] : 0.0;
-                ax[QC_AUX_NORM] = p.w * v0[0];
-            }
-        }
-    } else {
-        // get_data_xp (H/main_parallel.py:128-130) and phonon_number (H/main_parallel.py:88-89)
-        double v0[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // norm, <x>, <p>, |x psi|^2, |p psi|^2, Re<x psi|p psi>, <n>
-#pragma unroll
-        for (int j = 0; j < L; j++) {
-            const int i = g * L + j;
-            const double2 cn = ld_rel<L>(U, g, G, j + 1), cp_ = ld_rel<L>(U, g, G, j - 1);
-            const double2 nx = (j + 1 < L) ? psi[j + 1 < L ? j + 1 : 0] : mk2(sc * cn.x, sc * cn.y);
-            const double2 pv = (j - 1 >= 0) ? psi[j - 1 >= 0 ? j - 1 : 0] : mk2(sc * cp_.x, sc * cp_.y);
-            const double xa = xl[j + 2], xb = xl[j + 1];
-            const double xr_ = xa * nx.x + xb * pv.x, xi_ = xa * nx.y + xb * pv.y;                 // x psi
-            // p = i/sqrt2 (a^dag - a):  (p psi)_i = i (xl_{i-1} psi_{i-1} - xl_i psi_{i+1})     (H/main_parallel.py:66-67)
-            const double dr = xb * pv.x - xa * nx.x, di = xb * pv.y - xa * nx.y;
-            const double pr = -di, pim = dr;
-            const double a2 = psi[j].x * psi[j].x + psi[j].y * psi[j].y;
-            v0[0] += a2;
-            v0[1] += psi[j].x * xr_ + psi[j].y * xi_;
-            v0[2] += psi[j].x * pr + psi[j].y * pim;
-            v0[3] += xr_ * xr_ + xi_ * xi_;
-            v0[4] += pr * pr + pim * pim;
-            v0[5] += xr_ * pr + xi_ * pim;
-            v0[6] = fma((double)i, a2, v0[6]);
-        }
-        traj_reduce<7, MULTI>(v0, red, red_phase, wq, nwarps, lane, bar_id, G);
-        if (have && g == 0) {
-            if (p.moments) {
-                double* out = p.moments + (size_t)traj * p.K;
-                out[0] = v0[1]; out[1] = v0[2];
-                out[2] = v0[3] - v0[1] * v0[1]; out[3] = v0[4] - v0[2] * v0[2]; out[4] = v0[5] - v0[1] * v0[2];
-            }
-            if (p.aux) {
-                double* ax = p.aux + (size_t)traj * QC_AUX_COUNT;
-                ax[QC_AUX_ENERGY] = v0[6]; ax[QC_AUX_XMEAN] = v0[1]; ax[QC_AUX_OUTSIDE] = 0.0; ax[QC_AUX_NORM] = v0[0];
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// launch plumbing
-
-typedef void (*kern_t)(const StepParams);
-
-// Instantiations.  maxt = __launch_bounds__ of the instance (caps registers: 512 -> 128, 384 -> 168, 256 -> 255, 1024 -> 64
-// with spills to local memory: the "large grid" instances whose state no longer fits the register file).
-struct KernEntry { int var, L; bool multi; int maxt; bool tabs; kern_t fn; };
-#define QC_KE(VAR, L, MULTI, MAXT) {VAR, L, MULTI, MAXT, true, sse_step_kernel<VAR, L, MULTI, MAXT, true>}, {VAR, L, MULTI, MAXT, false, sse_step_kernel<VAR, L, MULTI, MAXT, false>}
-static const KernEntry g_kernels[] = {
-    QC_KE(QC_QUARTIC, 3, true, 512), QC_KE(QC_QUARTIC, 5, true, 384), QC_KE(QC_QUARTIC, 6, true, 384),
-    QC_KE(QC_QUARTIC, 6, false, 384), QC_KE(QC_QUARTIC, 9, true, 256), QC_KE(QC_QUARTIC, 5, true, 1024), QC_KE(QC_QUARTIC, 9, true, 1024),
-    QC_KE(QC_HARMONIC, 1, true, 512), QC_KE(QC_HARMONIC, 2, true, 512), QC_KE(QC_HARMONIC, 3, true, 384), QC_KE(QC_HARMONIC, 3, false, 384),
-    QC_KE(QC_INV_HARMONIC, 1, true, 512), QC_KE(QC_INV_HARMONIC, 2, true, 512), QC_KE(QC_INV_HARMONIC, 3, true, 384), QC_KE(QC_INV_HARMONIC, 6, false, 256),
-};
-
-static const KernEntry* find_kernel(int var, int L, bool multi, int threads_needed, bool tabs) {
+// best instance for (variant, L, G): exact compile-time geometry first, else the run-time-G instance; smallest launch bound that fits
+static const KernEntry* find_kernel(int var, int L, int G, int threads_needed, bool tabs, int force_gc = -1) {
+    static const std::vector<KernEntry> ks = all_kernels();
     const KernEntry* best = nullptr;
-    for (const KernEntry& e : g_kernels)
-        if (e.var == var && e.L == L && e.multi == multi && e.tabs == tabs && e.maxt >= threads_needed && (!best || e.maxt < best->maxt)) best = &e;
+    for (int pass = 0; pass < 2 && !best; pass++) {
+        const int want_gc = (pass == 0) ? G : 0;
+        if (force_gc >= 0 && want_gc != force_gc) continue;
+        for (const KernEntry& e : ks)
+            if (e.var == var && e.L == L && e.gc == want_gc && e.tabs == tabs && e.maxt >= threads_needed && (!best || e.maxt < best->maxt)) best = &e;
+    }
     return best;
 }
 
@@ -798,28 +49,29 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
     int smem_max = 227 * 1024; cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const int nbuf = (var == QC_QUARTIC) ? 2 : 3;
     const int forceL = env_int("QCART_L", 0), forceT = env_int("QCART_T", 0), forceP = env_int("QCART_P", 0);
-    const int forceMulti = env_int("QCART_MULTI", -1);
-    // candidate points-per-lane, preferred first
-    const int candG[] = {3, 5, 6, 9, 2}; const int candF[] = {2, 3, 1};
-    const int* cand = (var == QC_QUARTIC) ? candG : candF; const int ncand = (var == QC_QUARTIC) ? 5 : 3;
-    const int forceTabs = env_int("QCART_TABS", -1);
-    const int ba = m.ba, CS = (ba == 4) ? 5 : ((ba == 1) ? 3 : 5);
+    const int forceTabs = env_int("QCART_TABS", -1), forceGC = env_int("QCART_GC", -1);
+    const int CS = (var == QC_QUARTIC) ? m.ba + 1 : m.ba + 2;
+    // candidate points-per-lane, preferred first (few lanes -> fewer barriers and halos; more lanes when the registers do not suffice)
+    int cand[6]; int ncand = 0;
+    if (var == QC_QUARTIC) { const int c[] = {6, 9, 3, 5}; for (int v : c) cand[ncand++] = v; }
+    else if (var == QC_HARMONIC) { const int c[] = {3, 2, 1}; for (int v : c) cand[ncand++] = v; }
+    else { const int c[] = {6, 3, 2, 1}; for (int v : c) cand[ncand++] = v; }
+    for (int pass = 0; pass < 2; pass++)            // pass 0: only instances that fit without spilling (launch bound < 1024)
     for (int c = 0; c < ncand; c++) {
         const int L = cand[c];
         if (forceL && L != forceL) continue;
         const int G = ((n + L - 1) / L + 31) / 32 * 32;
         if (G > 1024) continue;
-        bool multi = G > 32;
-        if (!multi && forceMulti == 1) multi = true;
+        const int guard = (40 + L - 1) / L + 1, Gp = G + 2 * guard;
         for (int tabs = 1; tabs >= 0; tabs--) {
             if (forceTabs >= 0 && tabs != forceTabs) continue;
-            const KernEntry* ke = find_kernel(var, L, multi, G, tabs != 0);
-            if (!ke && !multi) ke = find_kernel(var, L, true, G, tabs != 0);    // bar.sync with 32 threads is fine too
+            const KernEntry* ke = find_kernel(var, L, G, G, tabs != 0, forceGC);
             if (!ke) continue;
+            if (pass == 0 && ke->maxt >= 1024) continue;
             cudaFuncAttributes fa;
             if (cudaFuncGetAttributes(&fa, (const void*)ke->fn) != cudaSuccess) { err = std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(cudaGetLastError()); return QC_ERR_CUDA; }
             const int NP = G * L;
-            int tstride = (nbuf + (tabs ? CS : 0)) * NP * 16 + n_sub * 16 + 2 * QC_MAXRED * (G / 32) * 8 + 128;
+            int tstride = nbuf * L * Gp * 16 + (tabs ? CS * L * G * 16 : 0) + n_sub * 16 + 2 * QC_MAXRED * (G / 32) * 8 + 128;
             tstride = (tstride + 15) / 16 * 16;
             int Tmax = ke->maxt / G;
             Tmax = std::min(Tmax, 65536 / std::max(1, fa.numRegs * G));
@@ -828,16 +80,20 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             if (Tmax < 1) continue;
             int T = forceT;
             if (T <= 0) { const int per_sm = (B + n_sm - 1) / n_sm; T = std::max(1, std::min(per_sm, 8)); }   // small batch: one even wave
-            if (tabs && Tmax < std::min(T, 3) && forceTabs < 0) continue;     // tables would squeeze the CTA too much: use the global-table variant
+            if (tabs && Tmax < std::min(T, 2) && forceTabs < 0) continue;     // tables would squeeze the CTA too much: use the global-table variant
             T = std::min(T, Tmax);
+            // solver geometry: P lanes of the trajectory's first warp, `mult` columns (mult*L points) each, warm-up W rounded up to whole columns
+            const int cols = (n + L - 1) / L;
+            int W = (W_needed + L - 1) / L * L;
             int P = forceP > 0 ? std::min(forceP, 32) : 32;
-            int chunk = (n + P - 1) / P;
-            chunk = (chunk + L - 1) / L * L;
-            P = (n + chunk - 1) / chunk;
-            plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = chunk; plan.W = (P == 1) ? 0 : W_needed;
-            plan.NP = NP; plan.threads = T * G; plan.tstride = tstride; plan.smem_bytes = T * tstride; plan.multi = ke->multi; plan.maxt = ke->maxt; plan.tabs = tabs != 0;
-            snprintf(plan.info, sizeof(plan.info), "sse_step_kernel<var=%d,L=%d,multi=%d,maxt=%d,tabs=%d> T=%d G=%d P=%d chunk=%d W=%d threads=%d smem=%d regs=%d lmem=%d",
-                     var, L, (int)ke->multi, ke->maxt, tabs, T, G, P, plan.chunk, plan.W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
+            if (W > (guard - 1) * L) { P = 1; }                               // decay too slow for the guard band: sequential solve
+            int mult = (cols + P - 1) / P;
+            P = (cols + mult - 1) / mult;
+            if (P == 1) { W = 0; mult = cols; }
+            plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = mult * L; plan.W = W;
+            plan.NP = NP; plan.threads = T * G; plan.tstride = tstride; plan.smem_bytes = T * tstride; plan.gc = ke->gc; plan.maxt = ke->maxt; plan.tabs = tabs != 0;
+            snprintf(plan.info, sizeof(plan.info), "sse_step_kernel<var=%d,L=%d,gc=%d,maxt=%d,tabs=%d> T=%d G=%d P=%d chunk=%d W=%d threads=%d smem=%d regs=%d lmem=%d",
+                     var, L, ke->gc, ke->maxt, tabs, T, G, P, plan.chunk, plan.W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
             return QC_OK;
         }
     }
@@ -846,7 +102,7 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
 }
 
 int launch_step(const LaunchPlan& plan, const StepParams& p, void* stream, std::string& err) {
-    const KernEntry* ke = find_kernel(p.variant, plan.L, plan.multi, plan.maxt, plan.tabs);
+    const KernEntry* ke = find_kernel(p.variant, plan.L, plan.G, plan.maxt, plan.tabs, plan.gc);
     if (!ke) { err = "kernel not found"; return QC_ERR_UNSUPPORTED; }
     kern_t fn = ke->fn;
     if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess) {
