@@ -118,7 +118,10 @@ def run_reference(args, task, params):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_thread = max(1, args.ref_traj_per_thread)
+    per_thread = args.ref_traj_per_thread
+    if per_thread <= 0:
+        r0, s0 = cpu_port_rate(task, params, 1, cores)          # calibration (also warms caches / builds the oracle)
+        per_thread = max(1, int(2.0 / max(s0, 1e-3)))
     rates, secs = [], []
     for i in range(args.warmup + args.steps):
         r, s = cpu_port_rate(task, params, per_thread, cores)
@@ -145,13 +148,13 @@ def workload_name(task, B, n, n_sub):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--task", default="quartic", help="quartic (BASELINE configs[1], default) | inverted_quartic | harmonic | inverted_harmonic")
     ap.add_argument("--batch", type=int, default=1024, help="trajectories per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-traj-per-thread", type=int, default=4)
+    ap.add_argument("--ref-traj-per-thread", type=int, default=0, help="0 = sized for ~2 s of CPU work per timed step")
     ap.add_argument("--no-l2-flush", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -288,7 +291,8 @@ def main():
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        per_thread = 8 if task in ("quartic", "harmonic", "inverted_harmonic") else 2
+        _, s0 = cpu_port_rate(task, params, 1, cores)
+        per_thread = max(2, int(12.0 / max(s0, 1e-3)))
         v, secs = cpu_port_rate(task, params, per_thread, cores)
         cpu_baseline = {"value": v, "unit": "traj-control-steps/s", "cores": cores, "kind": "port",
                         "sample": "%d threads x %d trajectories x 1 control step (%d substeps, N=%d) in %.1f s; oracle/sse_oracle.c built -Ofast (the reference's flag), "

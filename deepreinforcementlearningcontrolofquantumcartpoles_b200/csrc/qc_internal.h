@@ -74,13 +74,15 @@ struct StepParams {
     const int32_t* nsub_traj;// [B] or null
     // outputs
     double* moments; double* aux; unsigned char* flags_out; unsigned char* flags_latch; double* q_out; double* xmean_out;
+    int jacobi;              // 1: register-resident chunk-Jacobi solve (one-warp trajectories, chunk == L)
+    int debug;               // development only (QCART_DEBUG): 1 = skip the implicit solve, 2 = skip the explicit part; results are then wrong
     int moments_only;        // 1: skip the substep loop, only compute moments/aux of the resident state
 };
 
 struct LaunchPlan {
     int L, T, G, P, chunk, W, NP, threads, smem_bytes, tstride, maxt, gc;
-    bool tabs;
-    char info[224];
+    bool tabs; int jacobi;
+    char info[240];
 };
 
 int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan, std::string& err);

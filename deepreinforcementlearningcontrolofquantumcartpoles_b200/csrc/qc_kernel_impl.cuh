@@ -183,33 +183,47 @@ __device__ __forceinline__ void solve_traj(const StepParams& p, double2* __restr
     const int col0 = lane * mult;
     const bool act = lane < p.P;
     double nrm = 0.0, sx = 0.0, cen = 0.0;
+    // Row = what one recurrence step needs: the vector entry and the factor row of its point.  Loads run PF steps ahead of the
+    // arithmetic through a small register ring (explicit software pipelining: with one or two warps per scheduler nothing else hides
+    // the shared-memory latency of this serial loop).
+    struct Row { double2 v; double2 cf[BA + 2]; };
+    constexpr int PF = (L % 3 == 0) ? 2 : 0, NR = PF + 1;
+    auto load_row = [&](Row& r, const double2* __restrict__ buf, int col, int j, bool bwd) {
+        const int tc = min(max(col, 0), G - 1);
+        r.v = buf[j * Gp + GUARD + col];
+#pragma unroll
+        for (int k = 0; k <= BA; k++) {
+            if (bwd && k == BA) { if (VAR != QC_QUARTIC) r.cf[BA] = TABS ? tab[(j * CS + BA + 1) * G + tc] : mk2(__ldg(&p.x[min(tc * L + j, n - 1)]), 0.0); }
+            else r.cf[k] = TABS ? tab[(j * CS + k) * G + tc] : __ldg(&fac[(size_t)(tc * L + j) * (BA + 1) + k]);
+        }
+    };
     if (act) {
         // ---- forward: L y = rhs, z = D^{-1} y --------------------------------------------------------------
         double2 y[BA];
 #pragma unroll
         for (int k = 0; k < BA; k++) y[k] = mk2(0.0, 0.0);
+        Row ring[NR];
         int col = col0 - wb;
+#pragma unroll
+        for (int q = 0; q < PF; q++) load_row(ring[q], U, col, q, false);
         for (int b = 0; b < wb + mult; b++, col++) {
             const bool own = b >= wb;
-            const double2* __restrict__ ub = U + GUARD + col;
             double2* __restrict__ vb = V + GUARD + col;
-            const int tc = min(max(col, 0), G - 1);
 #pragma unroll
             for (int j = 0; j < L; j++) {
-                const double2 rhs = ub[j * Gp];
-                double2 cf[BA + 1];
-#pragma unroll
-                for (int k = 0; k <= BA; k++) cf[k] = TABS ? tab[(j * CS + k) * G + tc] : __ldg(&fac[(size_t)(tc * L + j) * (BA + 1) + k]);
-                double re = rhs.x, im = rhs.y;
+                if (j + PF < L) load_row(ring[(j + PF) % NR], U, col, j + PF, false);
+                else load_row(ring[(j + PF) % NR], U, col + 1, j + PF - L, false);        // next column (guard / clamped past the end)
+                const Row& r = ring[j % NR];
+                double re = r.v.x, im = r.v.y;
 #pragma unroll
                 for (int k = BA - 1; k >= 0; k--) {   // far history first: the newest value (k = 0) closes the dependency chain
-                    re = fma(-cf[k].x, y[k].x, re); re = fma(cf[k].y, y[k].y, re);
-                    im = fma(-cf[k].x, y[k].y, im); im = fma(-cf[k].y, y[k].x, im);
+                    re = fma(-r.cf[k].x, y[k].x, re); re = fma(r.cf[k].y, y[k].y, re);
+                    im = fma(-r.cf[k].x, y[k].y, im); im = fma(-r.cf[k].y, y[k].x, im);
                 }
 #pragma unroll
                 for (int k = BA - 1; k > 0; k--) y[k] = y[k - 1];
                 y[0] = mk2(re, im);
-                if (own) vb[j * Gp] = mk2(re * cf[BA].x - im * cf[BA].y, re * cf[BA].y + im * cf[BA].x);
+                if (own) vb[j * Gp] = mk2(re * r.cf[BA].x - im * r.cf[BA].y, re * r.cf[BA].y + im * r.cf[BA].x);
             }
         }
     }
@@ -221,24 +235,25 @@ __device__ __forceinline__ void solve_traj(const StepParams& p, double2* __restr
         for (int k = 0; k < BA; k++) pend[k] = mk2(0.0, 0.0);
         double2 xprev = mk2(0.0, 0.0);
         const bool do_cen = (VAR == QC_QUARTIC) && (p.cen_hi > p.cen_lo);
+        Row ring[NR];
         int col = col0 + mult + wb - 1;
+#pragma unroll
+        for (int q = 0; q < PF; q++) load_row(ring[q], V, col, L - 1 - q, true);
         for (int b = 0; b < wb + mult; b++, col--) {
             const bool own = b >= wb;
-            const double2* __restrict__ vb = V + GUARD + col;
             double2* __restrict__ ub = U + GUARD + col;
-            const int tc = min(max(col, 0), G - 1);
 #pragma unroll
-            for (int j = L - 1; j >= 0; j--) {
-                const double2 z = vb[j * Gp];
-                double2 cf[BA];
-#pragma unroll
-                for (int k = 0; k < BA; k++) cf[k] = TABS ? tab[(j * CS + k) * G + tc] : __ldg(&fac[(size_t)(tc * L + j) * (BA + 1) + k]);
-                const double xr = z.x + pend[0].x, xi = z.y + pend[0].y;
+            for (int jr = 0; jr < L; jr++) {          // jr-th step of the column, point j = L-1-jr
+                const int j = L - 1 - jr;
+                if (jr + PF < L) load_row(ring[(jr + PF) % NR], V, col, L - 1 - (jr + PF), true);
+                else load_row(ring[(jr + PF) % NR], V, col - 1, L - 1 - (jr + PF - L), true);
+                const Row& r = ring[jr % NR];
+                const double xr = r.v.x + pend[0].x, xi = r.v.y + pend[0].y;
 #pragma unroll
                 for (int k = 0; k < BA; k++) {
                     const double pr = (k + 1 < BA) ? pend[k + 1].x : 0.0, pi = (k + 1 < BA) ? pend[k + 1].y : 0.0;
-                    pend[k].x = fma(-xr, cf[k].x, fma(xi, cf[k].y, pr));
-                    pend[k].y = fma(-xr, cf[k].y, fma(-xi, cf[k].x, pi));
+                    pend[k].x = fma(-xr, r.cf[k].x, fma(xi, r.cf[k].y, pr));
+                    pend[k].y = fma(-xr, r.cf[k].y, fma(-xi, r.cf[k].x, pi));
                 }
                 if (own) {
                     ub[j * Gp] = mk2(xr, xi);
@@ -249,8 +264,7 @@ __device__ __forceinline__ void solve_traj(const StepParams& p, double2* __restr
                         sx = fma(p.h * (double)(i - p.half), a2, sx);
                         if (do_cen && i >= p.cen_lo && i < p.cen_hi) cen += a2;
                     } else {
-                        const double xlv = TABS ? tab[(j * CS + BA + 1) * G + tc].x : __ldg(&p.x[min(i, n - 1)]);
-                        sx = fma(2.0 * xlv, xr * xprev.x + xi * xprev.y, sx);     // 2 xl_i Re(conj(x_i) x_{i+1})
+                        sx = fma(2.0 * r.cf[BA].x, xr * xprev.x + xi * xprev.y, sx);     // 2 xl_i Re(conj(x_i) x_{i+1})
                     }
                 }
                 xprev = mk2(xr, xi);
@@ -277,6 +291,124 @@ __device__ __forceinline__ void solve_traj(const StepParams& p, double2* __restr
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Register-resident variant of the same truncated solve for one-warp trajectories whose lanes own exactly one column (chunk = L):
+// "chunk Jacobi".  Every lane keeps its own L factor rows in registers and repeats the substitution over its own L points K times;
+// after each pass it hands the BA boundary values (forward: the last BA entries of y; backward: the pending column updates) to its
+// neighbour lane by warp shuffle.  Pass k therefore sees the right-hand side of k previous chunks -- exactly the truncation of the
+// warm-up formulation above with W = (K-1) L -- but shared memory is touched only for the 5 L factor-row loads and the L result stores,
+// instead of ~11 L (K) loads: the shared-memory pipe, not the FP64 pipe, was the bound of the warm-up version (profiles/README.md).
+// rhs comes in registers (psi~ never goes through shared memory); returns the normalisation scale and <x> in registers.
+template <int VAR, int L>
+__device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const double2 (&rhs)[L], double2* __restrict__ U, const double2* __restrict__ tab,
+                                                  int* iflag, int lane, int G, int Gp, double& sc_out, double& xbar_out) {
+    constexpr int BA = SolveTraits<VAR>::BA, CS = SolveTraits<VAR>::CS, GUARD = Guard<L>::v;
+    const int n = p.n, K = p.W / L + 1;
+    double2 lr[L][BA], dinv[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) {
+#pragma unroll
+        for (int k = 0; k < BA; k++) lr[j][k] = tab[(j * CS + k) * G + lane];
+        dinv[j] = tab[(j * CS + BA) * G + lane];
+    }
+    // ---- forward: L y = rhs --------------------------------------------------------------------------------------
+    double2 y[L], hin[BA];
+#pragma unroll
+    for (int k = 0; k < BA; k++) hin[k] = mk2(0.0, 0.0);
+    for (int it = 0; it < K; it++) {
+        double2 h[BA];
+#pragma unroll
+        for (int k = 0; k < BA; k++) h[k] = hin[k];                 // h[k] = y_{i-1-k}
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            double re = rhs[j].x, im = rhs[j].y;
+#pragma unroll
+            for (int k = BA - 1; k >= 0; k--) {
+                re = fma(-lr[j][k].x, h[k].x, re); re = fma(lr[j][k].y, h[k].y, re);
+                im = fma(-lr[j][k].x, h[k].y, im); im = fma(-lr[j][k].y, h[k].x, im);
+            }
+#pragma unroll
+            for (int k = BA - 1; k > 0; k--) h[k] = h[k - 1];
+            h[0] = mk2(re, im);
+            y[j] = h[0];
+        }
+        if (it + 1 < K) {
+#pragma unroll
+            for (int k = 0; k < BA; k++) {
+                hin[k].x = __shfl_up_sync(0xffffffffu, h[k].x, 1); hin[k].y = __shfl_up_sync(0xffffffffu, h[k].y, 1);
+                if (lane == 0) hin[k] = mk2(0.0, 0.0);
+            }
+        }
+    }
+    // ---- z = D^{-1} y, backward: L^T x = z (column oriented) ------------------------------------------------------------
+    double2 z[L], x[L], pin[BA];
+#pragma unroll
+    for (int j = 0; j < L; j++) z[j] = mk2(y[j].x * dinv[j].x - y[j].y * dinv[j].y, y[j].x * dinv[j].y + y[j].y * dinv[j].x);
+#pragma unroll
+    for (int k = 0; k < BA; k++) pin[k] = mk2(0.0, 0.0);
+    for (int it = 0; it < K; it++) {
+        double2 pend[BA];
+#pragma unroll
+        for (int k = 0; k < BA; k++) pend[k] = pin[k];
+#pragma unroll
+        for (int j = L - 1; j >= 0; j--) {
+            const double xr = z[j].x + pend[0].x, xi = z[j].y + pend[0].y;
+            x[j] = mk2(xr, xi);
+#pragma unroll
+            for (int k = 0; k < BA; k++) {
+                const double pr = (k + 1 < BA) ? pend[k + 1].x : 0.0, pi = (k + 1 < BA) ? pend[k + 1].y : 0.0;
+                pend[k].x = fma(-xr, lr[j][k].x, fma(xi, lr[j][k].y, pr));
+                pend[k].y = fma(-xr, lr[j][k].y, fma(-xi, lr[j][k].x, pi));
+            }
+        }
+        if (it + 1 < K) {
+#pragma unroll
+            for (int k = 0; k < BA; k++) {
+                pin[k].x = __shfl_down_sync(0xffffffffu, pend[k].x, 1); pin[k].y = __shfl_down_sync(0xffffffffu, pend[k].y, 1);
+                if (lane == 31) pin[k] = mk2(0.0, 0.0);
+            }
+        }
+    }
+    // ---- result -> shared line (halos of the next substep), norm, <x>, escape probability, Fail -----------------------------
+    double nrm = 0.0, sx = 0.0, cen = 0.0;
+    const bool do_cen = (VAR == QC_QUARTIC) && (p.cen_hi > p.cen_lo);
+    double2 xnext = mk2(0.0, 0.0);
+    if constexpr (VAR != QC_QUARTIC) {
+        xnext.x = __shfl_down_sync(0xffffffffu, x[0].x, 1); xnext.y = __shfl_down_sync(0xffffffffu, x[0].y, 1);
+        if (lane == 31) xnext = mk2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int j = 0; j < L; j++) {
+        U[j * Gp + GUARD + lane] = x[j];
+        const double a2 = x[j].x * x[j].x + x[j].y * x[j].y;
+        nrm += a2;
+        const int i = lane * L + j;
+        if constexpr (VAR == QC_QUARTIC) {
+            sx = fma(p.h * (double)(i - p.half), a2, sx);
+            if (do_cen && i >= p.cen_lo && i < p.cen_hi) cen += a2;
+        } else {
+            const double2 nx = (j + 1 < L) ? x[(j + 1 < L) ? j + 1 : 0] : xnext;
+            sx = fma(2.0 * tab[(j * CS + BA + 1) * G + lane].x, x[j].x * nx.x + x[j].y * nx.y, sx);
+        }
+    }
+    nrm = warp_sum(nrm); sx = warp_sum(sx); if (do_cen) cen = warp_sum(cen);
+    const double s = 1.0 / sqrt(nrm) / sqrt(p.w);          // normalize(): Q:259-263, H:197-201
+    const double s2 = s * s;
+    sc_out = s; xbar_out = p.w * sx * s2;
+    __syncwarp();
+    if (lane == 0) {
+        double bl = 0.0, br = 0.0;                          // check_boundary_error (Q:559-565, H:403-407, I:422-426) on the normalised state
+        for (int k = 0; k < p.fail_len; k++) {
+            const double2 hi = U[lidx<L>(n - 1 - k, Gp)]; br += hi.x * hi.x + hi.y * hi.y;
+            if (VAR == QC_QUARTIC) { const double2 lo = U[lidx<L>(k, Gp)]; bl += lo.x * lo.x + lo.y * lo.y; }
+        }
+        int f = iflag[0];
+        if (bl * s2 > p.fail_thr2 || br * s2 > p.fail_thr2) f |= QC_FLAG_FAIL;
+        if (VAR == QC_QUARTIC && p.cen_hi > p.cen_lo) { if (1.0 - p.w * cen * s2 > 0.5) f |= QC_FLAG_ESCAPED; }
+        iflag[0] = f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 template <int VAR, int L, int GC, int MAXT, bool TABS>
 __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     constexpr bool MULTI = (GC != 32);                // GC = compile-time lanes per trajectory (0: run-time p.G)
@@ -285,8 +417,10 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, G = GC ? GC : p.G, n = p.n;
     const int Gp = G + 2 * GUARD, LB = L * Gp;         // line: L rows of Gp columns
-    const int t = tid / G, g = tid - t * G;
-    const int lane = tid & 31, wq = g >> 5, nwarps = G >> 5;
+    // warp w of the CTA serves trajectory (w % T) as its (w / T)-th warp: the first warps of all trajectories (which also run the serial
+    // part, the implicit solve) get consecutive warp ids and therefore spread over the four SM sub-partitions
+    const int lane = tid & 31, nwarps = G >> 5;
+    const int t = (tid >> 5) % p.T, wq = (tid >> 5) / p.T, g = wq * 32 + lane;
     const int bar_id = 1 + t;
     const int pos = blockIdx.x * p.T + t;
     const bool have = pos < p.B;
@@ -398,7 +532,7 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     // ---- substep loop ---------------------------------------------------------------------------------------
     for (int s = 0; s < p.n_sub; s++) {
         const bool active = s < my_nsub;
-        if (active) {
+        if (active && !(p.debug & 2)) {
             const double r0 = nz[2 * s], r1 = nz[2 * s + 1];
             const double dW = r0 * sdt, dZ = sdt * dt * 0.5 * (r0 + r1 / sqrt(3.0));       // Q:573
             const double k1 = 0.5 / sdt * dZ, k2 = 0.25 * dt, k3 = 0.25 / sdt * (dW * dW - dt), k4 = 0.5 / dt * (dW * dt - dZ),
@@ -579,17 +713,24 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
 #pragma unroll
             for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(v1[j].x + hw[j].x, v1[j].y + hw[j].y) : mk2(0.0, 0.0);
             sweep_h0<VAR, L, MULTI>(ops, b0, w, hw, g, G, Gp, bar_id);
-            // psi~ -> U (rhs of the implicit solve).  For the grid b0 == V so U's last readers (sweep 4) are behind a barrier;
-            // for Fock b0 == U: its halo readers must finish first.
-            if constexpr (VAR != QC_QUARTIC) traj_sync<MULTI>(bar_id, G);
+            // psi~ = acc + H0 w0: right-hand side of the implicit solve
+            constexpr bool JAC = (GC == 32) && TABS;
+            if (JAC && p.jacobi) {
+                double2 rhs[L];
 #pragma unroll
-            for (int j = 0; j < L; j++) U[j * Gp + GUARD + g] = valid[j] ? mk2(acc[j].x + hw[j].x, acc[j].y + hw[j].y) : mk2(0.0, 0.0);
-        }
-        if (active) {
-            traj_sync<MULTI>(bar_id, G);                       // psi~ complete in U
-            if (g < 32) solve_traj<VAR, L, TABS>(p, U, V, tab, fac, scal, iflag, g, G, Gp);
-            traj_sync<MULTI>(bar_id, G);
-            sc = scal[0]; xbar = scal[1];
+                for (int j = 0; j < L; j++) rhs[j] = valid[j] ? mk2(acc[j].x + hw[j].x, acc[j].y + hw[j].y) : mk2(0.0, 0.0);
+                if (!(p.debug & 1)) solve_traj_jacobi<VAR, L>(p, rhs, U, tab, iflag, g, G, Gp, sc, xbar);
+                __syncwarp();
+            } else {
+                // For the grid b0 == V so U's last readers (sweep 4) are behind a barrier; for Fock b0 == U: its halo readers must finish first.
+                if constexpr (VAR != QC_QUARTIC) traj_sync<MULTI>(bar_id, G);
+#pragma unroll
+                for (int j = 0; j < L; j++) U[j * Gp + GUARD + g] = valid[j] ? mk2(acc[j].x + hw[j].x, acc[j].y + hw[j].y) : mk2(0.0, 0.0);
+                traj_sync<MULTI>(bar_id, G);                       // psi~ complete in U
+                if (g < 32 && !(p.debug & 1)) solve_traj<VAR, L, TABS>(p, U, V, tab, fac, scal, iflag, g, G, Gp);
+                traj_sync<MULTI>(bar_id, G);
+                sc = scal[0]; xbar = scal[1];
+            }
         }
     }
 

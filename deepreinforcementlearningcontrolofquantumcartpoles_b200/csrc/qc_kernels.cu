@@ -91,9 +91,10 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             P = (cols + mult - 1) / mult;
             if (P == 1) { W = 0; mult = cols; }
             plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = mult * L; plan.W = W;
+            plan.jacobi = (ke->gc == 32 && tabs && mult == 1 && P > 1 && env_int("QCART_JACOBI", 1)) ? 1 : 0;
             plan.NP = NP; plan.threads = T * G; plan.tstride = tstride; plan.smem_bytes = T * tstride; plan.gc = ke->gc; plan.maxt = ke->maxt; plan.tabs = tabs != 0;
-            snprintf(plan.info, sizeof(plan.info), "sse_step_kernel<var=%d,L=%d,gc=%d,maxt=%d,tabs=%d> T=%d G=%d P=%d chunk=%d W=%d threads=%d smem=%d regs=%d lmem=%d",
-                     var, L, ke->gc, ke->maxt, tabs, T, G, P, plan.chunk, plan.W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
+            snprintf(plan.info, sizeof(plan.info), "sse_step_kernel<var=%d,L=%d,gc=%d,maxt=%d,tabs=%d> T=%d G=%d P=%d chunk=%d W=%d jac=%d threads=%d smem=%d regs=%d lmem=%d",
+                     var, L, ke->gc, ke->maxt, tabs, T, G, P, plan.chunk, plan.W, plan.jacobi, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
             return QC_OK;
         }
     }

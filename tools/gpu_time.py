@@ -43,20 +43,18 @@ if __name__ == "__main__":
     print("measured peaks: fp64 %.2f TFLOP/s, smem %.2f TB/s" % tuple(v / 1e12 for v in measure_peaks(0)))
     which = sys.argv[1] if len(sys.argv) > 1 else "quartic"
     if which == "quartic":
-        for L, T, P in [(6, 7, 32), (6, 7, 16), (6, 7, 8), (6, 4, 32), (3, 7, 32), (3, 7, 16), (9, 7, 32)]:
+        for L, T, P in [(6, 7, 32), (6, 4, 32), (6, 8, 32)]:
             run("quartic", 1024, {"QCART_L": L, "QCART_T": T, "QCART_P": P})
-        run("quartic", 1024, {"QCART_L": 6, "QCART_T": 7, "QCART_P": 32, "QCART_TABS": 0})
-        run("quartic", 1024, {"QCART_L": 6, "QCART_T": 7, "QCART_P": 32, "QCART_GC": 0})
-        for L, T, P in [(6, 7, 32), (6, 8, 32), (6, 8, 16), (6, 4, 32), (3, 4, 32)]:
+        for L, T, P in [(6, 7, 32), (6, 8, 32), (6, 4, 32)]:
             run("quartic", 8192, {"QCART_L": L, "QCART_T": T, "QCART_P": P})
-        run("quartic", 8192, {"QCART_L": 6, "QCART_T": 8, "QCART_P": 32, "QCART_TABS": 0})
     elif which == "iq":
-        for L, T, P in [(6, 3, 32), (6, 2, 32), (6, 1, 32), (6, 3, 16), (9, 3, 32), (5, 2, 32), (3, 2, 32)]:
-            run("inverted_quartic", 1024, {"QCART_L": L, "QCART_T": T, "QCART_P": P})
-        run("inverted_quartic", 1024, {"QCART_L": 6, "QCART_T": 4, "QCART_P": 32, "QCART_TABS": 0})
-        for L, T, P in [(6, 3, 32), (6, 2, 32), (9, 3, 32)]:
-            run("inverted_quartic", 8192, {"QCART_L": L, "QCART_T": T, "QCART_P": P})
+        for L, T, P in [(6, 3, 32), (6, 2, 32), (6, 1, 32), (9, 2, 32), (9, 3, 32), (3, 2, 32), (5, 2, 32)]:
+            run("inverted_quartic", 8192, {"QCART_L": L, "QCART_T": T, "QCART_P": P}, steps=5)
+        run("inverted_quartic", 8192, {"QCART_L": 6, "QCART_T": 3, "QCART_P": 32, "QCART_TABS": 0}, steps=5)
+        run("inverted_quartic", 8192, {"QCART_L": 6, "QCART_T": 4, "QCART_P": 32, "QCART_TABS": 0}, steps=5)
+        run("inverted_quartic", 1024, {}, steps=5)
     elif which == "fock":
-        for task in ("harmonic", "inverted_harmonic"):
-            for L, T, P in [(1, 2, 32), (1, 4, 32), (2, 4, 32), (2, 8, 32), (3, 8, 32), (3, 4, 32), (6, 7, 32)]:
-                run(task, 8192, {"QCART_L": L, "QCART_T": T, "QCART_P": P})
+        for task, Ls in (("harmonic", [(3, 8), (3, 4), (2, 8), (1, 4)]), ("inverted_harmonic", [(6, 8), (6, 4), (3, 8), (3, 4), (2, 4)])):
+            for L, T in Ls:
+                run(task, 8192, {"QCART_L": L, "QCART_T": T}, steps=10)
+            run(task, 1024, {}, steps=10)
