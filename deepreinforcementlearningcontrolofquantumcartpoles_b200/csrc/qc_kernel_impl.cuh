@@ -298,26 +298,29 @@ __device__ __forceinline__ void solve_traj(const StepParams& p, double2* __restr
 // warm-up formulation above with W = (K-1) L -- but shared memory is touched only for the 5 L factor-row loads and the L result stores,
 // instead of ~11 L (K) loads: the shared-memory pipe, not the FP64 pipe, was the bound of the warm-up version (profiles/README.md).
 // rhs comes in registers (psi~ never goes through shared memory); returns the normalisation scale and <x> in registers.
-template <int VAR, int L>
+template <int VAR, int L, bool MULTI>
 __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const double2 (&rhs)[L], double2* __restrict__ U, const double2* __restrict__ tab,
-                                                  int* iflag, int lane, int G, int Gp, double& sc_out, double& xbar_out) {
+                                                  double2* __restrict__ mbox, double* red, int& red_phase, int* iflag, int g, int G, int Gp, int bar_id,
+                                                  double& sc_out, double& xbar_out) {
     constexpr int BA = SolveTraits<VAR>::BA, CS = SolveTraits<VAR>::CS, GUARD = Guard<L>::v;
     const int n = p.n, K = p.W / L + 1;
+    const int lane = g & 31, wq = g >> 5, nwarps = G >> 5;
     double2 lr[L][BA], dinv[L];
 #pragma unroll
     for (int j = 0; j < L; j++) {
 #pragma unroll
-        for (int k = 0; k < BA; k++) lr[j][k] = tab[(j * CS + k) * G + lane];
-        dinv[j] = tab[(j * CS + BA) * G + lane];
+        for (int k = 0; k < BA; k++) lr[j][k] = tab[(j * CS + k) * G + g];
+        dinv[j] = tab[(j * CS + BA) * G + g];
     }
+    // Boundary values travel lane -> lane+1 (forward) / lane -> lane-1 (backward): warp shuffle inside a warp, a double-buffered
+    // shared mailbox + the trajectory's named barrier between warps.  Lane 0 of the trajectory needs no masking in the forward sweep: the
+    // factor entries that would multiply a value from before the first point are zero.  The last lane's incoming pending updates are
+    // forced to zero (there is no lane behind it).
     // ---- forward: L y = rhs --------------------------------------------------------------------------------------
-    double2 y[L], hin[BA];
+    double2 y[L], h[BA];
 #pragma unroll
-    for (int k = 0; k < BA; k++) hin[k] = mk2(0.0, 0.0);
+    for (int k = 0; k < BA; k++) h[k] = mk2(0.0, 0.0);              // h[k] = y_{i-1-k}
     for (int it = 0; it < K; it++) {
-        double2 h[BA];
-#pragma unroll
-        for (int k = 0; k < BA; k++) h[k] = hin[k];                 // h[k] = y_{i-1-k}
 #pragma unroll
         for (int j = 0; j < L; j++) {
             double re = rhs[j].x, im = rhs[j].y;
@@ -332,23 +335,33 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
             y[j] = h[0];
         }
         if (it + 1 < K) {
+            if constexpr (MULTI) {
+                double2* mb = mbox + (it & 1) * (nwarps * BA);
+                if (lane == 31) {
 #pragma unroll
-            for (int k = 0; k < BA; k++) {
-                hin[k].x = __shfl_up_sync(0xffffffffu, h[k].x, 1); hin[k].y = __shfl_up_sync(0xffffffffu, h[k].y, 1);
-                if (lane == 0) hin[k] = mk2(0.0, 0.0);
+                    for (int k = 0; k < BA; k++) mb[wq * BA + k] = h[k];
+                }
+                traj_sync<true>(bar_id, G);
+#pragma unroll
+                for (int k = 0; k < BA; k++) {
+                    const double2 up = (wq > 0) ? mb[(wq - 1) * BA + k] : mk2(0.0, 0.0);
+                    const double sx_ = __shfl_up_sync(0xffffffffu, h[k].x, 1), sy_ = __shfl_up_sync(0xffffffffu, h[k].y, 1);
+                    h[k] = (lane == 0) ? up : mk2(sx_, sy_);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < BA; k++) { h[k].x = __shfl_up_sync(0xffffffffu, h[k].x, 1); h[k].y = __shfl_up_sync(0xffffffffu, h[k].y, 1); }
             }
         }
     }
     // ---- z = D^{-1} y, backward: L^T x = z (column oriented) ------------------------------------------------------------
-    double2 z[L], x[L], pin[BA];
+    double2 z[L], x[L], pend[BA];
 #pragma unroll
     for (int j = 0; j < L; j++) z[j] = mk2(y[j].x * dinv[j].x - y[j].y * dinv[j].y, y[j].x * dinv[j].y + y[j].y * dinv[j].x);
 #pragma unroll
-    for (int k = 0; k < BA; k++) pin[k] = mk2(0.0, 0.0);
+    for (int k = 0; k < BA; k++) pend[k] = mk2(0.0, 0.0);
+    const bool last_lane = (g == G - 1);
     for (int it = 0; it < K; it++) {
-        double2 pend[BA];
-#pragma unroll
-        for (int k = 0; k < BA; k++) pend[k] = pin[k];
 #pragma unroll
         for (int j = L - 1; j >= 0; j--) {
             const double xr = z[j].x + pend[0].x, xi = z[j].y + pend[0].y;
@@ -361,41 +374,57 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
             }
         }
         if (it + 1 < K) {
+            if constexpr (MULTI) {
+                double2* mb = mbox + (it & 1) * (nwarps * BA);
+                if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < BA; k++) {
-                pin[k].x = __shfl_down_sync(0xffffffffu, pend[k].x, 1); pin[k].y = __shfl_down_sync(0xffffffffu, pend[k].y, 1);
-                if (lane == 31) pin[k] = mk2(0.0, 0.0);
+                    for (int k = 0; k < BA; k++) mb[wq * BA + k] = pend[k];
+                }
+                traj_sync<true>(bar_id, G);
+#pragma unroll
+                for (int k = 0; k < BA; k++) {
+                    const double2 dn = (wq + 1 < nwarps) ? mb[(wq + 1) * BA + k] : mk2(0.0, 0.0);
+                    const double sx_ = __shfl_down_sync(0xffffffffu, pend[k].x, 1), sy_ = __shfl_down_sync(0xffffffffu, pend[k].y, 1);
+                    pend[k] = (lane == 31) ? dn : mk2(sx_, sy_);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < BA; k++) {
+                    const double sx_ = __shfl_down_sync(0xffffffffu, pend[k].x, 1), sy_ = __shfl_down_sync(0xffffffffu, pend[k].y, 1);
+                    pend[k] = last_lane ? mk2(0.0, 0.0) : mk2(sx_, sy_);
+                }
             }
         }
     }
     // ---- result -> shared line (halos of the next substep), norm, <x>, escape probability, Fail -----------------------------
-    double nrm = 0.0, sx = 0.0, cen = 0.0;
+    double acc3[3] = {0.0, 0.0, 0.0};                     // norm, sum for <x>, centre probability
     const bool do_cen = (VAR == QC_QUARTIC) && (p.cen_hi > p.cen_lo);
+#pragma unroll
+    for (int j = 0; j < L; j++) U[j * Gp + GUARD + g] = x[j];
     double2 xnext = mk2(0.0, 0.0);
     if constexpr (VAR != QC_QUARTIC) {
-        xnext.x = __shfl_down_sync(0xffffffffu, x[0].x, 1); xnext.y = __shfl_down_sync(0xffffffffu, x[0].y, 1);
-        if (lane == 31) xnext = mk2(0.0, 0.0);
+        if constexpr (MULTI) { traj_sync<true>(bar_id, G); xnext = U[GUARD + g + 1]; }      // first point of the next lane (guard column = 0 behind the last lane)
+        else { xnext.x = __shfl_down_sync(0xffffffffu, x[0].x, 1); xnext.y = __shfl_down_sync(0xffffffffu, x[0].y, 1); if (last_lane) xnext = mk2(0.0, 0.0); }
     }
 #pragma unroll
     for (int j = 0; j < L; j++) {
-        U[j * Gp + GUARD + lane] = x[j];
         const double a2 = x[j].x * x[j].x + x[j].y * x[j].y;
-        nrm += a2;
-        const int i = lane * L + j;
+        acc3[0] += a2;
+        const int i = g * L + j;
         if constexpr (VAR == QC_QUARTIC) {
-            sx = fma(p.h * (double)(i - p.half), a2, sx);
-            if (do_cen && i >= p.cen_lo && i < p.cen_hi) cen += a2;
+            acc3[1] = fma(p.h * (double)(i - p.half), a2, acc3[1]);
+            if (do_cen && i >= p.cen_lo && i < p.cen_hi) acc3[2] += a2;
         } else {
             const double2 nx = (j + 1 < L) ? x[(j + 1 < L) ? j + 1 : 0] : xnext;
-            sx = fma(2.0 * tab[(j * CS + BA + 1) * G + lane].x, x[j].x * nx.x + x[j].y * nx.y, sx);
+            acc3[1] = fma(2.0 * tab[(j * CS + BA + 1) * G + g].x, x[j].x * nx.x + x[j].y * nx.y, acc3[1]);
         }
     }
-    nrm = warp_sum(nrm); sx = warp_sum(sx); if (do_cen) cen = warp_sum(cen);
-    const double s = 1.0 / sqrt(nrm) / sqrt(p.w);          // normalize(): Q:259-263, H:197-201
+    traj_reduce<3, MULTI>(acc3, red, red_phase, wq, nwarps, lane, bar_id, G);
+    const double s = 1.0 / sqrt(acc3[0]) / sqrt(p.w);      // normalize(): Q:259-263, H:197-201
     const double s2 = s * s;
-    sc_out = s; xbar_out = p.w * sx * s2;
-    __syncwarp();
-    if (lane == 0) {
+    sc_out = s; xbar_out = p.w * acc3[1] * s2;
+    traj_sync<MULTI>(bar_id, G);                           // the whole result is in U
+    if (g == 0) {
         double bl = 0.0, br = 0.0;                          // check_boundary_error (Q:559-565, H:403-407, I:422-426) on the normalised state
         for (int k = 0; k < p.fail_len; k++) {
             const double2 hi = U[lidx<L>(n - 1 - k, Gp)]; br += hi.x * hi.x + hi.y * hi.y;
@@ -403,7 +432,7 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
         }
         int f = iflag[0];
         if (bl * s2 > p.fail_thr2 || br * s2 > p.fail_thr2) f |= QC_FLAG_FAIL;
-        if (VAR == QC_QUARTIC && p.cen_hi > p.cen_lo) { if (1.0 - p.w * cen * s2 > 0.5) f |= QC_FLAG_ESCAPED; }
+        if (VAR == QC_QUARTIC && p.cen_hi > p.cen_lo) { if (1.0 - p.w * acc3[2] * s2 > 0.5) f |= QC_FLAG_ESCAPED; }
         iflag[0] = f;
     }
 }
@@ -435,6 +464,7 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     double2* tab = U + (size_t)NBUF * LB;                                // [L][CS][G] factor rows of this trajectory's force (TABS)
     double* nz = reinterpret_cast<double*>(base + ((size_t)NBUF * LB + (TABS ? (size_t)CS * L * G : 0)) * sizeof(double2));
     double* red = reinterpret_cast<double*>(base + p.tstride - 128 - 2 * QC_MAXRED * nwarps * sizeof(double));
+    double2* mbox = reinterpret_cast<double2*>(base + p.tstride - 128 - 2 * QC_MAXRED * nwarps * sizeof(double) - 2 * nwarps * 4 * sizeof(double2));
     double* scal = reinterpret_cast<double*>(base + p.tstride - 128);
     int* iflag = reinterpret_cast<int*>(scal + 8);   // [0] latched flags
     int red_phase = 0;
@@ -714,13 +744,13 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
             for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(v1[j].x + hw[j].x, v1[j].y + hw[j].y) : mk2(0.0, 0.0);
             sweep_h0<VAR, L, MULTI>(ops, b0, w, hw, g, G, Gp, bar_id);
             // psi~ = acc + H0 w0: right-hand side of the implicit solve
-            constexpr bool JAC = (GC == 32) && TABS;
-            if (JAC && p.jacobi) {
+            if (TABS && p.jacobi) {
                 double2 rhs[L];
 #pragma unroll
                 for (int j = 0; j < L; j++) rhs[j] = valid[j] ? mk2(acc[j].x + hw[j].x, acc[j].y + hw[j].y) : mk2(0.0, 0.0);
-                if (!(p.debug & 1)) solve_traj_jacobi<VAR, L>(p, rhs, U, tab, iflag, g, G, Gp, sc, xbar);
-                __syncwarp();
+                // Fock: the last sweep published w0 in U and its halo readers must be done before the solver overwrites U
+                if constexpr (VAR != QC_QUARTIC) traj_sync<MULTI>(bar_id, G);
+                if (!(p.debug & 1)) solve_traj_jacobi<VAR, L, MULTI>(p, rhs, U, tab, mbox, red, red_phase, iflag, g, G, Gp, bar_id, sc, xbar);
             } else {
                 // For the grid b0 == V so U's last readers (sweep 4) are behind a barrier; for Fock b0 == U: its halo readers must finish first.
                 if constexpr (VAR != QC_QUARTIC) traj_sync<MULTI>(bar_id, G);

@@ -71,7 +71,7 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             cudaFuncAttributes fa;
             if (cudaFuncGetAttributes(&fa, (const void*)ke->fn) != cudaSuccess) { err = std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(cudaGetLastError()); return QC_ERR_CUDA; }
             const int NP = G * L;
-            int tstride = nbuf * L * Gp * 16 + (tabs ? CS * L * G * 16 : 0) + n_sub * 16 + 2 * QC_MAXRED * (G / 32) * 8 + 128;
+            int tstride = nbuf * L * Gp * 16 + (tabs ? CS * L * G * 16 : 0) + n_sub * 16 + 2 * QC_MAXRED * (G / 32) * 8 + 2 * (G / 32) * 4 * 16 + 128;
             tstride = (tstride + 15) / 16 * 16;
             int Tmax = ke->maxt / G;
             Tmax = std::min(Tmax, 65536 / std::max(1, fa.numRegs * G));
@@ -85,13 +85,15 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             // solver geometry: P lanes of the trajectory's first warp, `mult` columns (mult*L points) each, warm-up W rounded up to whole columns
             const int cols = (n + L - 1) / L;
             int W = (W_needed + L - 1) / L * L;
+            // chunk-Jacobi solve (factor rows in registers, one column per lane, all G lanes) whenever the tables are shared-memory resident
+            const bool jac = tabs && W <= (guard - 1) * L && forceP <= 0 && env_int("QCART_JACOBI", G == 32 ? 1 : 0);   // multi-warp trajectories: the barrier per pass costs more than it saves (measured)
             int P = forceP > 0 ? std::min(forceP, 32) : 32;
             if (W > (guard - 1) * L) { P = 1; }                               // decay too slow for the guard band: sequential solve
             int mult = (cols + P - 1) / P;
             P = (cols + mult - 1) / mult;
             if (P == 1) { W = 0; mult = cols; }
-            plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = mult * L; plan.W = W;
-            plan.jacobi = (ke->gc == 32 && tabs && mult == 1 && P > 1 && env_int("QCART_JACOBI", 1)) ? 1 : 0;
+            if (jac) { P = cols; mult = 1; }
+            plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = mult * L; plan.W = W; plan.jacobi = jac ? 1 : 0;
             plan.NP = NP; plan.threads = T * G; plan.tstride = tstride; plan.smem_bytes = T * tstride; plan.gc = ke->gc; plan.maxt = ke->maxt; plan.tabs = tabs != 0;
             snprintf(plan.info, sizeof(plan.info), "sse_step_kernel<var=%d,L=%d,gc=%d,maxt=%d,tabs=%d> T=%d G=%d P=%d chunk=%d W=%d jac=%d threads=%d smem=%d regs=%d lmem=%d",
                      var, L, ke->gc, ke->maxt, tabs, T, G, P, plan.chunk, plan.W, plan.jacobi, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
