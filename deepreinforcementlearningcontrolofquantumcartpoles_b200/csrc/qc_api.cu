@@ -44,6 +44,7 @@ struct qc_sim {
     // single-trajectory shim state
     BatchView one; int32_t* d_slot1 = nullptr; double* d_noise1 = nullptr; double* d_out1 = nullptr;  // d_out1: moments[20] aux[4] q[16] xm[16]
     unsigned char* d_flag1 = nullptr;
+    int32_t* d_order = nullptr; int32_t* d_order_count = nullptr; int64_t order_cap = 0;
     int64_t launches = 0;
     std::string info;
 };
@@ -131,7 +132,7 @@ extern "C" int qc_destroy(qc_sim* s) {
     cudaSetDevice(s->device);
     cudaFree(s->raw_x); cudaFree(s->raw_hd); cudaFree(s->raw_h2); cudaFree(s->d_fac); cudaFree(s->d_slot_force); cudaFree(s->d_herm);
     cudaFree(s->batch.psi); cudaFree(s->batch.step); cudaFree(s->batch.flags);
-    cudaFree(s->d_action); cudaFree(s->d_noise); cudaFree(s->d_mom); cudaFree(s->d_aux); cudaFree(s->d_flagout);
+    cudaFree(s->d_order); cudaFree(s->d_order_count); cudaFree(s->d_action); cudaFree(s->d_noise); cudaFree(s->d_mom); cudaFree(s->d_aux); cudaFree(s->d_flagout);
     cudaFree(s->one.psi); cudaFree(s->one.step); cudaFree(s->one.flags); cudaFree(s->d_slot1); cudaFree(s->d_noise1); cudaFree(s->d_out1); cudaFree(s->d_flag1);
     if (s->stream) cudaStreamDestroy(s->stream);
     cudaGetLastError();
@@ -263,13 +264,24 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
     }
     const LaunchPlan& pl = b.plan;
     StepParams p; memset(&p, 0, sizeof(p));
+    if (pl.binned) {
+        const int64_t need = b.B + (int64_t)s->cap_slots * pl.T + 16;
+        if (s->order_cap < need) {
+            cudaFree(s->d_order); cudaFree(s->d_order_count); s->d_order = nullptr; s->d_order_count = nullptr; s->order_cap = 0;
+            QC_CUDA(cudaMalloc(&s->d_order, sizeof(int32_t) * need)); QC_CUDA(cudaMalloc(&s->d_order_count, sizeof(int32_t)));
+            s->order_cap = need;
+        }
+        if (launch_bin(slot_dev, (int)b.B, s->n_slots, pl.T, s->d_order, s->d_order_count, stream)) return fail(QC_ERR_CUDA, "bin kernel launch failed");
+        s->launches++;
+        p.order = s->d_order; p.order_count = s->d_order_count; p.shared_tab = 1;
+    }
     p.n = m.n; p.B = (int)b.B; p.T = pl.T; p.G = pl.G; p.P = pl.P; p.chunk = pl.chunk; p.W = pl.W; p.NP = pl.NP; p.n_sub = n_sub;
     p.K = m.K; p.M = m.cfg.moment_order; p.tstride = pl.tstride; p.variant = m.cfg.variant; p.ba = m.ba; p.herm_mode = m.cfg.herm_mode;
     p.half = m.half; p.fail_len = m.fail_len; p.cen_lo = m.cen_lo; p.cen_hi = m.cen_hi;
     p.w = m.w; p.kappa = m.kappa; p.dt = m.cfg.dt; p.gamma = m.cfg.gamma; p.fail_thr2 = m.fail_thr * m.fail_thr; p.h = m.cfg.grid_size;
     for (int k = 0; k < 4; k++) { p.tk[k] = (m.cfg.variant == QC_QUARTIC) ? m.hoff[k] : 0.0; p.pk[k] = m.pk[k]; }
     p.x = s->raw_x + 8; p.hdiag = s->raw_hd + 8; p.h2 = s->raw_h2 ? s->raw_h2 + 8 : nullptr;
-    p.fac = s->d_fac; p.slot_force = s->d_slot_force; p.slot = slot_dev; p.order = nullptr; p.n_slots = s->n_slots; p.herm_tab = s->d_herm;
+    p.fac = s->d_fac; p.slot_force = s->d_slot_force; p.slot = slot_dev; p.n_slots = s->n_slots; p.herm_tab = s->d_herm;
     p.psi = b.psi; p.noise = noise; p.seed = s->seed; p.traj_offset = s->traj_offset; p.step_count = b.step; p.nsub_traj = nsub_traj;
     p.moments = moments; p.aux = aux; p.flags_out = flags; p.flags_latch = b.flags; p.q_out = q_out; p.xmean_out = xmean_out;
     p.moments_only = moments_only; p.jacobi = pl.jacobi;

@@ -63,7 +63,9 @@ struct StepParams {
     const double2* fac;      // [slots][n][ba+1]
     const double* slot_force;// [slots]
     const int32_t* slot;     // [B] slot per trajectory
-    const int32_t* order;    // [B] work list (null = identity)
+    const int32_t* order;    // binned work list: trajectory id or -1 per position (null = identity)
+    const int32_t* order_count; // device scalar: number of valid positions in `order`
+    int shared_tab;          // 1: one factor table per CTA (binned by slot) instead of one per trajectory
     const double* herm_tab;  // inverted harmonic, herm_mode 0/1: [slots][n][11] = {K_ii, K[i][i-1..i-10]}, K = Im(C)
     int n_slots;
     // state
@@ -81,12 +83,13 @@ struct StepParams {
 
 struct LaunchPlan {
     int L, T, G, P, chunk, W, NP, threads, smem_bytes, tstride, maxt, gc;
-    bool tabs; int jacobi;
+    bool tabs; int jacobi; int binned; int smem_cta_extra;
     char info[240];
 };
 
 int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan, std::string& err);
 int launch_step(const LaunchPlan& plan, const StepParams& p, void* stream, std::string& err);
+int launch_bin(const int32_t* slot, int B, int n_slots, int T, int32_t* order, int32_t* order_count, void* stream);
 int launch_init_packets(double2* psi, int B, int n, double h, int half, const double* k, const double* mean, double stdv, void* stream);
 int launch_init_fock(double2* psi, int B, int n, const double* alpha, void* stream);
 int measure_fp64_peak(int device, double* flops);

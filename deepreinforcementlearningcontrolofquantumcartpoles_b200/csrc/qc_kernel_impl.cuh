@@ -451,18 +451,25 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     const int lane = tid & 31, nwarps = G >> 5;
     const int t = (tid >> 5) % p.T, wq = (tid >> 5) / p.T, g = wq * 32 + lane;
     const int bar_id = 1 + t;
+    // Work list: without binning position == trajectory.  With binning (p.order) trajectories are grouped by factor slot (= force level),
+    // every CTA holds trajectories of ONE slot (bins padded with -1) and stages that slot's factor table once for all of them.
     const int pos = blockIdx.x * p.T + t;
-    const bool have = pos < p.B;
-    const int traj = have ? (p.order ? p.order[pos] : pos) : 0;
+    int traj_ = pos;
+    bool have_ = pos < p.B;
+    if (p.order) { const int npos = *p.order_count; have_ = pos < npos; if (have_) { traj_ = p.order[pos]; have_ = traj_ >= 0; } }
+    const bool have = have_;
+    const int traj = have ? traj_ : 0;
 
-    unsigned char* base = smem + (size_t)t * p.tstride;
+    constexpr int CS_ = SolveTraits<VAR>::CS;
+    const size_t tab_bytes = (size_t)CS_ * L * G * sizeof(double2);
+    unsigned char* base = smem + (p.shared_tab ? tab_bytes : 0) + (size_t)t * p.tstride;
     double2* U = reinterpret_cast<double2*>(base);
     double2* V = U + LB;
     double2* X3 = V + LB;                                                // Fock only (plan allocates it)
     constexpr int NBUF = (VAR == QC_QUARTIC) ? 2 : 3;
     constexpr int CS = SolveTraits<VAR>::CS, BAs = SolveTraits<VAR>::BA;
-    double2* tab = U + (size_t)NBUF * LB;                                // [L][CS][G] factor rows of this trajectory's force (TABS)
-    double* nz = reinterpret_cast<double*>(base + ((size_t)NBUF * LB + (TABS ? (size_t)CS * L * G : 0)) * sizeof(double2));
+    double2* tab = p.shared_tab ? reinterpret_cast<double2*>(smem) : U + (size_t)NBUF * LB;   // [L][CS][G] factor rows of this trajectory's force (TABS)
+    double* nz = reinterpret_cast<double*>(base + ((size_t)NBUF * LB + ((TABS && !p.shared_tab) ? (size_t)CS * L * G : 0)) * sizeof(double2));
     double* red = reinterpret_cast<double*>(base + p.tstride - 128 - 2 * QC_MAXRED * nwarps * sizeof(double));
     double2* mbox = reinterpret_cast<double2*>(base + p.tstride - 128 - 2 * QC_MAXRED * nwarps * sizeof(double) - 2 * nwarps * 4 * sizeof(double2));
     double* scal = reinterpret_cast<double*>(base + p.tstride - 128);
@@ -519,13 +526,36 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     if (g == 0) iflag[0] = have ? (int)p.flags_latch[traj] : 0;
     const double2* __restrict__ fac = p.fac + (size_t)slot * n * (BAs + 1);
     if (TABS) {
-        for (int i = g; i < p.NP; i += G) {
-            const int jj = i % L, cc = i / L;
+        if (p.shared_tab) {
+            // all trajectories of the CTA use the same slot: find it (first present trajectory) and stage its table with the whole CTA
+            __shared__ int cta_slot;
+            if (tid == 0) {
+                int sl = 0;
+                const int npos = *p.order_count;
+                for (int q = 0; q < p.T; q++) { const int ps = blockIdx.x * p.T + q; if (ps < npos && p.order[ps] >= 0) { sl = min(max(p.slot[p.order[ps]], 0), p.n_slots - 1); break; } }
+                cta_slot = sl;
+            }
+            __syncthreads();
+            const double2* __restrict__ fs = p.fac + (size_t)cta_slot * n * (BAs + 1);
+            for (int i = tid; i < p.NP; i += blockDim.x) {
+                const int jj = i % L, cc = i / L;
 #pragma unroll
-            for (int k = 0; k < CS; k++) {
-                double2 v = mk2(0.0, 0.0);
-                if (have && i < n) { if (k <= BAs) v = __ldg(&fac[(size_t)i * (BAs + 1) + k]); else if (VAR != QC_QUARTIC) v = mk2(__ldg(&p.x[i]), 0.0); }
-                tab[(jj * CS + k) * G + cc] = v;
+                for (int k = 0; k < CS; k++) {
+                    double2 v = mk2(0.0, 0.0);
+                    if (i < n) { if (k <= BAs) v = __ldg(&fs[(size_t)i * (BAs + 1) + k]); else if (VAR != QC_QUARTIC) v = mk2(__ldg(&p.x[i]), 0.0); }
+                    tab[(jj * CS + k) * G + cc] = v;
+                }
+            }
+            __syncthreads();
+        } else {
+            for (int i = g; i < p.NP; i += G) {
+                const int jj = i % L, cc = i / L;
+#pragma unroll
+                for (int k = 0; k < CS; k++) {
+                    double2 v = mk2(0.0, 0.0);
+                    if (have && i < n) { if (k <= BAs) v = __ldg(&fac[(size_t)i * (BAs + 1) + k]); else if (VAR != QC_QUARTIC) v = mk2(__ldg(&p.x[i]), 0.0); }
+                    tab[(jj * CS + k) * G + cc] = v;
+                }
             }
         }
     }

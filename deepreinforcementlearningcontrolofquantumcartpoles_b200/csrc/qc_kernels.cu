@@ -28,16 +28,45 @@ static std::vector<KernEntry> all_kernels() {
 }
 
 // best instance for (variant, L, G): exact compile-time geometry first, else the run-time-G instance; smallest launch bound that fits
-static const KernEntry* find_kernel(int var, int L, int G, int threads_needed, bool tabs, int force_gc = -1) {
+static const KernEntry* find_kernel(int var, int L, int G, int threads_needed, bool tabs, int force_gc = -1, int exact_maxt = 0) {
     static const std::vector<KernEntry> ks = all_kernels();
     const KernEntry* best = nullptr;
     for (int pass = 0; pass < 2 && !best; pass++) {
         const int want_gc = (pass == 0) ? G : 0;
         if (force_gc >= 0 && want_gc != force_gc) continue;
         for (const KernEntry& e : ks)
-            if (e.var == var && e.L == L && e.gc == want_gc && e.tabs == tabs && e.maxt >= threads_needed && (!best || e.maxt < best->maxt)) best = &e;
+            if (e.var == var && e.L == L && e.gc == want_gc && e.tabs == tabs && e.maxt >= threads_needed && (exact_maxt == 0 || e.maxt == exact_maxt) &&
+                (!best || e.maxt < best->maxt)) best = &e;
     }
     return best;
+}
+
+// Counting sort of the trajectories by factor slot (force level), every bin padded with -1 to a multiple of T positions so that a CTA
+// never mixes slots.  One CTA; B is at most a few 10^5.
+__global__ void bin_by_slot_kernel(const int32_t* __restrict__ slot, int B, int n_slots, int T, int32_t* __restrict__ order, int32_t* __restrict__ order_count) {
+    extern __shared__ int sh[];            // hist[n_slots], offs[n_slots], cursor[n_slots]
+    int* hist = sh; int* offs = sh + n_slots; int* cur = sh + 2 * n_slots;
+    __shared__ int total;
+    for (int s = threadIdx.x; s < n_slots; s += blockDim.x) { hist[s] = 0; cur[s] = 0; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < B; i += blockDim.x) atomicAdd(&hist[min(max(slot[i], 0), n_slots - 1)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int o = 0;
+        for (int s = 0; s < n_slots; s++) { offs[s] = o; o += (hist[s] + T - 1) / T * T; }
+        total = o; *order_count = o;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += blockDim.x) order[i] = -1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const int s = min(max(slot[i], 0), n_slots - 1);
+        order[offs[s] + atomicAdd(&cur[s], 1)] = i;
+    }
+}
+int launch_bin(const int32_t* slot, int B, int n_slots, int T, int32_t* order, int32_t* order_count, void* stream) {
+    bin_by_slot_kernel<<<1, 1024, 3 * n_slots * sizeof(int), (cudaStream_t)stream>>>(slot, B, n_slots, T, order, order_count);
+    return cudaGetLastError() == cudaSuccess ? QC_OK : QC_ERR_CUDA;
 }
 
 static int env_int(const char* name, int dflt) { const char* s = getenv(name); return (s && *s) ? atoi(s) : dflt; }
@@ -65,7 +94,11 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
         const int guard = (40 + L - 1) / L + 1, Gp = G + 2 * guard;
         for (int tabs = 1; tabs >= 0; tabs--) {
             if (forceTabs >= 0 && tabs != forceTabs) continue;
-            const KernEntry* ke = find_kernel(var, L, G, G, tabs != 0, forceGC);
+            // instance choice (measured): one-warp trajectories run best with the 255-register instance (the in-register Jacobi solve);
+            // multi-warp trajectories with the 168-register one (more trajectories resident per SM)
+            const int pref_maxt = env_int("QCART_MAXT", 0) ? env_int("QCART_MAXT", 0) : ((G == 32) ? 256 : 384);
+            const KernEntry* ke = find_kernel(var, L, G, G, tabs != 0, forceGC, pref_maxt);
+            if (!ke && !env_int("QCART_MAXT", 0)) ke = find_kernel(var, L, G, G, tabs != 0, forceGC, 0);
             if (!ke) continue;
             if (pass == 0 && ke->maxt >= 1024) continue;
             cudaFuncAttributes fa;
@@ -73,15 +106,21 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             const int NP = G * L;
             int tstride = nbuf * L * Gp * 16 + (tabs ? CS * L * G * 16 : 0) + n_sub * 16 + 2 * QC_MAXRED * (G / 32) * 8 + 2 * (G / 32) * 4 * 16 + 128;
             tstride = (tstride + 15) / 16 * 16;
+            // binned mode (large batches): trajectories are grouped by force level, the factor table is staged once per CTA
+            const int tab_bytes = CS * L * G * 16;
+            const int want_bin = env_int("QCART_BIN", -1);
+            bool binned = tabs && (want_bin == 1 || (want_bin < 0 && B >= 8 * n_sm && B >= 64 * m.cfg.n_levels));
+            int tstride_b = tstride - tab_bytes;
             int Tmax = ke->maxt / G;
             Tmax = std::min(Tmax, 65536 / std::max(1, fa.numRegs * G));
-            Tmax = std::min(Tmax, (smem_max - 1024) / tstride);
+            Tmax = std::min(Tmax, binned ? (smem_max - 1024 - tab_bytes) / tstride_b : (smem_max - 1024) / tstride);
             Tmax = std::min(Tmax, 15);
             if (Tmax < 1) continue;
             int T = forceT;
-            if (T <= 0) { const int per_sm = (B + n_sm - 1) / n_sm; T = std::max(1, std::min(per_sm, 8)); }   // small batch: one even wave
-            if (tabs && Tmax < std::min(T, 2) && forceTabs < 0) continue;     // tables would squeeze the CTA too much: use the global-table variant
+            if (T <= 0) { const int per_sm = (B + n_sm - 1) / n_sm; T = std::max(1, std::min(per_sm, 8)); if (binned && G > 32) T = std::min(Tmax, 4); }   // small batch: one even wave
+            if (tabs && !binned && Tmax < std::min(T, 2) && forceTabs < 0) continue;     // tables would squeeze the CTA too much: use the global-table variant
             T = std::min(T, Tmax);
+            if (binned) { tstride = tstride_b; }
             // solver geometry: P lanes of the trajectory's first warp, `mult` columns (mult*L points) each, warm-up W rounded up to whole columns
             const int cols = (n + L - 1) / L;
             int W = (W_needed + L - 1) / L * L;
@@ -94,9 +133,10 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             if (P == 1) { W = 0; mult = cols; }
             if (jac) { P = cols; mult = 1; }
             plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = mult * L; plan.W = W; plan.jacobi = jac ? 1 : 0;
-            plan.NP = NP; plan.threads = T * G; plan.tstride = tstride; plan.smem_bytes = T * tstride; plan.gc = ke->gc; plan.maxt = ke->maxt; plan.tabs = tabs != 0;
-            snprintf(plan.info, sizeof(plan.info), "sse_step_kernel<var=%d,L=%d,gc=%d,maxt=%d,tabs=%d> T=%d G=%d P=%d chunk=%d W=%d jac=%d threads=%d smem=%d regs=%d lmem=%d",
-                     var, L, ke->gc, ke->maxt, tabs, T, G, P, plan.chunk, plan.W, plan.jacobi, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
+            plan.binned = binned ? 1 : 0; plan.smem_cta_extra = binned ? tab_bytes : 0;
+            plan.NP = NP; plan.threads = T * G; plan.tstride = tstride; plan.smem_bytes = T * tstride + plan.smem_cta_extra; plan.gc = ke->gc; plan.maxt = ke->maxt; plan.tabs = tabs != 0;
+            snprintf(plan.info, sizeof(plan.info), "sse_step_kernel<var=%d,L=%d,gc=%d,maxt=%d,tabs=%d> T=%d G=%d P=%d chunk=%d W=%d jac=%d bin=%d threads=%d smem=%d regs=%d lmem=%d",
+                     var, L, ke->gc, ke->maxt, tabs, T, G, P, plan.chunk, plan.W, plan.jacobi, plan.binned, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
             return QC_OK;
         }
     }
@@ -105,13 +145,13 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
 }
 
 int launch_step(const LaunchPlan& plan, const StepParams& p, void* stream, std::string& err) {
-    const KernEntry* ke = find_kernel(p.variant, plan.L, plan.G, plan.maxt, plan.tabs, plan.gc);
+    const KernEntry* ke = find_kernel(p.variant, plan.L, plan.G, plan.maxt, plan.tabs, plan.gc, plan.maxt);
     if (!ke) { err = "kernel not found"; return QC_ERR_UNSUPPORTED; }
     kern_t fn = ke->fn;
     if (cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess) {
         err = std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(cudaGetLastError()); return QC_ERR_CUDA;
     }
-    const int grid = (p.B + plan.T - 1) / plan.T;
+    const int grid = (p.B + plan.T - 1) / plan.T + (plan.binned ? p.n_slots : 0);     // binned: every bin may add one partly filled CTA
     fn<<<grid, plan.threads, plan.smem_bytes, (cudaStream_t)stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("kernel launch: ") + cudaGetErrorString(e) + " [" + plan.info + "]"; return QC_ERR_CUDA; }

@@ -8,7 +8,7 @@ from common import TASKS, oracle_for, initial_states, oracle_control_step, fock_
 from deepreinforcementlearningcontrolofquantumcartpoles_b200 import configs, BatchedSim, _lib as L
 
 def one(task, B, n_sub, env):
-    for k in ("QCART_L", "QCART_T", "QCART_P"):
+    for k in ("QCART_L", "QCART_T", "QCART_P", "QCART_BIN", "QCART_JACOBI"):
         os.environ.pop(k, None)
     os.environ.update(env)
     params = configs.PRESETS[task](); params["n_sub"] = n_sub
@@ -43,6 +43,8 @@ if __name__ == "__main__":
             cases.append((task, 9, 8, {"QCART_L": Lv}))
         cases.append((task, 9, 8, {"QCART_P": "1"}))
         cases.append((task, 9, 8, {"QCART_T": "1"}))
+        cases.append((task, 40, 8, {"QCART_BIN": "1", "QCART_T": "3"}))
+        cases.append((task, 40, 8, {"QCART_BIN": "1", "QCART_T": "2", "QCART_JACOBI": "0"}))
     for c in cases:
         try:
             one(*c)

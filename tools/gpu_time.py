@@ -10,7 +10,7 @@ from deepreinforcementlearningcontrolofquantumcartpoles_b200 import configs, Bat
 FLOPS = {"harmonic": 1.80e6, "inverted_harmonic": 5.28e6, "quartic": 7.81e6, "inverted_quartic": 47.5e6}
 
 def run(task, B, env, steps=20, check=False):
-    for k in ("QCART_L", "QCART_T", "QCART_P", "QCART_TABS", "QCART_GC", "QCART_JACOBI"):
+    for k in ("QCART_L", "QCART_T", "QCART_P", "QCART_TABS", "QCART_GC", "QCART_JACOBI", "QCART_BIN", "QCART_MAXT"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
     params = configs.PRESETS[task]()
