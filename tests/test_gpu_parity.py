@@ -282,3 +282,30 @@ def test_reference_build_fixture_through_the_abi(task):
     if "quartic" in task:
         m = out["moments"].cpu().numpy()
         assert np.max(np.abs(m - g[task + "_moments"]) / np.maximum(np.abs(g[task + "_moments"]), 1e-3)) < TOL_STEP
+
+
+def test_force_binning_is_bitwise_neutral(monkeypatch):
+    """Large batches are grouped by force level so that a CTA stages one factor table for all its trajectories (QCART_BIN).  The grouping
+    only changes which trajectories share a CTA: every output must be bitwise identical to the un-binned launch."""
+    torch = _torch()
+    params = configs.inverted_quartic(n_sub=6)
+    B = 300
+    psi0 = initial_states(params, B, 3)
+    rng = np.random.default_rng(1)
+    actions = rng.integers(0, 21, B).astype(np.int32)
+    actions[:40] = 7                                    # a bin that is not a multiple of the CTA size, plus sparse bins
+    noise = rng.standard_normal((B, 6, 2))
+    res = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("QCART_BIN", mode)
+        sim = BatchedSim(params, batch=B)
+        sim.set_state(psi0)
+        out = sim.step(torch.as_tensor(actions, device="cuda"), noise=torch.as_tensor(noise, device="cuda"))
+        torch.cuda.synchronize()
+        assert ("bin=%s" % mode) in sim.kernel_info()
+        res.append((sim.get_state(), out["moments"].cpu().numpy(), out["aux"].cpu().numpy(), out["flags"].cpu().numpy()))
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    orc = oracle_for(params)
+    ref, _, _ = oracle_control_step(orc, params, psi0[:8], actions[:8], noise[:8])
+    assert rel_err(res[1][0][:8], ref) < TOL_STEP
