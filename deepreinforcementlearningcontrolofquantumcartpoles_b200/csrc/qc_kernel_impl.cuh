@@ -164,8 +164,25 @@ __device__ __forceinline__ void sweep_h0(const LaneOps<VAR, L>& ops, double2* __
     double2 ext[L + 2 * HB];
 #pragma unroll
     for (int r = -HB; r < L + HB; r++) ext[r + HB] = (r >= 0 && r < L) ? w[r] : ld_rel<L>(buf, g, Gp, r);
+    if constexpr (VAR == QC_QUARTIC) {
+        // "vertical" order: all 2L accumulation chains advance together (ILP for a warp that is alone on its scheduler)
+        double re[L], im[L];
 #pragma unroll
-    for (int j = 0; j < L; j++) hw[j] = ops.h0(ext, j);
+        for (int j = 0; j < L; j++) { re[j] = ops.dg[j] * ext[j + HB].x; im[j] = ops.dg[j] * ext[j + HB].y; }
+#pragma unroll
+        for (int k = 1; k <= 4; k++) {
+#pragma unroll
+            for (int j = 0; j < L; j++) {
+                re[j] = fma(ops.tk[k - 1], ext[j + HB - k].x + ext[j + HB + k].x, re[j]);
+                im[j] = fma(ops.tk[k - 1], ext[j + HB - k].y + ext[j + HB + k].y, im[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < L; j++) hw[j] = mk2(re[j], im[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < L; j++) hw[j] = ops.h0(ext, j);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -303,7 +320,7 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
                                                   double2* __restrict__ mbox, double* red, int& red_phase, int* iflag, int g, int G, int Gp, int bar_id,
                                                   double& sc_out, double& xbar_out) {
     constexpr int BA = SolveTraits<VAR>::BA, CS = SolveTraits<VAR>::CS, GUARD = Guard<L>::v;
-    const int n = p.n, K = p.W / L + 1;
+    const int n = p.n, K = (p.debug & 4) ? 1 : ((p.debug & 8) ? 3 : p.W / L + 1);      // debug bits 4/8: timing experiments only (wrong results)
     const int lane = g & 31, wq = g >> 5, nwarps = G >> 5;
     double2 lr[L][BA], dinv[L];
 #pragma unroll
@@ -316,61 +333,94 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
     // shared mailbox + the trajectory's named barrier between warps.  Lane 0 of the trajectory needs no masking in the forward sweep: the
     // factor entries that would multiply a value from before the first point are zero.  The last lane's incoming pending updates are
     // forced to zero (there is no lane behind it).
+    // Both sweeps are written in "scatter" form inside the chunk: as soon as an unknown is final, its contributions to the (at most BA)
+    // later rows are subtracted from their accumulators -- 2 BA independent two-FMA chains per step.  With in-order issue and one or two
+    // warps per scheduler this matters: the gather form (one 2 BA-deep dependent chain per step) ran 3x slower (profiles/README.md).
     // ---- forward: L y = rhs --------------------------------------------------------------------------------------
-    double2 y[L], h[BA];
+    double2 y[L], h[BA];                                            // h[m] = y_{-1-m}: last values of the previous lane(s)
 #pragma unroll
-    for (int k = 0; k < BA; k++) h[k] = mk2(0.0, 0.0);              // h[k] = y_{i-1-k}
+    for (int k = 0; k < BA; k++) h[k] = mk2(0.0, 0.0);
     for (int it = 0; it < K; it++) {
+        double2 acc[L];
 #pragma unroll
-        for (int j = 0; j < L; j++) {
-            double re = rhs[j].x, im = rhs[j].y;
+        for (int j = 0; j < L; j++) acc[j] = rhs[j];
 #pragma unroll
-            for (int k = BA - 1; k >= 0; k--) {
-                re = fma(-lr[j][k].x, h[k].x, re); re = fma(lr[j][k].y, h[k].y, re);
-                im = fma(-lr[j][k].x, h[k].y, im); im = fma(-lr[j][k].y, h[k].x, im);
+        for (int j = 0; j < L && j < BA; j++) {                     // boundary gather: rows that still see the incoming history
+            double pr[BA], pi[BA];                                  // independent complex products, then a short sum (not one long chain)
+#pragma unroll
+            for (int k = j; k < BA; k++) {
+                pr[k] = fma(lr[j][k].y, h[k - j].y, -lr[j][k].x * h[k - j].x);
+                pi[k] = fma(-lr[j][k].y, h[k - j].x, -lr[j][k].x * h[k - j].y);
             }
+            double sr = 0.0, si = 0.0;
 #pragma unroll
-            for (int k = BA - 1; k > 0; k--) h[k] = h[k - 1];
-            h[0] = mk2(re, im);
-            y[j] = h[0];
+            for (int k = j + 1; k < BA; k++) { sr += pr[k]; si += pi[k]; }       // far terms (available early)
+            acc[j].x += sr + pr[j]; acc[j].y += si + pi[j];
+        }
+#pragma unroll
+        for (int j = 0; j < L; j++) {                               // in-chunk scatter
+            y[j] = acc[j];
+#pragma unroll
+            for (int k = 0; k < BA; k++) {
+                const int t = j + 1 + k;
+                if (t < L) {
+                    acc[t].x = fma(-lr[t][k].x, y[j].x, acc[t].x); acc[t].x = fma(lr[t][k].y, y[j].y, acc[t].x);
+                    acc[t].y = fma(-lr[t][k].x, y[j].y, acc[t].y); acc[t].y = fma(-lr[t][k].y, y[j].x, acc[t].y);
+                }
+            }
         }
         if (it + 1 < K) {
+            double2 ho[BA];                                          // outgoing history: my last values, then (L < BA) the tail of what I received
+#pragma unroll
+            for (int m = 0; m < BA; m++) ho[m] = (m < L) ? y[(m < L) ? L - 1 - m : 0] : h[(m >= L) ? m - L : 0];
             if constexpr (MULTI) {
                 double2* mb = mbox + (it & 1) * (nwarps * BA);
                 if (lane == 31) {
 #pragma unroll
-                    for (int k = 0; k < BA; k++) mb[wq * BA + k] = h[k];
+                    for (int k = 0; k < BA; k++) mb[wq * BA + k] = ho[k];
                 }
                 traj_sync<true>(bar_id, G);
 #pragma unroll
                 for (int k = 0; k < BA; k++) {
                     const double2 up = (wq > 0) ? mb[(wq - 1) * BA + k] : mk2(0.0, 0.0);
-                    const double sx_ = __shfl_up_sync(0xffffffffu, h[k].x, 1), sy_ = __shfl_up_sync(0xffffffffu, h[k].y, 1);
+                    const double sx_ = __shfl_up_sync(0xffffffffu, ho[k].x, 1), sy_ = __shfl_up_sync(0xffffffffu, ho[k].y, 1);
                     h[k] = (lane == 0) ? up : mk2(sx_, sy_);
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < BA; k++) { h[k].x = __shfl_up_sync(0xffffffffu, h[k].x, 1); h[k].y = __shfl_up_sync(0xffffffffu, h[k].y, 1); }
+                for (int k = 0; k < BA; k++) { h[k].x = __shfl_up_sync(0xffffffffu, ho[k].x, 1); h[k].y = __shfl_up_sync(0xffffffffu, ho[k].y, 1); }
             }
         }
     }
-    // ---- z = D^{-1} y, backward: L^T x = z (column oriented) ------------------------------------------------------------
-    double2 z[L], x[L], pend[BA];
+    // ---- z = D^{-1} y, backward: L^T x = z -----------------------------------------------------------------------------
+    double2 z[L], x[L], pin[BA];                                     // pin[m] = pending update of my row L-1-m from the rows behind my chunk
 #pragma unroll
     for (int j = 0; j < L; j++) z[j] = mk2(y[j].x * dinv[j].x - y[j].y * dinv[j].y, y[j].x * dinv[j].y + y[j].y * dinv[j].x);
 #pragma unroll
-    for (int k = 0; k < BA; k++) pend[k] = mk2(0.0, 0.0);
+    for (int k = 0; k < BA; k++) pin[k] = mk2(0.0, 0.0);
     const bool last_lane = (g == G - 1);
     for (int it = 0; it < K; it++) {
+        double2 acc[L], po[BA];                                      // po[m] = pending update of the row (m+1) positions before my first row
+#pragma unroll
+        for (int j = 0; j < L; j++) acc[j] = z[j];
+#pragma unroll
+        for (int m = 0; m < BA; m++) {
+            if (m < L) { acc[(m < L) ? L - 1 - m : 0].x += pin[m].x; acc[(m < L) ? L - 1 - m : 0].y += pin[m].y; }
+            po[m] = (m + L < BA) ? pin[(m + L < BA) ? m + L : 0] : mk2(0.0, 0.0);      // (L < BA) updates that only pass through my chunk
+        }
 #pragma unroll
         for (int j = L - 1; j >= 0; j--) {
-            const double xr = z[j].x + pend[0].x, xi = z[j].y + pend[0].y;
-            x[j] = mk2(xr, xi);
+            x[j] = acc[j];
 #pragma unroll
             for (int k = 0; k < BA; k++) {
-                const double pr = (k + 1 < BA) ? pend[k + 1].x : 0.0, pi = (k + 1 < BA) ? pend[k + 1].y : 0.0;
-                pend[k].x = fma(-xr, lr[j][k].x, fma(xi, lr[j][k].y, pr));
-                pend[k].y = fma(-xr, lr[j][k].y, fma(-xi, lr[j][k].x, pi));
+                const int t = j - 1 - k;
+                if (t >= 0) {
+                    acc[t].x = fma(-x[j].x, lr[j][k].x, fma(x[j].y, lr[j][k].y, acc[t].x));
+                    acc[t].y = fma(-x[j].x, lr[j][k].y, fma(-x[j].y, lr[j][k].x, acc[t].y));
+                } else {
+                    po[-t - 1].x = fma(-x[j].x, lr[j][k].x, fma(x[j].y, lr[j][k].y, po[-t - 1].x));
+                    po[-t - 1].y = fma(-x[j].x, lr[j][k].y, fma(-x[j].y, lr[j][k].x, po[-t - 1].y));
+                }
             }
         }
         if (it + 1 < K) {
@@ -378,26 +428,26 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
                 double2* mb = mbox + (it & 1) * (nwarps * BA);
                 if (lane == 0) {
 #pragma unroll
-                    for (int k = 0; k < BA; k++) mb[wq * BA + k] = pend[k];
+                    for (int k = 0; k < BA; k++) mb[wq * BA + k] = po[k];
                 }
                 traj_sync<true>(bar_id, G);
 #pragma unroll
                 for (int k = 0; k < BA; k++) {
                     const double2 dn = (wq + 1 < nwarps) ? mb[(wq + 1) * BA + k] : mk2(0.0, 0.0);
-                    const double sx_ = __shfl_down_sync(0xffffffffu, pend[k].x, 1), sy_ = __shfl_down_sync(0xffffffffu, pend[k].y, 1);
-                    pend[k] = (lane == 31) ? dn : mk2(sx_, sy_);
+                    const double sx_ = __shfl_down_sync(0xffffffffu, po[k].x, 1), sy_ = __shfl_down_sync(0xffffffffu, po[k].y, 1);
+                    pin[k] = (lane == 31) ? dn : mk2(sx_, sy_);
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < BA; k++) {
-                    const double sx_ = __shfl_down_sync(0xffffffffu, pend[k].x, 1), sy_ = __shfl_down_sync(0xffffffffu, pend[k].y, 1);
-                    pend[k] = last_lane ? mk2(0.0, 0.0) : mk2(sx_, sy_);
+                    const double sx_ = __shfl_down_sync(0xffffffffu, po[k].x, 1), sy_ = __shfl_down_sync(0xffffffffu, po[k].y, 1);
+                    pin[k] = last_lane ? mk2(0.0, 0.0) : mk2(sx_, sy_);
                 }
             }
         }
     }
     // ---- result -> shared line (halos of the next substep), norm, <x>, escape probability, Fail -----------------------------
-    double acc3[3] = {0.0, 0.0, 0.0};                     // norm, sum for <x>, centre probability
+    double acc5[5] = {0.0, 0.0, 0.0, 0.0, 0.0};           // norm, sum for <x>, centre probability, low / high boundary norms
     const bool do_cen = (VAR == QC_QUARTIC) && (p.cen_hi > p.cen_lo);
 #pragma unroll
     for (int j = 0; j < L; j++) U[j * Gp + GUARD + g] = x[j];
@@ -409,32 +459,29 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
 #pragma unroll
     for (int j = 0; j < L; j++) {
         const double a2 = x[j].x * x[j].x + x[j].y * x[j].y;
-        acc3[0] += a2;
+        acc5[0] += a2;
         const int i = g * L + j;
         if constexpr (VAR == QC_QUARTIC) {
-            acc3[1] = fma(p.h * (double)(i - p.half), a2, acc3[1]);
-            if (do_cen && i >= p.cen_lo && i < p.cen_hi) acc3[2] += a2;
+            acc5[1] = fma(p.h * (double)(i - p.half), a2, acc5[1]);
+            if (do_cen && i >= p.cen_lo && i < p.cen_hi) acc5[2] += a2;
+            if (i < p.fail_len) acc5[3] += a2;
         } else {
             const double2 nx = (j + 1 < L) ? x[(j + 1 < L) ? j + 1 : 0] : xnext;
-            acc3[1] = fma(2.0 * tab[(j * CS + BA + 1) * G + g].x, x[j].x * nx.x + x[j].y * nx.y, acc3[1]);
+            acc5[1] = fma(2.0 * tab[(j * CS + BA + 1) * G + g].x, x[j].x * nx.x + x[j].y * nx.y, acc5[1]);
         }
+        if (i >= n - p.fail_len && i < n) acc5[4] += a2;
     }
-    traj_reduce<3, MULTI>(acc3, red, red_phase, wq, nwarps, lane, bar_id, G);
-    const double s = 1.0 / sqrt(acc3[0]) / sqrt(p.w);      // normalize(): Q:259-263, H:197-201
+    traj_reduce<5, MULTI>(acc5, red, red_phase, wq, nwarps, lane, bar_id, G);
+    const double s = rsqrt(acc5[0] * p.w);                 // normalize(): psi / (||psi||_2 sqrt(w))   (Q:259-263, H:197-201)
     const double s2 = s * s;
-    sc_out = s; xbar_out = p.w * acc3[1] * s2;
-    traj_sync<MULTI>(bar_id, G);                           // the whole result is in U
+    sc_out = s; xbar_out = p.w * acc5[1] * s2;
     if (g == 0) {
-        double bl = 0.0, br = 0.0;                          // check_boundary_error (Q:559-565, H:403-407, I:422-426) on the normalised state
-        for (int k = 0; k < p.fail_len; k++) {
-            const double2 hi = U[lidx<L>(n - 1 - k, Gp)]; br += hi.x * hi.x + hi.y * hi.y;
-            if (VAR == QC_QUARTIC) { const double2 lo = U[lidx<L>(k, Gp)]; bl += lo.x * lo.x + lo.y * lo.y; }
-        }
-        int f = iflag[0];
-        if (bl * s2 > p.fail_thr2 || br * s2 > p.fail_thr2) f |= QC_FLAG_FAIL;
-        if (VAR == QC_QUARTIC && p.cen_hi > p.cen_lo) { if (1.0 - p.w * acc3[2] * s2 > 0.5) f |= QC_FLAG_ESCAPED; }
+        int f = iflag[0];                                  // check_boundary_error (Q:559-565, H:403-407, I:422-426) on the normalised state
+        if (acc5[3] * s2 > p.fail_thr2 || acc5[4] * s2 > p.fail_thr2) f |= QC_FLAG_FAIL;
+        if (VAR == QC_QUARTIC && p.cen_hi > p.cen_lo) { if (1.0 - p.w * acc5[2] * s2 > 0.5) f |= QC_FLAG_ESCAPED; }
         iflag[0] = f;
     }
+    traj_sync<MULTI>(bar_id, G);                           // the whole result is in U
 }
 
 // ------------------------------------------------------------------------------------------------------
