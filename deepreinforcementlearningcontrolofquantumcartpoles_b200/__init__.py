@@ -4,6 +4,7 @@ Public surface:
   BatchedSim           one libqcart handle: set_state / step / get_moments on B trajectories (sim.py)
   QuantumCartpoleEnv   reset/step environment API with the reference's observation, reward and termination rules (env.py)
   simulation           drop-in mirror of the reference's compiled `simulation` module (simulation.py)
+  controllers          analytic controllers (LQG / damping / semiclassical) + 21-level quantisation from the GPU moment block (controllers.py)
   configs              the four task presets + the grid-size sweep (configs.py)
 The CUDA library (csrc/, built to libqcart.so) is required: there is no CPU fallback.
 """
@@ -12,5 +13,6 @@ from ._lib import QcartError, LIB_PATH  # noqa: F401
 from .sim import BatchedSim, philox_normals, measure_peaks, make_config  # noqa: F401
 from .env import QuantumCartpoleEnv  # noqa: F401
 from . import simulation  # noqa: F401
+from . import controllers  # noqa: F401
 
 __all__ = ["BatchedSim", "QuantumCartpoleEnv", "simulation", "configs", "philox_normals", "measure_peaks", "QcartError"]

@@ -170,6 +170,29 @@ def make_reference_build_fixture():
     print("wrote reference_build_control_step.npz")
 
 
+def make_controller_fixture():
+    """Outputs of the reference's analytic controllers (quartic oscillator/controllers.py), extracted by AST and run unmodified."""
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200 import configs
+    from common import initial_states
+    params = configs.quartic()
+    n = 171
+    g, ns = grid_reference("quartic oscillator", params["x_max"], n, params["lambda_"], params["mass"])
+    extract_functions(os.path.join(REF, "quartic oscillator", "main_parallel.py"), ["x_2_expct", "xpx_expct"], ns)
+    ns.update({"x_2": g["x_2"], "lambda_": params["lambda_"], "mass": params["mass"], "control_time": 1.0 / 18, "controls_per_unit_time": 18,
+               "sqrt": __import__("math").sqrt})
+    extract_functions(os.path.join(REF, "quartic oscillator", "controllers.py"), ["steepest_descent", "LinearQuadratic", "Gaussian_approx"], ns)
+    rng = np.random.default_rng(3)
+    psi = initial_states(params, 8, seed=13)
+    psi = psi * (1 + 0.3 * np.cos(0.7 * g["x"])[None, :])            # make them non-Gaussian (non-zero third moments)
+    psi /= np.sqrt(np.sum(np.abs(psi) ** 2, axis=1, keepdims=True) * params["grid_size"])
+    out = {"states": psi,
+           "damping": np.array([ns["steepest_descent"](s, damping=0.5) for s in psi]),
+           "lqg": np.array([ns["LinearQuadratic"](s, k=params["lambda_"] * 2.0) for s in psi]),
+           "semiclassical": np.array([ns["Gaussian_approx"](s) for s in psi])}
+    np.savez_compressed(os.path.join(HERE, "controllers_reference_python.npz"), **out)
+    print("wrote controllers_reference_python.npz")
+
+
 if __name__ == "__main__":
     from deepreinforcementlearningcontrolofquantumcartpoles_b200 import configs
     make_grid_fixture("grid_reference_python_quartic.npz", "quartic oscillator", configs.quartic())
@@ -177,3 +200,4 @@ if __name__ == "__main__":
     make_fock_fixture()
     make_oracle_fixture()
     make_reference_build_fixture()
+    make_controller_fixture()
