@@ -111,6 +111,33 @@ def cpu_port_rate(task, params, n_traj_per_thread, threads, fast=True):
     return threads * n_traj_per_thread / dt, dt
 
 
+def reference_build_call_pattern(task, params, n_ctrl=3):
+    """The reference's own simulation*.cpp (built against the MKL-API shim, oracle/_ref) driven the way the reference drives it:
+    one Python->C call per substep, force change (-> its reset_ab) once per control step.  Single process; the reference runs one such
+    process per core.  Informational: the shim is slower than real MKL, so this is NOT the baseline the speed-up is quoted against."""
+    try:
+        import numpy as np
+        from oracle.ref_module import RefModule, available
+        if not available(task):
+            return None
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from common import initial_states, level_force
+        ref = RefModule(task)
+        psi = initial_states(params, 1, seed=5)[0]
+        rng = np.random.default_rng(1)
+        ref.step(psi, params["dt"], 0.0, params["gamma"], rng.standard_normal(2))
+        t0 = time.perf_counter()
+        for c in range(n_ctrl):
+            F = level_force(params, int(rng.integers(0, params["n_levels"])))
+            for s in range(params["n_sub"]):
+                ref.step(psi, params["dt"], F, params["gamma"], rng.standard_normal(2))
+        dt = time.perf_counter() - t0
+        return {"value_per_core": n_ctrl / dt, "unit": "traj-control-steps/s", "kind": "reference sources + MKL-API shim, Python call per substep (as shipped)",
+                "sample": "%d control steps, 1 process" % n_ctrl}
+    except Exception as e:      # never let the informational leg break the bench
+        return {"error": repr(e)}
+
+
 def run_reference(args, task, params):
     """--impl reference: the reference's own CPU algorithm for the path on all host cores.  The MKL original cannot be built
     here (no MKL), so this is the oracle port (kind "port"); each step = a bounded sample of the workload."""
@@ -296,7 +323,8 @@ def main():
         v, secs = cpu_port_rate(task, params, per_thread, cores)
         cpu_baseline = {"value": v, "unit": "traj-control-steps/s", "cores": cores, "kind": "port",
                         "sample": "%d threads x %d trajectories x 1 control step (%d substeps, N=%d) in %.1f s; oracle/sse_oracle.c built -Ofast (the reference's flag), "
-                                  "per-force refactorisation included as in the reference" % (cores, per_thread, params["n_sub"], n, secs)}
+                                  "per-force refactorisation included as in the reference" % (cores, per_thread, params["n_sub"], n, secs),
+                        "reference_build_as_shipped": reference_build_call_pattern(task, params)}
 
     line = {"metric": "trajectory-control-steps/sec", "value": value, "unit": "traj-control-steps/s", "n_gpus": world, "steps": K_steps,
             "warmup": W_steps, "ms_per_step": ms_total / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     // ---- per-lane constants -------------------------------------------------------------------------------
     LaneOps<VAR, L> ops;
     double xs[(VAR == QC_QUARTIC) ? L : 1];      // grid: x_j
+    double xs2[(VAR == QC_QUARTIC) ? L : 1];     // grid: x_j^2
     double xl[(VAR == QC_QUARTIC) ? 1 : L + 3];  // Fock: xl_r, r in [-2, L]  (index r+2)
     bool valid[L];
 #pragma unroll
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
         const int i = g * L + j;
         valid[j] = have && (i < n);
         if constexpr (VAR == QC_QUARTIC) {
-            xs[j] = valid[j] ? __ldg(&p.x[i]) : 0.0;
+            xs[j] = valid[j] ? __ldg(&p.x[i]) : 0.0; xs2[j] = xs[j] * xs[j];
             ops.dg[j] = valid[j] ? (__ldg(&p.hdiag[i]) - p.kappa * F * xs[j]) : 0.0;
         } else {
             ops.dg[j] = valid[j] ? __ldg(&p.hdiag[i]) : 0.0;
@@ -654,40 +655,54 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
                 double2 ext[L + 8];
 #pragma unroll
                 for (int r = -4; r < L + 4; r++) { const double2 c = ld_rel<L>(U, g, Gp, r); ext[r + 4] = mk2(sc * c.x, sc * c.y); }
+                // All per-point factors below are quadratics in x_j whose coefficients depend only on per-substep scalars: evaluate them as
+                // c0 + c1 x + c2 x^2 (2 FMA) instead of rebuilding (x - <x>) powers per point.
+                const double Q0 = g4 * xbar * xbar, Q1 = -2.0 * g4 * xbar, G0 = -gs * xbar;
                 double m[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                 for (int j = 0; j < L; j++) {
                     psi[j] = ext[j + 4];
                     const double2 h = ops.h0(ext, j);
-                    const double d = xs[j] - xbar, d2g = g4 * d * d;
+                    const double x = xs[j], x2 = xs2[j];
+                    const double d2g = fma(Q1, x, fma(g4, x2, Q0));                 // gamma/4 (x-<x>)^2
+                    const double gsd = fma(gs, x, G0);                              // sqrt(gamma/2) (x-<x>)
                     // a = -i H0 psi - gamma/4 (x-<x>)^2 psi      (D1, Q:434-449)
-                    a[j] = valid[j] ? mk2(h.y - d2g * psi[j].x, -h.x - d2g * psi[j].y) : mk2(0.0, 0.0);
-                    const double bx_ = gs * d * psi[j].x, by_ = gs * d * psi[j].y;         // b = sqrt(gamma/2)(x-<x>) psi   (D2, Q:473-486)
+                    a[j] = valid[j] ? mk2(fma(-d2g, psi[j].x, h.y), fma(-d2g, psi[j].y, -h.x)) : mk2(0.0, 0.0);
+                    const double bx_ = gsd * psi[j].x, by_ = gsd * psi[j].y;        // b = sqrt(gamma/2)(x-<x>) psi   (D2, Q:473-486)
                     const double ux = fma(dt, a[j].x, psi[j].x), uy = fma(dt, a[j].y, psi[j].y);
                     const double ypx = fma(sdt, bx_, ux), ypy = fma(sdt, by_, uy), ymx = fma(-sdt, bx_, ux), ymy = fma(-sdt, by_, uy);   // Y+-  (Q:589-594)
-                    const double p2 = ypx * ypx + ypy * ypy, m2 = ymx * ymx + ymy * ymy;
-                    const double xp2 = xs[j] * p2;
-                    m[0] += xp2; m[1] = fma(xs[j], xp2, m[1]); m[2] = fma(xs[j] * xs[j], xp2, m[2]); m[3] = fma(xs[j], m2, m[3]);
+                    const double p2 = fma(ypx, ypx, ypy * ypy), m2 = fma(ymx, ymx, ymy * ymy);
+                    const double xp2 = x * p2;
+                    m[0] += xp2; m[1] = fma(x, xp2, m[1]); m[2] = fma(x2, xp2, m[2]); m[3] = fma(x, m2, m[3]);
                 }
                 traj_reduce<4, MULTI>(m, red, red_phase, wq, nwarps, lane, bar_id, G);
                 // un-normalised <x> of Y+, Y- (D1ImRe, Q:457-460) and of Phi+- = Y+ (1 +- sig (x - <x>_Y+)) (Q:605-615,479-482)
                 const double xbp = p.w * m[0], xbm = p.w * m[3];
                 const double t1 = m[1] - xbp * m[0], t2 = m[2] - 2.0 * xbp * m[1] + xbp * xbp * m[0];
                 const double xfp = p.w * (m[0] + 2.0 * sig * t1 + sig * sig * t2), xfm = p.w * (m[0] - 2.0 * sig * t1 + sig * sig * t2);
-                const double cvb = 2.0 * sdt * (k1 - k6) * gs, cvp = 2.0 * k2;
+                // psi~ - (linear H0 terms) = cpsi psi + cP Y+ + cM Y-   (all multipliers real on the grid), v1 = -i cv psi:
+                //   cpsi = 1 + (dW - 2 k4) gs d - 2 k2 g4 d^2,                     d  = x - <x>
+                //   cP   = -(k1+k2) g4 dp^2 + (k3+k4-k5) gs dp + k5 gs ((x-xfp)(1+sig dp) - (x-xfm)(1-sig dp)),   dp = x - <x>_Y+
+                //   cM   = (k1-k2) g4 dm^2 + (k4-k3+k5) gs dm,                     dm = x - <x>_Y-
+                //   cv   = 2 sdt (k1-k6) gs d + 2 k2
+                const double al = (dW - 2.0 * k4) * gs, be = 2.0 * k2 * g4;
+                const double A2 = -be, A1 = fma(2.0 * be, xbar, al), A0 = 1.0 - al * xbar - be * xbar * xbar;
+                const double c1 = (k1 + k2) * g4, c2 = (k3 + k4 - k5) * gs, c3 = k5 * gs, c3s = c3 * sig, sf = xfp + xfm;
+                const double P2 = 2.0 * c3s - c1, P1 = 2.0 * c1 * xbp + c2 - c3s * (sf + 2.0 * xbp);
+                const double P0 = -c1 * xbp * xbp - c2 * xbp + c3 * (xfm - xfp) + c3s * xbp * sf;
+                const double c4 = (k1 - k2) * g4, c5 = (k4 - k3 + k5) * gs;
+                const double M2 = c4, M1 = c5 - 2.0 * c4 * xbm, M0 = c4 * xbm * xbm - c5 * xbm;
+                const double V1 = 2.0 * sdt * (k1 - k6) * gs, V0 = 2.0 * k2 - V1 * xbar;
 #pragma unroll
                 for (int j = 0; j < L; j++) {
-                    const double x = xs[j], d = x - xbar, dp = x - xbp, dm = x - xbm;
-                    const double bx_ = gs * d * psi[j].x, by_ = gs * d * psi[j].y;
+                    const double x = xs[j], x2 = xs2[j];
+                    const double gsd = fma(gs, x, G0);
+                    const double bx_ = gsd * psi[j].x, by_ = gsd * psi[j].y;
                     const double ux = fma(dt, a[j].x, psi[j].x), uy = fma(dt, a[j].y, psi[j].y);
                     const double ypx = fma(sdt, bx_, ux), ypy = fma(sdt, by_, uy), ymx = fma(-sdt, bx_, ux), ymy = fma(-sdt, by_, uy);
-                    // psi~ - (linear H0 terms) = cpsi psi + cP Y+ + cM Y-   (all multipliers real on the grid)
-                    const double cpsi = 1.0 + (dW - 2.0 * k4) * gs * d - 2.0 * k2 * g4 * d * d;
-                    const double php = 1.0 + sig * dp, phm = 1.0 - sig * dp;
-                    const double cP = -(k1 + k2) * g4 * dp * dp + (k3 + k4 - k5) * gs * dp + k5 * gs * ((x - xfp) * php - (x - xfm) * phm);
-                    const double cM = (k1 - k2) * g4 * dm * dm + (k4 - k3 + k5) * gs * dm;
-                    acc[j] = mk2(cpsi * psi[j].x + cP * ypx + cM * ymx, cpsi * psi[j].y + cP * ypy + cM * ymy);
-                    const double cv = cvb * d + cvp;                                       // v1 = -i (cvb b/gs... ) see header
+                    const double cpsi = fma(A2, x2, fma(A1, x, A0)), cP = fma(P2, x2, fma(P1, x, P0)), cM = fma(M2, x2, fma(M1, x, M0));
+                    acc[j] = mk2(fma(cM, ymx, fma(cP, ypx, cpsi * psi[j].x)), fma(cM, ymy, fma(cP, ypy, cpsi * psi[j].y)));
+                    const double cv = fma(V1, x, V0);
                     v1[j] = mk2(cv * psi[j].y, -cv * psi[j].x);
                 }
             } else {
