@@ -45,6 +45,7 @@ struct qc_sim {
     BatchView one; int32_t* d_slot1 = nullptr; double* d_noise1 = nullptr; double* d_out1 = nullptr;  // d_out1: moments[20] aux[4] q[16] xm[16]
     unsigned char* d_flag1 = nullptr;
     int32_t* d_order = nullptr; int32_t* d_order_count = nullptr; int64_t order_cap = 0;
+    double2* d_vglobal = nullptr; size_t vglobal_cap = 0;
     int64_t launches = 0;
     std::string info;
 };
@@ -132,7 +133,7 @@ extern "C" int qc_destroy(qc_sim* s) {
     cudaSetDevice(s->device);
     cudaFree(s->raw_x); cudaFree(s->raw_hd); cudaFree(s->raw_h2); cudaFree(s->d_fac); cudaFree(s->d_slot_force); cudaFree(s->d_herm);
     cudaFree(s->batch.psi); cudaFree(s->batch.step); cudaFree(s->batch.flags);
-    cudaFree(s->d_order); cudaFree(s->d_order_count); cudaFree(s->d_action); cudaFree(s->d_noise); cudaFree(s->d_mom); cudaFree(s->d_aux); cudaFree(s->d_flagout);
+    cudaFree(s->d_vglobal); cudaFree(s->d_order); cudaFree(s->d_order_count); cudaFree(s->d_action); cudaFree(s->d_noise); cudaFree(s->d_mom); cudaFree(s->d_aux); cudaFree(s->d_flagout);
     cudaFree(s->one.psi); cudaFree(s->one.step); cudaFree(s->one.flags); cudaFree(s->d_slot1); cudaFree(s->d_noise1); cudaFree(s->d_out1); cudaFree(s->d_flag1);
     if (s->stream) cudaStreamDestroy(s->stream);
     cudaGetLastError();
@@ -264,10 +265,16 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
     }
     const LaunchPlan& pl = b.plan;
     StepParams p; memset(&p, 0, sizeof(p));
+    if (pl.vglobal) {
+        const size_t ntraj = (size_t)((b.B + pl.T - 1) / pl.T + s->cap_slots) * pl.T;
+        const size_t need_v = ntraj * (size_t)pl.vglobal_elems_per_traj;
+        if (s->vglobal_cap < need_v) { cudaFree(s->d_vglobal); s->d_vglobal = nullptr; s->vglobal_cap = 0; QC_CUDA(cudaMalloc(&s->d_vglobal, sizeof(double2) * need_v)); s->vglobal_cap = need_v; }
+        p.vglobal = s->d_vglobal;
+    }
     if (pl.binned) {
         const int64_t need = b.B + (int64_t)s->cap_slots * pl.T + 16;
         if (s->order_cap < need) {
-            cudaFree(s->d_order); cudaFree(s->d_order_count); s->d_order = nullptr; s->d_order_count = nullptr; s->order_cap = 0;
+            cudaFree(s->d_vglobal); cudaFree(s->d_order); cudaFree(s->d_order_count); s->d_order = nullptr; s->d_order_count = nullptr; s->order_cap = 0;
             QC_CUDA(cudaMalloc(&s->d_order, sizeof(int32_t) * need)); QC_CUDA(cudaMalloc(&s->d_order_count, sizeof(int32_t)));
             s->order_cap = need;
         }

@@ -70,6 +70,7 @@ struct StepParams {
     int n_slots;
     // state
     double2* psi;            // [B][n]
+    double2* vglobal;        // optional: second line buffer(s) in global memory, [grid*T][(NBUF-1)*L*Gp] (largest grids only)
     const double* noise;     // [B][n_sub][2] or null
     unsigned long long seed; long long traj_offset;
     long long* step_count;   // [B]
@@ -83,7 +84,7 @@ struct StepParams {
 
 struct LaunchPlan {
     int L, T, G, P, chunk, W, NP, threads, smem_bytes, tstride, maxt, gc;
-    bool tabs; int jacobi; int binned; int smem_cta_extra;
+    bool tabs; int jacobi; int binned; int smem_cta_extra; int vglobal; long long vglobal_elems_per_traj;
     char info[240];
 };
 

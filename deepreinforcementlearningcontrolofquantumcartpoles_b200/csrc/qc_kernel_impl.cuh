@@ -511,12 +511,14 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     const size_t tab_bytes = (size_t)CS_ * L * G * sizeof(double2);
     unsigned char* base = smem + (p.shared_tab ? tab_bytes : 0) + (size_t)t * p.tstride;
     double2* U = reinterpret_cast<double2*>(base);
-    double2* V = U + LB;
+    // Largest grids (two lines no longer fit 227 KB): the second line lives in global memory (p.vglobal, L2 resident); bar.sync orders it.
+    double2* V = p.vglobal ? p.vglobal + (size_t)(blockIdx.x * p.T + t) * LB : U + LB;
     double2* X3 = V + LB;                                                // Fock only (plan allocates it)
     constexpr int NBUF = (VAR == QC_QUARTIC) ? 2 : 3;
     constexpr int CS = SolveTraits<VAR>::CS, BAs = SolveTraits<VAR>::BA;
-    double2* tab = p.shared_tab ? reinterpret_cast<double2*>(smem) : U + (size_t)NBUF * LB;   // [L][CS][G] factor rows of this trajectory's force (TABS)
-    double* nz = reinterpret_cast<double*>(base + ((size_t)NBUF * LB + ((TABS && !p.shared_tab) ? (size_t)CS * L * G : 0)) * sizeof(double2));
+    const int nbuf_s = p.vglobal ? 1 : NBUF;                             // line buffers that live in shared memory
+    double2* tab = p.shared_tab ? reinterpret_cast<double2*>(smem) : U + (size_t)nbuf_s * LB;   // [L][CS][G] factor rows of this trajectory's force (TABS)
+    double* nz = reinterpret_cast<double*>(base + ((size_t)nbuf_s * LB + ((TABS && !p.shared_tab) ? (size_t)CS * L * G : 0)) * sizeof(double2));
     double* red = reinterpret_cast<double*>(base + p.tstride - 128 - 2 * QC_MAXRED * nwarps * sizeof(double));
     double2* mbox = reinterpret_cast<double2*>(base + p.tstride - 128 - 2 * QC_MAXRED * nwarps * sizeof(double) - 2 * nwarps * 4 * sizeof(double2));
     double* scal = reinterpret_cast<double*>(base + p.tstride - 128);
@@ -562,7 +564,8 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     }
 
     // ---- prologue: state -> shared line U, noise table, initial <x> ----------------------------------------
-    for (int e = g; e < NBUF * LB; e += G) U[e] = mk2(0.0, 0.0);       // lines incl. guard columns (U, V, X3 are contiguous)
+    for (int e = g; e < nbuf_s * LB; e += G) U[e] = mk2(0.0, 0.0);     // lines incl. guard columns (U, V, X3 are contiguous)
+    if (p.vglobal) { for (int e = g; e < (NBUF - 1) * LB; e += G) V[e] = mk2(0.0, 0.0); }
     traj_sync<MULTI>(bar_id, G);
     for (int i = g; i < n; i += G) { if (have) U[lidx<L>(i, Gp)] = p.psi[(size_t)traj * n + i]; }
     for (int s = g; s < my_nsub; s += G) {

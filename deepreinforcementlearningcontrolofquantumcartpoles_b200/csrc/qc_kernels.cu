@@ -106,6 +106,10 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             const int NP = G * L;
             int tstride = nbuf * L * Gp * 16 + (tabs ? CS * L * G * 16 : 0) + n_sub * 16 + 2 * QC_MAXRED * (G / 32) * 8 + 2 * (G / 32) * 4 * 16 + 128;
             tstride = (tstride + 15) / 16 * 16;
+            bool vglobal = false;
+            if (!tabs && tstride > smem_max - 1024) {        // largest grids: keep only the first line in shared memory
+                tstride -= (nbuf - 1) * L * Gp * 16; vglobal = true;
+            }
             // binned mode (large batches): trajectories are grouped by force level, the factor table is staged once per CTA
             const int tab_bytes = CS * L * G * 16;
             const int want_bin = env_int("QCART_BIN", -1);
@@ -133,6 +137,7 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             if (P == 1) { W = 0; mult = cols; }
             if (jac) { P = cols; mult = 1; }
             plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = mult * L; plan.W = W; plan.jacobi = jac ? 1 : 0;
+            plan.vglobal = vglobal ? 1 : 0; plan.vglobal_elems_per_traj = (long long)(nbuf - 1) * L * Gp;
             plan.binned = binned ? 1 : 0; plan.smem_cta_extra = binned ? tab_bytes : 0;
             plan.NP = NP; plan.threads = T * G; plan.tstride = tstride; plan.smem_bytes = T * tstride + plan.smem_cta_extra; plan.gc = ke->gc; plan.maxt = ke->maxt; plan.tabs = tabs != 0;
             snprintf(plan.info, sizeof(plan.info), "sse_step_kernel<var=%d,L=%d,gc=%d,maxt=%d,tabs=%d> T=%d G=%d P=%d chunk=%d W=%d jac=%d bin=%d threads=%d smem=%d regs=%d lmem=%d",

@@ -186,9 +186,9 @@ def test_arbitrary_force_values():
         assert np.linalg.norm(got[b] - st) / np.linalg.norm(st) < TOL_STEP
 
 
-@pytest.mark.parametrize("npts,env", [(257, {}), (513, {}), (1025, {}), (2049, {}), (4097, {})])
+@pytest.mark.parametrize("npts,env", [(257, {}), (513, {}), (1025, {}), (2049, {}), (4097, {}), (8193, {})])
 def test_grid_size_sweep(npts, env):
-    """BASELINE.json config 5: x_max 13, N points, dt ~ h^2; tolerance check vs the oracle at every N the resident kernel supports."""
+    """BASELINE.json config 5: x_max 13, N points, dt ~ h^2; tolerance check vs the oracle at every N of the sweep (257 ... 8193)."""
     torch = _torch()
     params = configs.quartic_sweep(npts, n_sub=3)
     B = 2
