@@ -68,6 +68,7 @@ struct StepParams {
     int shared_tab;          // 1: one factor table per CTA (binned by slot) instead of one per trajectory
     const double* herm_tab;  // inverted harmonic, herm_mode 0/1: [slots][n][11] = {K_ii, K[i][i-1..i-10]}, K = Im(C)
     int n_slots;
+    int herm_smem;           // 1: the Im C band is staged in shared memory next to the factor table (binned launches)
     // state
     double2* psi;            // [B][n]
     double2* vglobal;        // optional: second line buffer(s) in global memory, [grid*T][(NBUF-1)*L*Gp] (largest grids only)
@@ -84,7 +85,7 @@ struct StepParams {
 
 struct LaunchPlan {
     int L, T, G, P, chunk, W, NP, threads, smem_bytes, tstride, maxt, gc;
-    bool tabs; int jacobi; int binned; int smem_cta_extra; int vglobal; long long vglobal_elems_per_traj;
+    bool tabs; int jacobi; int binned; int smem_cta_extra; int vglobal; long long vglobal_elems_per_traj; int herm_smem;
     char info[240];
 };
 

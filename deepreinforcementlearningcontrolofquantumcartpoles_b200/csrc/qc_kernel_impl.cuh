@@ -508,17 +508,21 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     const int traj = have ? traj_ : 0;
 
     constexpr int CS_ = SolveTraits<VAR>::CS;
-    const size_t tab_bytes = (size_t)CS_ * L * G * sizeof(double2);
+    // factor table [L][CS][G] complex (+ inverted harmonic: band of Im C, [L][11][G] real, for the HERMITIAN-descriptor term)
+    constexpr int HT = (VAR == QC_INV_HARMONIC) ? 11 : 0;
+    const size_t tab_bytes = (size_t)CS_ * L * G * sizeof(double2) + (p.herm_smem ? (size_t)HT * L * G * sizeof(double) : 0);
     unsigned char* base = smem + (p.shared_tab ? tab_bytes : 0) + (size_t)t * p.tstride;
     double2* U = reinterpret_cast<double2*>(base);
     // Largest grids (two lines no longer fit 227 KB): the second line lives in global memory (p.vglobal, L2 resident); bar.sync orders it.
     double2* V = p.vglobal ? p.vglobal + (size_t)(blockIdx.x * p.T + t) * LB : U + LB;
     double2* X3 = V + LB;                                                // Fock only (plan allocates it)
-    constexpr int NBUF = (VAR == QC_QUARTIC) ? 2 : 3;
+    double2* A4 = X3 + LB;                                               // inverted harmonic only
+    constexpr int NBUF = (VAR == QC_QUARTIC) ? 2 : ((VAR == QC_INV_HARMONIC) ? 4 : 3);   // U, V, [X3: Y-], [A4: a, for the HERMITIAN-descriptor term]
     constexpr int CS = SolveTraits<VAR>::CS, BAs = SolveTraits<VAR>::BA;
     const int nbuf_s = p.vglobal ? 1 : NBUF;                             // line buffers that live in shared memory
     double2* tab = p.shared_tab ? reinterpret_cast<double2*>(smem) : U + (size_t)nbuf_s * LB;   // [L][CS][G] factor rows of this trajectory's force (TABS)
-    double* nz = reinterpret_cast<double*>(base + ((size_t)nbuf_s * LB + ((TABS && !p.shared_tab) ? (size_t)CS * L * G : 0)) * sizeof(double2));
+    double* nz = reinterpret_cast<double*>(base + (size_t)nbuf_s * LB * sizeof(double2) + ((TABS && !p.shared_tab) ? tab_bytes : 0));
+    double* khs = reinterpret_cast<double*>(tab + (size_t)CS * L * G);    // shared copy of the Im C band (TABS, inverted harmonic)
     double* red = reinterpret_cast<double*>(base + p.tstride - 128 - 2 * QC_MAXRED * nwarps * sizeof(double));
     double2* mbox = reinterpret_cast<double2*>(base + p.tstride - 128 - 2 * QC_MAXRED * nwarps * sizeof(double) - 2 * nwarps * 4 * sizeof(double2));
     double* scal = reinterpret_cast<double*>(base + p.tstride - 128);
@@ -596,6 +600,12 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
                     if (i < n) { if (k <= BAs) v = __ldg(&fs[(size_t)i * (BAs + 1) + k]); else if (VAR != QC_QUARTIC) v = mk2(__ldg(&p.x[i]), 0.0); }
                     tab[(jj * CS + k) * G + cc] = v;
                 }
+                if constexpr (HT > 0) {
+                    if (p.herm_smem) {
+#pragma unroll
+                        for (int k = 0; k < HT; k++) khs[(jj * HT + k) * G + cc] = (i < n) ? __ldg(&p.herm_tab[((size_t)cta_slot * n + i) * HT + k]) : 0.0;
+                    }
+                }
             }
             __syncthreads();
         } else {
@@ -606,6 +616,12 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
                     double2 v = mk2(0.0, 0.0);
                     if (have && i < n) { if (k <= BAs) v = __ldg(&fac[(size_t)i * (BAs + 1) + k]); else if (VAR != QC_QUARTIC) v = mk2(__ldg(&p.x[i]), 0.0); }
                     tab[(jj * CS + k) * G + cc] = v;
+                }
+                if constexpr (HT > 0) {
+                    if (p.herm_smem) {
+#pragma unroll
+                        for (int k = 0; k < HT; k++) khs[(jj * HT + k) * G + cc] = (have && i < n) ? __ldg(&p.herm_tab[((size_t)slot * n + i) * HT + k]) : 0.0;
+                    }
                 }
             }
         }
@@ -734,7 +750,10 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
                 }
                 // exchange Y+ (-> V) and Y- (-> X3) with halo 2
 #pragma unroll
-                for (int j = 0; j < L; j++) { V[j * Gp + GUARD + g] = yp[j]; X3[j * Gp + GUARD + g] = ym[j]; }
+                for (int j = 0; j < L; j++) {
+                    V[j * Gp + GUARD + g] = yp[j]; X3[j * Gp + GUARD + g] = ym[j];
+                    if constexpr (VAR == QC_INV_HARMONIC) A4[j * Gp + GUARD + g] = a[j];     // left halo of a for the HERMITIAN-descriptor term below
+                }
                 traj_sync<MULTI>(bar_id, G);
                 double2 ype[L + 4], yme[L + 4];
 #pragma unroll
@@ -799,13 +818,9 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
                 // The reference applies the complex-symmetric correction matrix C with a HERMITIAN/UPPER descriptor (I:23,551):
                 // C_herm = C - 2i strict_lower(Im C).  herm_mode 0 reproduces that; 1 additionally drops Im(C_ii); 2 = symmetric (as H:532).
                 if (p.herm_mode != 2) {
-                    traj_sync<MULTI>(bar_id, G);
-#pragma unroll
-                    for (int j = 0; j < L; j++) V[j * Gp + GUARD + g] = a[j];
-                    traj_sync<MULTI>(bar_id, G);
                     double2 ah[L + 10];
 #pragma unroll
-                    for (int r = -10; r < L; r++) ah[r + 10] = (r >= 0) ? a[r] : ld_rel<L>(V, g, Gp, r);
+                    for (int r = -10; r < L; r++) ah[r + 10] = (r >= 0) ? a[r] : ld_rel<L>(A4, g, Gp, r);
                     const double* __restrict__ kt = p.herm_tab + (size_t)slot * n * 11;
 #pragma unroll
                     for (int j = 0; j < L; j++) {
@@ -813,9 +828,12 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
                             const int i = g * L + j;
                             double cr = 0.0, ci = 0.0;
 #pragma unroll
-                            for (int k = 1; k <= 10; k++) { const double c = __ldg(&kt[(size_t)i * 11 + k]); cr = fma(c, ah[j + 10 - k].x, cr); ci = fma(c, ah[j + 10 - k].y, ci); }
+                            for (int k = 1; k <= 10; k++) {
+                                const double c = (TABS && p.herm_smem) ? khs[(j * 11 + k) * G + g] : __ldg(&kt[(size_t)i * 11 + k]);
+                                cr = fma(c, ah[j + 10 - k].x, cr); ci = fma(c, ah[j + 10 - k].y, ci);
+                            }
                             acc[j].x += 2.0 * ci; acc[j].y -= 2.0 * cr;
-                            if (p.herm_mode == 1) { const double kd = __ldg(&kt[(size_t)i * 11]); acc[j].x += kd * a[j].y; acc[j].y -= kd * a[j].x; }
+                            if (p.herm_mode == 1) { const double kd = (TABS && p.herm_smem) ? khs[(j * 11) * G + g] : __ldg(&kt[(size_t)i * 11]); acc[j].x += kd * a[j].y; acc[j].y -= kd * a[j].x; }
                         }
                     }
                 }

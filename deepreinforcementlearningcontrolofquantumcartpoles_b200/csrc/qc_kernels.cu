@@ -76,7 +76,7 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
     int dev = 0; cudaGetDevice(&dev);
     int n_sm = 148; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     int smem_max = 227 * 1024; cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const int nbuf = (var == QC_QUARTIC) ? 2 : 3;
+    const int nbuf = (var == QC_QUARTIC) ? 2 : ((var == QC_INV_HARMONIC) ? 4 : 3);
     const int forceL = env_int("QCART_L", 0), forceT = env_int("QCART_T", 0), forceP = env_int("QCART_P", 0);
     const int forceTabs = env_int("QCART_TABS", -1), forceGC = env_int("QCART_GC", -1);
     const int CS = (var == QC_QUARTIC) ? m.ba + 1 : m.ba + 2;
@@ -104,16 +104,17 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             cudaFuncAttributes fa;
             if (cudaFuncGetAttributes(&fa, (const void*)ke->fn) != cudaSuccess) { err = std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(cudaGetLastError()); return QC_ERR_CUDA; }
             const int NP = G * L;
-            int tstride = nbuf * L * Gp * 16 + (tabs ? CS * L * G * 16 : 0) + n_sub * 16 + 2 * QC_MAXRED * (G / 32) * 8 + 2 * (G / 32) * 4 * 16 + 128;
+            // binned mode (large batches): trajectories are grouped by force level, the factor table is staged once per CTA
+            const int want_bin = env_int("QCART_BIN", -1);
+            const bool binned = tabs && (want_bin == 1 || (want_bin < 0 && B >= 8 * n_sm && B >= 64 * m.cfg.n_levels));
+            const bool herm_smem = binned && var == QC_INV_HARMONIC && m.cfg.herm_mode != 2;     // 17 KB band table: only worth it when shared by a CTA
+            const int tab_bytes = CS * L * G * 16 + (herm_smem ? 11 * L * G * 8 : 0);
+            int tstride = nbuf * L * Gp * 16 + (tabs ? tab_bytes : 0) + n_sub * 16 + 2 * QC_MAXRED * (G / 32) * 8 + 2 * (G / 32) * 4 * 16 + 128;
             tstride = (tstride + 15) / 16 * 16;
             bool vglobal = false;
             if (!tabs && tstride > smem_max - 1024) {        // largest grids: keep only the first line in shared memory
                 tstride -= (nbuf - 1) * L * Gp * 16; vglobal = true;
             }
-            // binned mode (large batches): trajectories are grouped by force level, the factor table is staged once per CTA
-            const int tab_bytes = CS * L * G * 16;
-            const int want_bin = env_int("QCART_BIN", -1);
-            bool binned = tabs && (want_bin == 1 || (want_bin < 0 && B >= 8 * n_sm && B >= 64 * m.cfg.n_levels));
             int tstride_b = tstride - tab_bytes;
             int Tmax = ke->maxt / G;
             Tmax = std::min(Tmax, 65536 / std::max(1, fa.numRegs * G));
@@ -138,7 +139,7 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             if (jac) { P = cols; mult = 1; }
             plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = mult * L; plan.W = W; plan.jacobi = jac ? 1 : 0;
             plan.vglobal = vglobal ? 1 : 0; plan.vglobal_elems_per_traj = (long long)(nbuf - 1) * L * Gp;
-            plan.binned = binned ? 1 : 0; plan.smem_cta_extra = binned ? tab_bytes : 0;
+            plan.binned = binned ? 1 : 0; plan.herm_smem = herm_smem ? 1 : 0; plan.smem_cta_extra = binned ? tab_bytes : 0;
             plan.NP = NP; plan.threads = T * G; plan.tstride = tstride; plan.smem_bytes = T * tstride + plan.smem_cta_extra; plan.gc = ke->gc; plan.maxt = ke->maxt; plan.tabs = tabs != 0;
             snprintf(plan.info, sizeof(plan.info), "sse_step_kernel<var=%d,L=%d,gc=%d,maxt=%d,tabs=%d> T=%d G=%d P=%d chunk=%d W=%d jac=%d bin=%d threads=%d smem=%d regs=%d lmem=%d",
                      var, L, ke->gc, ke->maxt, tabs, T, G, P, plan.chunk, plan.W, plan.jacobi, plan.binned, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
