@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqcart.so")
+LIB_PATH = os.environ.get("QCART_LIB") or os.path.join(_HERE, "libqcart.so")   # QCART_LIB: A/B-test another build of the same ABI
 
 QC_HARMONIC, QC_INV_HARMONIC, QC_QUARTIC = 0, 1, 2
 QC_FLAG_FAIL, QC_FLAG_ESCAPED = 1, 2

@@ -6,20 +6,24 @@
 // (Q = quartic oscillator/simulation_quart.cpp, H = harmonic oscillator/simulation.cpp,
 //  I = inverted harmonic oscillator/simulation_i.cpp under /root/reference/implementation codes/.)
 //
-// Mapping (see DESIGN.md):
+// Mapping (see DESIGN.md section 4):
 //   * a trajectory is owned by G lanes (G = 32*warps); lane g keeps points [g*L, g*L+L) of every live vector
 //     in REGISTERS for the whole control step; the wavefunction crosses HBM only at kernel entry/exit;
 //   * band operators (9-point kinetic stencil / ladder operators) read their halos from a j-major shared-memory
-//     line ( point i -> [(i % L) * G + i / L] ), bank-conflict free for every L, one barrier per sweep;
+//     line with zero guard columns (see Guard<> / lidx below): bank-conflict free for every L, no bounds checks,
+//     one warp- or named barrier per sweep; trajectories of a CTA never synchronise with each other in the substep loop;
 //   * all linear terms of the scheme are merged into ONE Horner chain in H0 = H - kappa F x (5 sweeps):
 //       psi~ = acc + H0 ( v1 + H0 ( c2 a + H0 ( c3 a + H0 ( c4 a + H0 c5 a ) ) ) )
 //     which equals  k(aIm(Y+) - aIm(Y-)) + 2 k2 aIm(psi) + C a  of simple_sum_up because aIm is linear;
-//   * the implicit solve (I + i dt/2 H0) psi' = psi~ is the one serial recurrence: it is done by P "solver" lanes
-//     per trajectory, all T*P of them in warp 0, one lane per contiguous chunk, with the pivot-free L D L^T factors
-//     precomputed per force level.  A lane starts its substitution W points early with zero history: L^{-1} decays
-//     below 1e-18 within W points (measured at create time), so the result equals the sequential solve to round-off;
-//   * norm, <x>, boundary norms and the escape probability are accumulated by the solver lanes in the backward
-//     sweep; the only other reduction per substep is one warp-shuffle butterfly (deterministic, fixed shape).
+//   * the implicit solve (I + i dt/2 H0) psi' = psi~ is the one serial recurrence.  With the pivot-free L D L^T factors precomputed per
+//     force level, L^{-1} decays below 1e-18 within W points (measured at create time), so a substitution that starts W points early
+//     with zero history equals the sequential solve to round-off.  Two formulations of that truncation:
+//       solve_traj_jacobi  one-warp trajectories: factor rows in registers, K = W/L + 1 passes over the lane's own L points,
+//                          boundary values handed to the neighbour lane by shuffle (FP64-issue bound);
+//       solve_traj         multi-warp trajectories: first warp, one contiguous chunk + W warm-up points per lane, factor rows streamed
+//                          from shared memory (shared-memory-bandwidth bound);
+//   * norm, <x>, boundary norms and the escape probability ride on the solver's final reduction; the only other reduction per substep
+//     is one warp-shuffle butterfly (deterministic, fixed shape).
 #pragma once
 #include "qc_internal.h"
 #include <cuda_runtime.h>
@@ -164,8 +168,9 @@ __device__ __forceinline__ void sweep_h0(const LaneOps<VAR, L>& ops, double2* __
     double2 ext[L + 2 * HB];
 #pragma unroll
     for (int r = -HB; r < L + HB; r++) ext[r + HB] = (r >= 0 && r < L) ? w[r] : ld_rel<L>(buf, g, Gp, r);
-    if constexpr (VAR == QC_QUARTIC) {
-        // "vertical" order: all 2L accumulation chains advance together (ILP for a warp that is alone on its scheduler)
+    if constexpr (VAR == QC_QUARTIC && !MULTI) {
+        // "vertical" order: all 2L accumulation chains advance together (ILP for a warp that is alone on its scheduler).  Multi-warp
+        // trajectories run in the register-tight 168-register instances with 3+ warps per scheduler: they keep the point-by-point order.
         double re[L], im[L];
 #pragma unroll
         for (int j = 0; j < L; j++) { re[j] = ops.dg[j] * ext[j + HB].x; im[j] = ops.dg[j] * ext[j + HB].y; }
@@ -514,12 +519,16 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     unsigned char* base = smem + (p.shared_tab ? tab_bytes : 0) + (size_t)t * p.tstride;
     double2* U = reinterpret_cast<double2*>(base);
     // Largest grids (two lines no longer fit 227 KB): the second line lives in global memory (p.vglobal, L2 resident); bar.sync orders it.
-    double2* V = p.vglobal ? p.vglobal + (size_t)(blockIdx.x * p.T + t) * LB : U + LB;
+    // Compile-time gated (generic-width, table-less instances only) so that every other instance keeps pure shared-memory addressing.
+    constexpr bool VG = (!TABS && GC == 0);
+    const bool vglobal = VG && p.vglobal != nullptr;
+    double2* V = U + LB;
+    if constexpr (VG) { if (vglobal) V = p.vglobal + (size_t)(blockIdx.x * p.T + t) * LB; }
     double2* X3 = V + LB;                                                // Fock only (plan allocates it)
     double2* A4 = X3 + LB;                                               // inverted harmonic only
     constexpr int NBUF = (VAR == QC_QUARTIC) ? 2 : ((VAR == QC_INV_HARMONIC) ? 4 : 3);   // U, V, [X3: Y-], [A4: a, for the HERMITIAN-descriptor term]
     constexpr int CS = SolveTraits<VAR>::CS, BAs = SolveTraits<VAR>::BA;
-    const int nbuf_s = p.vglobal ? 1 : NBUF;                             // line buffers that live in shared memory
+    const int nbuf_s = vglobal ? 1 : NBUF;                             // line buffers that live in shared memory
     double2* tab = p.shared_tab ? reinterpret_cast<double2*>(smem) : U + (size_t)nbuf_s * LB;   // [L][CS][G] factor rows of this trajectory's force (TABS)
     double* nz = reinterpret_cast<double*>(base + (size_t)nbuf_s * LB * sizeof(double2) + ((TABS && !p.shared_tab) ? tab_bytes : 0));
     double* khs = reinterpret_cast<double*>(tab + (size_t)CS * L * G);    // shared copy of the Im C band (TABS, inverted harmonic)
@@ -537,7 +546,6 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     // ---- per-lane constants -------------------------------------------------------------------------------
     LaneOps<VAR, L> ops;
     double xs[(VAR == QC_QUARTIC) ? L : 1];      // grid: x_j
-    double xs2[(VAR == QC_QUARTIC) ? L : 1];     // grid: x_j^2
     double xl[(VAR == QC_QUARTIC) ? 1 : L + 3];  // Fock: xl_r, r in [-2, L]  (index r+2)
     bool valid[L];
 #pragma unroll
@@ -545,7 +553,7 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
         const int i = g * L + j;
         valid[j] = have && (i < n);
         if constexpr (VAR == QC_QUARTIC) {
-            xs[j] = valid[j] ? __ldg(&p.x[i]) : 0.0; xs2[j] = xs[j] * xs[j];
+            xs[j] = valid[j] ? __ldg(&p.x[i]) : 0.0;
             ops.dg[j] = valid[j] ? (__ldg(&p.hdiag[i]) - p.kappa * F * xs[j]) : 0.0;
         } else {
             ops.dg[j] = valid[j] ? __ldg(&p.hdiag[i]) : 0.0;
@@ -569,7 +577,7 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
 
     // ---- prologue: state -> shared line U, noise table, initial <x> ----------------------------------------
     for (int e = g; e < nbuf_s * LB; e += G) U[e] = mk2(0.0, 0.0);     // lines incl. guard columns (U, V, X3 are contiguous)
-    if (p.vglobal) { for (int e = g; e < (NBUF - 1) * LB; e += G) V[e] = mk2(0.0, 0.0); }
+    if (vglobal) { for (int e = g; e < (NBUF - 1) * LB; e += G) V[e] = mk2(0.0, 0.0); }
     traj_sync<MULTI>(bar_id, G);
     for (int i = g; i < n; i += G) { if (have) U[lidx<L>(i, Gp)] = p.psi[(size_t)traj * n + i]; }
     for (int s = g; s < my_nsub; s += G) {
@@ -676,15 +684,18 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
                 for (int r = -4; r < L + 4; r++) { const double2 c = ld_rel<L>(U, g, Gp, r); ext[r + 4] = mk2(sc * c.x, sc * c.y); }
                 // All per-point factors below are quadratics in x_j whose coefficients depend only on per-substep scalars: evaluate them as
                 // c0 + c1 x + c2 x^2 (2 FMA) instead of rebuilding (x - <x>) powers per point.
+                // (Only where registers allow: the 168-register instances keep the difference form, which has fewer live scalars.)
+                constexpr bool POLY = (MAXT <= 256);
                 const double Q0 = g4 * xbar * xbar, Q1 = -2.0 * g4 * xbar, G0 = -gs * xbar;
                 double m[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                 for (int j = 0; j < L; j++) {
                     psi[j] = ext[j + 4];
                     const double2 h = ops.h0(ext, j);
-                    const double x = xs[j], x2 = xs2[j];
-                    const double d2g = fma(Q1, x, fma(g4, x2, Q0));                 // gamma/4 (x-<x>)^2
-                    const double gsd = fma(gs, x, G0);                              // sqrt(gamma/2) (x-<x>)
+                    const double x = xs[j], x2 = x * x;
+                    double d2g, gsd;                                                // gamma/4 (x-<x>)^2,  sqrt(gamma/2) (x-<x>)
+                    if constexpr (POLY) { d2g = fma(Q1, x, fma(g4, x2, Q0)); gsd = fma(gs, x, G0); }
+                    else { const double d = x - xbar; d2g = g4 * d * d; gsd = gs * d; }
                     // a = -i H0 psi - gamma/4 (x-<x>)^2 psi      (D1, Q:434-449)
                     a[j] = valid[j] ? mk2(fma(-d2g, psi[j].x, h.y), fma(-d2g, psi[j].y, -h.x)) : mk2(0.0, 0.0);
                     const double bx_ = gsd * psi[j].x, by_ = gsd * psi[j].y;        // b = sqrt(gamma/2)(x-<x>) psi   (D2, Q:473-486)
@@ -714,14 +725,22 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
                 const double V1 = 2.0 * sdt * (k1 - k6) * gs, V0 = 2.0 * k2 - V1 * xbar;
 #pragma unroll
                 for (int j = 0; j < L; j++) {
-                    const double x = xs[j], x2 = xs2[j];
-                    const double gsd = fma(gs, x, G0);
+                    const double x = xs[j], x2 = x * x;
+                    const double gsd = POLY ? fma(gs, x, G0) : gs * (x - xbar);
                     const double bx_ = gsd * psi[j].x, by_ = gsd * psi[j].y;
                     const double ux = fma(dt, a[j].x, psi[j].x), uy = fma(dt, a[j].y, psi[j].y);
                     const double ypx = fma(sdt, bx_, ux), ypy = fma(sdt, by_, uy), ymx = fma(-sdt, bx_, ux), ymy = fma(-sdt, by_, uy);
-                    const double cpsi = fma(A2, x2, fma(A1, x, A0)), cP = fma(P2, x2, fma(P1, x, P0)), cM = fma(M2, x2, fma(M1, x, M0));
+                    double cpsi, cP, cM, cv;
+                    if constexpr (POLY) {
+                        cpsi = fma(A2, x2, fma(A1, x, A0)); cP = fma(P2, x2, fma(P1, x, P0)); cM = fma(M2, x2, fma(M1, x, M0)); cv = fma(V1, x, V0);
+                    } else {                 // fewer live scalars (register-tight 168-register instances): rebuild the differences per point
+                        const double d = x - xbar, dp = x - xbp, dm = x - xbm;
+                        cpsi = 1.0 + al * d - be * d * d;
+                        cP = -c1 * dp * dp + c2 * dp + c3 * ((x - xfp) * (1.0 + sig * dp) - (x - xfm) * (1.0 - sig * dp));
+                        cM = c4 * dm * dm + c5 * dm;
+                        cv = V1 * d + 2.0 * k2;
+                    }
                     acc[j] = mk2(fma(cM, ymx, fma(cP, ypx, cpsi * psi[j].x)), fma(cM, ymy, fma(cP, ypy, cpsi * psi[j].y)));
-                    const double cv = fma(V1, x, V0);
                     v1[j] = mk2(cv * psi[j].y, -cv * psi[j].x);
                 }
             } else {

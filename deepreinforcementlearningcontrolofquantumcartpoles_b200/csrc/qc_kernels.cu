@@ -113,6 +113,7 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             tstride = (tstride + 15) / 16 * 16;
             bool vglobal = false;
             if (!tabs && tstride > smem_max - 1024) {        // largest grids: keep only the first line in shared memory
+                if (ke->gc != 0) continue;                   // only the generic-width instances carry the global-line code path
                 tstride -= (nbuf - 1) * L * Gp * 16; vglobal = true;
             }
             int tstride_b = tstride - tab_bytes;
