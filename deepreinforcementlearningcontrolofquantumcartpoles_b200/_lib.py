@@ -9,6 +9,10 @@ QC_HARMONIC, QC_INV_HARMONIC, QC_QUARTIC = 0, 1, 2
 QC_FLAG_FAIL, QC_FLAG_ESCAPED = 1, 2
 QC_AUX_ENERGY, QC_AUX_XMEAN, QC_AUX_OUTSIDE, QC_AUX_NORM, QC_AUX_COUNT = 0, 1, 2, 3, 4
 QC_ERR_ARG, QC_ERR_CUDA, QC_ERR_PIVOT, QC_ERR_UNSUPPORTED, QC_ERR_STATE = -1, -2, -3, -4, -5
+QC_NOISE_OFF, QC_NOISE_GIVEN, QC_NOISE_PHILOX = 0, 1, 2
+# qc_policy parameter tensors (include/qcart_rollout.h), in ABI order
+POLICY_PARAMS = ["FC1_W", "FC1_B", "FC2_W", "FC2_B", "FC31_UW", "FC31_SW", "FC31_UB", "FC31_SB", "FC41_UW", "FC41_SW", "FC41_UB", "FC41_SB",
+                 "FC32_W", "FC32_B", "FC42_W", "FC42_B"]
 
 
 class QcConfig(C.Structure):
@@ -25,7 +29,7 @@ class QcartError(RuntimeError):
         self.code = code
 
 
-# every symbol include/qcart.h declares: (name, restype, argtypes)
+# every symbol include/qcart.h and include/qcart_rollout.h declare: (name, restype, argtypes)
 _vp, _dp, _ip, _i64 = C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64
 SYMBOLS = [
     ("qc_last_error", C.c_char_p, []),
@@ -59,6 +63,30 @@ SYMBOLS = [
     ("qc_measure_smem_peak", C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     ("qc_launch_count", _i64, [_vp]),
     ("qc_kernel_info", C.c_char_p, [_vp]),
+    # ---- include/qcart_rollout.h ----
+    ("qc_obs_f32", C.c_int, [_dp, _i64, C.c_double, _vp, _vp]),
+    ("qc_policy_create", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),
+    ("qc_policy_destroy", C.c_int, [_vp]),
+    ("qc_policy_param_size", _i64, [_vp, C.c_int32]),
+    ("qc_policy_set_param", C.c_int, [_vp, C.c_int32, _vp, _i64]),
+    ("qc_policy_noise_width", _i64, [_vp]),
+    ("qc_policy_forward", C.c_int, [_vp, _vp, _i64, C.c_int32, _vp, C.c_uint64, _i64, C.c_uint64, _vp, _vp, _vp, _vp]),
+    ("qc_epsilon_greedy", C.c_int, [_vp, _i64, C.c_int32, C.c_double, C.c_uint64, _i64, C.c_uint64, _vp, _vp, C.c_int32, _vp]),
+    ("qc_action_forces", C.c_int, [_vp, _i64, C.c_int32, C.c_double, _vp, C.c_int32, _vp]),
+    ("qc_policy_launch_count", _i64, [_vp]),
+    ("qc_replay_create", C.c_int, [C.c_int32, _i64, C.c_int32, C.POINTER(_vp)]),
+    ("qc_replay_destroy", C.c_int, [_vp]),
+    ("qc_replay_push", C.c_int, [_vp, _vp, _vp, C.c_int32, _vp, _vp, _i64, C.c_double, _vp, _i64, _vp]),
+    ("qc_replay_total", C.c_int, [_vp, C.POINTER(_i64), _vp]),
+    ("qc_replay_data", C.c_void_p, [_vp]),
+    ("qc_replay_read", C.c_int, [_vp, _i64, _i64, _vp, _vp]),
+    ("qc_record_create", C.c_int, [_i64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),
+    ("qc_record_destroy", C.c_int, [_vp]),
+    ("qc_record_reset", C.c_int, [_vp, _vp, _vp]),
+    ("qc_record_push", C.c_int, [_vp, _vp, C.c_int32, _vp, C.c_double, _vp]),
+    ("qc_record_window", C.c_int, [_vp, _vp, _vp]),
+    ("qc_record_experience", C.c_int, [_vp, _vp, _vp]),
+    ("qc_record_row_len", _i64, [_vp]),
 ]
 
 _lib = None

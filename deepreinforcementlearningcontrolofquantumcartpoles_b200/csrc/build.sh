@@ -8,7 +8,7 @@ mkdir -p "$OBJ"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 pids=()
-SRCS="qc_kernels.cu qc_api.cu qc_model.cpp $(cd "$HERE" && ls qc_inst_*.cu)"
+SRCS="qc_kernels.cu qc_api.cu qc_rollout.cu qc_model.cpp $(cd "$HERE" && ls qc_inst_*.cu)"
 for f in $SRCS; do
   $NVCC $FLAGS ${QC_PTXAS_V:+-Xptxas -v} -c -o "$OBJ/${f%.*}.o" "$HERE/$f" > "$OBJ/${f%.*}.log" 2>&1 &
   pids+=($!)

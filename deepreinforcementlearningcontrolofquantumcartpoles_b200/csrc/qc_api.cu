@@ -12,6 +12,7 @@ using namespace qc;
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int qc::set_error(int code, const std::string& msg) { return fail(code, msg); }
 #define QC_CUDA(call)                                                                                              \
     do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaGetLastError();                                      \
         return fail(QC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)

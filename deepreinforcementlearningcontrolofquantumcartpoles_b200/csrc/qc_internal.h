@@ -99,4 +99,7 @@ int measure_smem_peak(int device, double* bps);
 
 void philox_normals_host(uint64_t seed, uint64_t traj, uint64_t step, double* out2);
 
+// Records the calling thread's error message (returned by qc_last_error) and returns `code`; shared by all translation units of the ABI.
+int set_error(int code, const std::string& msg);
+
 }  // namespace qc

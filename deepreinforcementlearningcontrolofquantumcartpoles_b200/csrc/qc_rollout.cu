@@ -1,0 +1,627 @@
+// Device-resident steps either side of the SSE kernel (include/qcart_rollout.h): float32 observation, the
+// reference's direct_DQN policy on the whole batch, epsilon-greedy action selection, the experience-row ring and the measurement record.
+//
+// The policy is GEMM-shaped but small (0.55 MFMA per trajectory, 2-8 % of the SSE step's time) and the reference evaluates it in fp32
+// (torch modules, no TF32), so it runs as fp32 FMA on the CUDA cores: a 64x64x16 register-tiled kernel per hidden layer with the bias /
+// ReLU / factorised-noise epilogue fused, and one warp per trajectory for the n_actions-wide output layer + argmax.  A noisy layer
+// (layers.py:42-57, per-sample noise) is evaluated WITHOUT materialising the per-sample weight matrix w = u_w + sigma_w * (e_out e_in^T):
+//     y = x u_w^T + u_b + e_out * ((x * e_in) sigma_w^T + sigma_b)
+// i.e. a second accumulator over the same tiles.
+#include "qc_internal.h"
+#include "qc_philox.cuh"
+#include "../../include/qcart_rollout.h"
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace qc;
+
+#define RO_CUDA(call)                                                                                              \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cudaGetLastError();                                      \
+        return set_error(QC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+
+namespace {
+
+constexpr int H1 = 512, H2 = 512, H3 = 256, HV = 128;           // direct_DQN widths (Q/RL.py:87-98)
+constexpr uint64_t TAG_NOISE = 0x6e6f697379ull << 20;            // key tags separating the Philox streams from the SSE measurement noise
+constexpr uint64_t TAG_EPS = 0x657073ull << 24;
+
+int use_device(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return set_error(QC_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)"); }
+    if (device < 0 || device >= ndev) return set_error(QC_ERR_ARG, "device ordinal out of range");
+    RO_CUDA(cudaSetDevice(device));
+    return QC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void obs_kernel(const double* __restrict__ m, int64_t count, float scale, float* __restrict__ obs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) obs[i] = (float)m[i] * scale;
+}
+
+// h[b, o] = relu(b1[o] + sum_i W1[o, i] x[b, i]);  n_in is small (20 grid moments / 5 Fock moments): one CTA per 32 rows
+__global__ void __launch_bounds__(256) fc1_kernel(const float* __restrict__ obs, const float* __restrict__ W, const float* __restrict__ bias,
+                                                  float* __restrict__ h, int64_t B, int n_in, int n_out) {
+    constexpr int ROWS = 32;
+    extern __shared__ float xs[];                      // [ROWS][n_in]
+    const int64_t m0 = (int64_t)blockIdx.x * ROWS;
+    const int rows = (int)min((int64_t)ROWS, B - m0);
+    for (int e = threadIdx.x; e < ROWS * n_in; e += blockDim.x) xs[e] = (e < rows * n_in) ? obs[m0 * n_in + e] : 0.0f;
+    __syncthreads();
+    for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+        const float b0 = bias[o];
+        for (int r0 = 0; r0 < rows; r0 += 8) {
+            float acc[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) acc[r] = b0;
+            for (int i = 0; i < n_in; i++) {
+                const float w = __ldg(&W[(size_t)o * n_in + i]);
+#pragma unroll
+                for (int r = 0; r < 8; r++) acc[r] = fmaf(xs[(r0 + r) * n_in + i], w, acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++) if (r0 + r < rows) h[(m0 + r0 + r) * n_out + o] = fmaxf(acc[r], 0.0f);
+        }
+    }
+}
+
+// C[M, N] = act(A[M, K] W[N, K]^T + bias (+ eo * ((A * ei) S[N, K]^T + sbias)))      N % 64 == 0, K % 16 == 0
+struct GemmArgs {
+    const float* A; const float* W; const float* S; const float* bias; const float* sbias;
+    const float* ei; const float* eo; int ldn;          // per-sample noise rows: ei[m * ldn + k], eo[m * ldn + n]
+    float* C; int M, N, K;
+};
+constexpr int BM = 64, BN = 64, BK = 16, LDT = BM + 4;
+
+template <bool NOISY, bool RELU>
+__global__ void __launch_bounds__(256) gemm_tn_kernel(const GemmArgs g) {
+    __shared__ __align__(16) float As[BK][LDT], Ws[BK][LDT];
+    __shared__ __align__(16) float A2s[NOISY ? BK : 1][LDT], Ss[NOISY ? BK : 1][LDT];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int lrow = tid >> 2, lk = (tid & 3) * 4;                // this thread's float4 of the A / W tile
+    const bool arow_ok = (m0 + lrow) < g.M;
+    const float* ap = g.A + (size_t)(m0 + lrow) * g.K + lk;
+    const float* wp = g.W + (size_t)(n0 + lrow) * g.K + lk;
+    const float* sp = NOISY ? g.S + (size_t)(n0 + lrow) * g.K + lk : nullptr;
+    const float* ep = NOISY ? g.ei + (size_t)(m0 + lrow) * g.ldn + lk : nullptr;
+    float acc[4][4], acc2[NOISY ? 4 : 1][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[i][j] = 0.0f; if constexpr (NOISY) acc2[i][j] = 0.0f; }
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 ra = arow_ok ? *reinterpret_cast<const float4*>(ap) : z4, rw = *reinterpret_cast<const float4*>(wp), re = z4, rs = z4;
+    if constexpr (NOISY) { re = arow_ok ? *reinterpret_cast<const float4*>(ep) : z4; rs = *reinterpret_cast<const float4*>(sp); }
+    for (int k0 = 0; k0 < g.K; k0 += BK) {
+        As[lk + 0][lrow] = ra.x; As[lk + 1][lrow] = ra.y; As[lk + 2][lrow] = ra.z; As[lk + 3][lrow] = ra.w;
+        Ws[lk + 0][lrow] = rw.x; Ws[lk + 1][lrow] = rw.y; Ws[lk + 2][lrow] = rw.z; Ws[lk + 3][lrow] = rw.w;
+        if constexpr (NOISY) {
+            A2s[lk + 0][lrow] = ra.x * re.x; A2s[lk + 1][lrow] = ra.y * re.y; A2s[lk + 2][lrow] = ra.z * re.z; A2s[lk + 3][lrow] = ra.w * re.w;
+            Ss[lk + 0][lrow] = rs.x; Ss[lk + 1][lrow] = rs.y; Ss[lk + 2][lrow] = rs.z; Ss[lk + 3][lrow] = rs.w;
+        }
+        __syncthreads();
+        if (k0 + BK < g.K) {                                       // prefetch the next tile into registers while this one is consumed
+            ra = arow_ok ? *reinterpret_cast<const float4*>(ap + k0 + BK) : z4; rw = *reinterpret_cast<const float4*>(wp + k0 + BK);
+            if constexpr (NOISY) { re = arow_ok ? *reinterpret_cast<const float4*>(ep + k0 + BK) : z4; rs = *reinterpret_cast<const float4*>(sp + k0 + BK); }
+        }
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]), w = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+            if constexpr (NOISY) {
+                const float4 a2 = *reinterpret_cast<const float4*>(&A2s[k][ty * 4]), s = *reinterpret_cast<const float4*>(&Ss[k][tx * 4]);
+                const float a2v[4] = {a2.x, a2.y, a2.z, a2.w}, sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc2[i][j] = fmaf(a2v[i], sv[j], acc2[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+    const int n = n0 + tx * 4;
+    const float4 b4 = *reinterpret_cast<const float4*>(g.bias + n);
+    const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+    float sbv[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (NOISY) { const float4 s4 = *reinterpret_cast<const float4*>(g.sbias + n); sbv[0] = s4.x; sbv[1] = s4.y; sbv[2] = s4.z; sbv[3] = s4.w; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            v[j] = acc[i][j] + bv[j];
+            if constexpr (NOISY) v[j] = fmaf(g.eo[(size_t)m * g.ldn + n + j], acc2[i][j] + sbv[j], v[j]);
+            if (RELU) v[j] = fmaxf(v[j], 0.0f);
+        }
+        *reinterpret_cast<float4*>(g.C + (size_t)m * g.N + n) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// Output layer (K = 256 inputs, A <= 32 outputs) + argmax: one warp per trajectory, inputs in registers.
+template <bool NOISY>
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, const float* __restrict__ U, const float* __restrict__ S,
+                                                   const float* __restrict__ ub, const float* __restrict__ sb, const float* __restrict__ ei,
+                                                   const float* __restrict__ eo, int ldn, int A, float* __restrict__ q, int32_t* __restrict__ greedy, int64_t B) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B) return;
+    float xv[H3 / 32], x2[H3 / 32];
+#pragma unroll
+    for (int t = 0; t < H3 / 32; t++) {
+        xv[t] = x[row * H3 + lane + 32 * t];
+        if constexpr (NOISY) x2[t] = xv[t] * ei[row * ldn + lane + 32 * t]; else x2[t] = 0.0f;
+    }
+    float best = 0.0f; int besti = 0;
+    for (int o = 0; o < A; o++) {
+        float d1 = 0.0f, d2 = 0.0f;
+#pragma unroll
+        for (int t = 0; t < H3 / 32; t++) {
+            d1 = fmaf(xv[t], __ldg(&U[(size_t)o * H3 + lane + 32 * t]), d1);
+            if constexpr (NOISY) d2 = fmaf(x2[t], __ldg(&S[(size_t)o * H3 + lane + 32 * t]), d2);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            d1 += __shfl_xor_sync(0xffffffffu, d1, off);
+            if constexpr (NOISY) d2 += __shfl_xor_sync(0xffffffffu, d2, off);
+        }
+        float v = d1 + ub[o];
+        if constexpr (NOISY) v = fmaf(eo[row * ldn + o], d2 + sb[o], v);
+        if (o == 0 || v > best) { best = v; besti = o; }           // first maximum, like torch.max(1)[1]
+        if (lane == 0 && q) q[row * A + o] = v;
+    }
+    if (lane == 0 && greedy) greedy[row] = besti;
+}
+
+// value[b] = b42 + sum_i W42[i] v[b, i]   (fc42, 128 -> 1)
+__global__ void __launch_bounds__(256) value_kernel(const float* __restrict__ v, const float* __restrict__ W, const float* __restrict__ b, float* __restrict__ out, int64_t B) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B) return;
+    float d = 0.0f;
+#pragma unroll
+    for (int t = 0; t < HV / 32; t++) d = fmaf(v[row * HV + lane + 32 * t], __ldg(&W[lane + 32 * t]), d);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+    if (lane == 0) out[row] = d + b[0];
+}
+
+__device__ __forceinline__ float noisy_f(float x) { return copysignf(sqrtf(fabsf(x)), x); }     // layers.py:82-83
+
+// Factorised-noise entries of one control step: 4 normals per Philox block, counter = (traj, counter, chunk)
+__global__ void noise_kernel(float* __restrict__ out, int64_t B, int width, uint64_t seed, int64_t traj_offset, uint64_t counter) {
+    const int chunks = (width + 3) / 4;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * chunks) return;
+    const int64_t b = idx / chunks; const int c = (int)(idx % chunks);
+    const uint64_t traj = (uint64_t)(traj_offset + b), key = seed ^ TAG_NOISE;
+    uint32_t o[4];
+    philox4x32_10((uint32_t)traj, (uint32_t)(traj >> 32), (uint32_t)counter, ((uint32_t)(counter >> 32) << 16) ^ (uint32_t)c, (uint32_t)key, (uint32_t)(key >> 32), o);
+    float nrm[4];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const float u1 = ((float)(o[2 * h] >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(o[2 * h + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float rad = sqrtf(-2.0f * logf(u1));
+        float s, cc; sincospif(2.0f * u2, &s, &cc);
+        nrm[2 * h] = rad * cc; nrm[2 * h + 1] = rad * s;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) if (c * 4 + e < width) out[b * width + c * 4 + e] = noisy_f(nrm[e]);
+}
+
+__global__ void eps_greedy_kernel(const int32_t* __restrict__ greedy, int64_t B, int A, double eps, uint64_t seed, int64_t traj_offset, uint64_t counter,
+                                  int32_t* __restrict__ action, uint8_t* __restrict__ rnd) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double u1, u2;
+    philox_uniforms(seed ^ TAG_EPS, (uint64_t)(traj_offset + b), counter, &u1, &u2);
+    const bool r = u1 < eps;                                                   // `random.uniform() < eps_threshold` (Q/main_parallel.py:155)
+    int a = greedy[b];
+    if (r) { a = (int)(u2 * A); if (a >= A) a = A - 1; }                         // `random.randint(no_action_choice*2+1)` (:156)
+    action[b] = a;
+    if (rnd) rnd[b] = r ? 1 : 0;
+}
+
+__global__ void action_force_kernel(const int32_t* __restrict__ action, int64_t B, int half, double spacing, double* __restrict__ force) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) force[b] = (double)(action[b] - half) * spacing;
+}
+
+// ---- experience rows ------------------------------------------------------------------------------------------------------
+// Exclusive scan of keep[] in trajectory order by one CTA (B <= a few 1e5: a handful of passes), cursor update on the device.
+__global__ void __launch_bounds__(1024) replay_scan_kernel(const uint8_t* __restrict__ keep, int64_t B, int32_t* __restrict__ pos, unsigned long long* cursor /* [0] = rows pushed so far, [1] = base of this push */) {
+    __shared__ int warp_excl[32];
+    __shared__ int pass_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int carry = 0;                                                             // rows kept in earlier passes (same value in every thread)
+    for (int64_t start = 0; start < B; start += 1024) {
+        const int64_t b = start + tid;
+        const int k = (b < B && (keep == nullptr || keep[b])) ? 1 : 0;
+        int incl = k;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+        if (lane == 31) warp_excl[wid] = incl;                                  // warp totals
+        __syncthreads();
+        if (wid == 0) {
+            const int ws = warp_excl[lane];
+            int wincl = ws;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wincl, off); if (lane >= off) wincl += t; }
+            warp_excl[lane] = wincl - ws;                                       // exclusive prefix over the warps
+            if (lane == 31) pass_total = wincl;
+        }
+        __syncthreads();
+        if (b < B) pos[b] = carry + warp_excl[wid] + incl - k;
+        carry += pass_total;
+        __syncthreads();                                                        // before the next pass overwrites the shared arrays
+    }
+    if (tid == 0) { const unsigned long long old = cursor[0]; cursor[1] = old; cursor[0] = old + (unsigned long long)carry; }
+}
+
+__global__ void __launch_bounds__(256) replay_write_kernel(float* __restrict__ ring, int64_t capacity, int row_len, const unsigned long long* __restrict__ cursor,
+                                                           const int32_t* __restrict__ pos, const uint8_t* __restrict__ keep, const float* __restrict__ last_obs,
+                                                           const float* __restrict__ obs, int K, const int32_t* __restrict__ last_action,
+                                                           const double* __restrict__ reward_src, int64_t reward_stride, double reward_scale, int64_t B) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B || (keep != nullptr && !keep[b])) return;
+    float* row = ring + (size_t)((cursor[1] + (unsigned long long)pos[b]) % (unsigned long long)capacity) * row_len;
+    for (int e = lane; e < row_len; e += 32) {
+        float v;
+        if (e < K) v = last_obs[b * K + e];
+        else if (e < 2 * K) v = obs[b * K + e - K];
+        else if (e == 2 * K) v = (float)last_action[b];
+        else v = (float)(reward_scale * reward_src[b * reward_stride]);
+        row[e] = v;
+    }
+}
+
+// ---- measurement record -----------------------------------------------------------------------------------------------------
+__global__ void record_push_kernel(float* __restrict__ meas, float* __restrict__ forces, int64_t B, int RLC, int NF, int head, int head_f,
+                                   const double* __restrict__ q, int n_sub, int cg, int CL, const double* __restrict__ force, double scale) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * CL) return;
+    const int64_t b = idx / CL; const int c = (int)(idx % CL);
+    double s = 0.0;
+    for (int k = 0; k < cg; k++) s += q[b * n_sub + c * cg + k];                // `sum(measurements_cache)` (H/main_parallel.py:287)
+    meas[b * RLC + (head + c) % RLC] = (float)(s / cg * scale);
+    if (c == 0) forces[b * NF + head_f % NF] = (float)(force[b] * scale);       // `forces_to_store.append(force*args.input_scaling)` (:268)
+}
+
+__global__ void record_window_kernel(const float* __restrict__ meas, const float* __restrict__ forces, int64_t B, int RL, int RLC, int NF, int CL,
+                                     int head, int head_f, float* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * RL) return;
+    const int64_t b = idx / RL; const int j = (int)(idx % RL);
+    out[(b * 2 + 0) * RL + j] = meas[b * RLC + ((head - 1 - j) % RLC + RLC) % RLC];
+    out[(b * 2 + 1) * RL + j] = forces[b * NF + ((head_f - 1 - j / CL) % NF + NF) % NF];
+}
+
+__global__ void record_experience_kernel(const float* __restrict__ meas, const float* __restrict__ forces, int64_t B, int RLC, int NF, int head, int head_f,
+                                         float* __restrict__ out) {
+    const int W = RLC + NF;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * W) return;
+    const int64_t b = idx / W; const int j = (int)(idx % W);
+    out[idx] = (j < RLC) ? meas[b * RLC + ((head - 1 - j) % RLC + RLC) % RLC] : forces[b * NF + ((head_f - 1 - (j - RLC)) % NF + NF) % NF];
+}
+
+__global__ void record_reset_kernel(float* __restrict__ meas, float* __restrict__ forces, int64_t B, int RLC, int NF, const uint8_t* __restrict__ mask) {
+    const int W = RLC + NF;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * W) return;
+    const int64_t b = idx / W; const int j = (int)(idx % W);
+    if (mask != nullptr && !mask[b]) return;
+    if (j < RLC) meas[b * RLC + j] = 0.0f; else forces[b * NF + j - RLC] = 0.0f;
+}
+
+inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+}  // namespace
+
+// =============================================================================================================================
+struct qc_policy {
+    int n_in = 0, n_actions = 0, noisy_layers = 0, device = 0;
+    float* param[QC_P_COUNT] = {};
+    int64_t psize[QC_P_COUNT] = {};
+    bool pset[QC_P_COUNT] = {};
+    float *h1 = nullptr, *h2 = nullptr, *a3 = nullptr, *hv = nullptr, *noise = nullptr;
+    int64_t cap = 0;
+    int64_t launches = 0;
+};
+
+extern "C" int qc_obs_f32(const double* moments, int64_t count, double input_scaling, float* obs, void* stream) {
+    if (!moments || !obs || count < 0) return set_error(QC_ERR_ARG, "qc_obs_f32: null pointer or negative count");
+    if (count == 0) return QC_OK;
+    obs_kernel<<<blocks_for(count, 256), 256, 0, (cudaStream_t)stream>>>(moments, count, (float)input_scaling, obs);
+    RO_CUDA(cudaGetLastError());
+    return QC_OK;
+}
+
+extern "C" int qc_policy_create(int32_t n_in, int32_t n_actions, int32_t noisy_layers, int32_t device, qc_policy** out) {
+    if (!out) return set_error(QC_ERR_ARG, "qc_policy_create: out is NULL");
+    *out = nullptr;
+    if (int rc = use_device(device)) return rc;
+    if (n_in < 1 || n_in > 256) return set_error(QC_ERR_ARG, "qc_policy_create: n_in must be in [1, 256]");
+    if (n_actions < 1 || n_actions > 32) return set_error(QC_ERR_ARG, "qc_policy_create: n_actions must be in [1, 32]");
+    if (noisy_layers < 0 || noisy_layers > 2) return set_error(QC_ERR_ARG, "qc_policy_create: noisy_layers must be 0, 1 or 2");
+    qc_policy* p = new (std::nothrow) qc_policy();
+    if (!p) return set_error(QC_ERR_CUDA, "out of host memory");
+    p->n_in = n_in; p->n_actions = n_actions; p->noisy_layers = noisy_layers; p->device = device;
+    int64_t* z = p->psize;
+    z[QC_P_FC1_W] = (int64_t)H1 * n_in; z[QC_P_FC1_B] = H1; z[QC_P_FC2_W] = (int64_t)H2 * H1; z[QC_P_FC2_B] = H2;
+    z[QC_P_FC31_UW] = (int64_t)H3 * H2; z[QC_P_FC31_UB] = H3;
+    z[QC_P_FC31_SW] = noisy_layers >= 2 ? (int64_t)H3 * H2 : 0; z[QC_P_FC31_SB] = noisy_layers >= 2 ? H3 : 0;
+    z[QC_P_FC41_UW] = (int64_t)n_actions * H3; z[QC_P_FC41_UB] = n_actions;
+    z[QC_P_FC41_SW] = noisy_layers >= 1 ? (int64_t)n_actions * H3 : 0; z[QC_P_FC41_SB] = noisy_layers >= 1 ? n_actions : 0;
+    z[QC_P_FC32_W] = (int64_t)HV * H2; z[QC_P_FC32_B] = HV; z[QC_P_FC42_W] = HV; z[QC_P_FC42_B] = 1;
+    for (int i = 0; i < QC_P_COUNT; i++) {
+        if (z[i] == 0) { p->pset[i] = true; continue; }
+        if (cudaMalloc(&p->param[i], sizeof(float) * (size_t)((z[i] + 3) / 4 * 4)) != cudaSuccess) { cudaGetLastError(); qc_policy_destroy(p); return set_error(QC_ERR_CUDA, "cudaMalloc failed for the policy parameters"); }
+    }
+    *out = p;
+    return QC_OK;
+}
+
+extern "C" int qc_policy_destroy(qc_policy* p) {
+    if (!p) return QC_OK;
+    cudaSetDevice(p->device);
+    for (int i = 0; i < QC_P_COUNT; i++) cudaFree(p->param[i]);
+    cudaFree(p->h1); cudaFree(p->h2); cudaFree(p->a3); cudaFree(p->hv); cudaFree(p->noise);
+    delete p;
+    return QC_OK;
+}
+
+extern "C" int64_t qc_policy_param_size(const qc_policy* p, int32_t which) {
+    if (!p || which < 0 || which >= QC_P_COUNT) return set_error(QC_ERR_ARG, "qc_policy_param_size: bad handle or index");
+    return p->psize[which];
+}
+
+extern "C" int64_t qc_policy_noise_width(const qc_policy* p) {
+    if (!p) return set_error(QC_ERR_ARG, "qc_policy_noise_width: NULL handle");
+    return ((int64_t)H2 + H3 + H3 + p->n_actions + 3) / 4 * 4;      // rows padded to 16 bytes (vector loads)
+}
+
+extern "C" int64_t qc_policy_launch_count(const qc_policy* p) { return p ? p->launches : 0; }
+
+extern "C" int qc_policy_set_param(qc_policy* p, int32_t which, const float* host, int64_t count) {
+    if (!p || which < 0 || which >= QC_P_COUNT || !host) return set_error(QC_ERR_ARG, "qc_policy_set_param: bad handle, index or pointer");
+    if (p->psize[which] == 0) return set_error(QC_ERR_ARG, "qc_policy_set_param: this tensor does not exist for the policy's noisy_layers");
+    if (count != p->psize[which]) return set_error(QC_ERR_ARG, "qc_policy_set_param: wrong element count (expected " + std::to_string(p->psize[which]) + ", got " + std::to_string(count) + ")");
+    RO_CUDA(cudaSetDevice(p->device));
+    RO_CUDA(cudaMemcpy(p->param[which], host, sizeof(float) * (size_t)count, cudaMemcpyHostToDevice));
+    p->pset[which] = true;
+    return QC_OK;
+}
+
+template <bool RELU>
+static void launch_gemm(bool noisy, const GemmArgs& g, cudaStream_t st) {
+    const dim3 grid(g.N / BN, (g.M + BM - 1) / BM);
+    if (noisy) gemm_tn_kernel<true, RELU><<<grid, 256, 0, st>>>(g);
+    else gemm_tn_kernel<false, RELU><<<grid, 256, 0, st>>>(g);
+}
+
+extern "C" int qc_policy_forward(qc_policy* p, const float* obs, int64_t B, int32_t noise_mode, const float* noise, uint64_t seed,
+                                 int64_t traj_offset, uint64_t counter, float* q, float* value, int32_t* greedy, void* stream) {
+    if (!p || !obs) return set_error(QC_ERR_ARG, "qc_policy_forward: NULL handle or observation pointer");
+    if (B < 0 || B > (int64_t)1 << 24) return set_error(QC_ERR_ARG, "qc_policy_forward: batch out of range");
+    if (noise_mode < QC_NOISE_OFF || noise_mode > QC_NOISE_PHILOX) return set_error(QC_ERR_ARG, "qc_policy_forward: unknown noise_mode");
+    if (noise_mode == QC_NOISE_GIVEN && !noise) return set_error(QC_ERR_ARG, "qc_policy_forward: noise_mode GIVEN needs the noise rows");
+    for (int i = 0; i < QC_P_COUNT; i++) if (!p->pset[i]) return set_error(QC_ERR_STATE, "qc_policy_forward: parameter tensor " + std::to_string(i) + " was never set");
+    if (B == 0) return QC_OK;
+    RO_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int NW = (int)qc_policy_noise_width(p);
+    if (p->cap < B) {
+        cudaFree(p->h1); cudaFree(p->h2); cudaFree(p->a3); cudaFree(p->hv); cudaFree(p->noise);
+        p->h1 = p->h2 = p->a3 = p->hv = p->noise = nullptr; p->cap = 0;
+        RO_CUDA(cudaMalloc(&p->h1, sizeof(float) * (size_t)B * H1)); RO_CUDA(cudaMalloc(&p->h2, sizeof(float) * (size_t)B * H2));
+        RO_CUDA(cudaMalloc(&p->a3, sizeof(float) * (size_t)B * H3)); RO_CUDA(cudaMalloc(&p->hv, sizeof(float) * (size_t)B * HV));
+        RO_CUDA(cudaMalloc(&p->noise, sizeof(float) * ((size_t)B * NW + 4)));
+        p->cap = B;
+    }
+    const bool any_noise = noise_mode != QC_NOISE_OFF && p->noisy_layers > 0;
+    const float* nz = nullptr;
+    if (any_noise) {
+        if (noise_mode == QC_NOISE_PHILOX) {
+            noise_kernel<<<blocks_for(B * ((NW + 3) / 4), 256), 256, 0, st>>>(p->noise, B, NW, seed, traj_offset, counter);
+            p->launches++;
+            nz = p->noise;
+        } else nz = noise;
+    }
+    fc1_kernel<<<blocks_for(B, 32), 256, sizeof(float) * 32 * p->n_in, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], p->h1, B, p->n_in, H1);
+    GemmArgs g{};
+    g.A = p->h1; g.W = p->param[QC_P_FC2_W]; g.bias = p->param[QC_P_FC2_B]; g.C = p->h2; g.M = (int)B; g.N = H2; g.K = H1; g.ldn = NW;
+    launch_gemm<true>(false, g, st);
+    const bool n31 = any_noise && p->noisy_layers >= 2, n41 = any_noise && p->noisy_layers >= 1;
+    g = GemmArgs{};
+    g.A = p->h2; g.W = p->param[QC_P_FC31_UW]; g.S = p->param[QC_P_FC31_SW]; g.bias = p->param[QC_P_FC31_UB]; g.sbias = p->param[QC_P_FC31_SB];
+    g.ei = nz; g.eo = nz ? nz + H2 : nullptr; g.ldn = NW; g.C = p->a3; g.M = (int)B; g.N = H3; g.K = H2;
+    launch_gemm<true>(n31, g, st);
+    p->launches += 3;
+    if (q || greedy) {
+        const unsigned nb = blocks_for(B, 8);
+        if (n41) head_kernel<true><<<nb, 256, 0, st>>>(p->a3, p->param[QC_P_FC41_UW], p->param[QC_P_FC41_SW], p->param[QC_P_FC41_UB], p->param[QC_P_FC41_SB],
+                                                        nz + H2 + H3, nz + H2 + H3 + H3, NW, p->n_actions, q, greedy, B);
+        else head_kernel<false><<<nb, 256, 0, st>>>(p->a3, p->param[QC_P_FC41_UW], nullptr, p->param[QC_P_FC41_UB], nullptr, nullptr, nullptr, NW, p->n_actions, q, greedy, B);
+        p->launches++;
+    }
+    if (value) {
+        g = GemmArgs{};
+        g.A = p->h2; g.W = p->param[QC_P_FC32_W]; g.bias = p->param[QC_P_FC32_B]; g.C = p->hv; g.M = (int)B; g.N = HV; g.K = H2; g.ldn = NW;
+        launch_gemm<true>(false, g, st);
+        value_kernel<<<blocks_for(B, 8), 256, 0, st>>>(p->hv, p->param[QC_P_FC42_W], p->param[QC_P_FC42_B], value, B);
+        p->launches += 2;
+    }
+    RO_CUDA(cudaGetLastError());
+    return QC_OK;
+}
+
+extern "C" int qc_epsilon_greedy(const int32_t* greedy, int64_t B, int32_t n_actions, double eps, uint64_t seed, int64_t traj_offset,
+                                 uint64_t counter, int32_t* action, uint8_t* random_flag, int32_t device, void* stream) {
+    if (!greedy || !action || B < 0 || n_actions < 1) return set_error(QC_ERR_ARG, "qc_epsilon_greedy: bad argument");
+    if (int rc = use_device(device)) return rc;
+    if (B == 0) return QC_OK;
+    eps_greedy_kernel<<<blocks_for(B, 256), 256, 0, (cudaStream_t)stream>>>(greedy, B, n_actions, eps, seed, traj_offset, counter, action, random_flag);
+    RO_CUDA(cudaGetLastError());
+    return QC_OK;
+}
+
+extern "C" int qc_action_forces(const int32_t* action, int64_t B, int32_t n_levels, double f_max, double* force, int32_t device, void* stream) {
+    if (!action || !force || B < 0 || n_levels < 3 || n_levels % 2 == 0) return set_error(QC_ERR_ARG, "qc_action_forces: bad argument (n_levels must be odd, >= 3)");
+    if (int rc = use_device(device)) return rc;
+    if (B == 0) return QC_OK;
+    const int half = (n_levels - 1) / 2;
+    action_force_kernel<<<blocks_for(B, 256), 256, 0, (cudaStream_t)stream>>>(action, B, half, f_max / half, force);
+    RO_CUDA(cudaGetLastError());
+    return QC_OK;
+}
+
+// ---- experience rows ---------------------------------------------------------------------------------------------------------
+struct qc_replay {
+    int row_len = 0, device = 0; int64_t capacity = 0;
+    float* ring = nullptr; unsigned long long* cursor = nullptr; int32_t* pos = nullptr; int64_t pos_cap = 0;
+};
+
+extern "C" int qc_replay_create(int32_t row_len, int64_t capacity, int32_t device, qc_replay** out) {
+    if (!out) return set_error(QC_ERR_ARG, "qc_replay_create: out is NULL");
+    *out = nullptr;
+    if (int rc = use_device(device)) return rc;
+    if (row_len < 4 || row_len % 2 != 0 || capacity < 1) return set_error(QC_ERR_ARG, "qc_replay_create: row_len must be 2K+2 and capacity positive");
+    qc_replay* r = new (std::nothrow) qc_replay();
+    if (!r) return set_error(QC_ERR_CUDA, "out of host memory");
+    r->row_len = row_len; r->capacity = capacity; r->device = device;
+    if (cudaMalloc(&r->ring, sizeof(float) * (size_t)capacity * row_len) != cudaSuccess || cudaMalloc(&r->cursor, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaGetLastError(); qc_replay_destroy(r); return set_error(QC_ERR_CUDA, "cudaMalloc failed for the experience ring");
+    }
+    RO_CUDA(cudaMemset(r->ring, 0, sizeof(float) * (size_t)capacity * row_len));
+    RO_CUDA(cudaMemset(r->cursor, 0, 2 * sizeof(unsigned long long)));
+    *out = r;
+    return QC_OK;
+}
+
+extern "C" int qc_replay_destroy(qc_replay* r) {
+    if (!r) return QC_OK;
+    cudaSetDevice(r->device);
+    cudaFree(r->ring); cudaFree(r->cursor); cudaFree(r->pos);
+    delete r;
+    return QC_OK;
+}
+
+extern "C" int qc_replay_push(qc_replay* r, const float* last_obs, const float* obs, int32_t K, const int32_t* last_action, const double* reward_src,
+                              int64_t reward_stride, double reward_scale, const uint8_t* keep, int64_t B, void* stream) {
+    if (!r || !last_obs || !obs || !last_action || !reward_src) return set_error(QC_ERR_ARG, "qc_replay_push: NULL argument");
+    if (2 * K + 2 != r->row_len) return set_error(QC_ERR_ARG, "qc_replay_push: K does not match the ring's row length (row_len = 2K+2)");
+    if (B < 0 || B > r->capacity) return set_error(QC_ERR_ARG, "qc_replay_push: batch larger than the ring capacity");
+    if (B == 0) return QC_OK;
+    RO_CUDA(cudaSetDevice(r->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (r->pos_cap < B) { cudaFree(r->pos); r->pos = nullptr; r->pos_cap = 0; RO_CUDA(cudaMalloc(&r->pos, sizeof(int32_t) * (size_t)B)); r->pos_cap = B; }
+    replay_scan_kernel<<<1, 1024, 0, st>>>(keep, B, r->pos, r->cursor);
+    replay_write_kernel<<<blocks_for(B, 8), 256, 0, st>>>(r->ring, r->capacity, r->row_len, r->cursor, r->pos, keep, last_obs, obs, K, last_action,
+                                                           reward_src, reward_stride, reward_scale, B);
+    RO_CUDA(cudaGetLastError());
+    return QC_OK;
+}
+
+extern "C" int qc_replay_total(qc_replay* r, int64_t* total, void* stream) {
+    if (!r || !total) return set_error(QC_ERR_ARG, "qc_replay_total: NULL argument");
+    RO_CUDA(cudaSetDevice(r->device));
+    unsigned long long t = 0;
+    RO_CUDA(cudaMemcpyAsync(&t, r->cursor, sizeof(t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    RO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *total = (int64_t)t;
+    return QC_OK;
+}
+
+extern "C" float* qc_replay_data(qc_replay* r) { return r ? r->ring : nullptr; }
+
+extern "C" int qc_replay_read(qc_replay* r, int64_t first_row, int64_t n_rows, float* host, void* stream) {
+    if (!r || !host || first_row < 0 || n_rows < 0 || n_rows > r->capacity) return set_error(QC_ERR_ARG, "qc_replay_read: bad argument");
+    RO_CUDA(cudaSetDevice(r->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t s = first_row % r->capacity, n1 = std::min(n_rows, r->capacity - s);
+    if (n1 > 0) RO_CUDA(cudaMemcpyAsync(host, r->ring + (size_t)s * r->row_len, sizeof(float) * (size_t)n1 * r->row_len, cudaMemcpyDeviceToHost, st));
+    if (n_rows > n1) RO_CUDA(cudaMemcpyAsync(host + (size_t)n1 * r->row_len, r->ring, sizeof(float) * (size_t)(n_rows - n1) * r->row_len, cudaMemcpyDeviceToHost, st));
+    RO_CUDA(cudaStreamSynchronize(st));
+    return QC_OK;
+}
+
+// ---- measurement record --------------------------------------------------------------------------------------------------------
+struct qc_record {
+    int64_t B = 0; int RL = 0, cg = 0, CL = 0, RLC = 0, NF = 0, device = 0;
+    int head = 0, head_f = 0;                 // next write position of the two rings (all trajectories advance in lock step)
+    float *meas = nullptr, *forces = nullptr;
+};
+
+extern "C" int qc_record_create(int64_t B, int32_t read_length, int32_t coarse_grain, int32_t control_len, int32_t device, qc_record** out) {
+    if (!out) return set_error(QC_ERR_ARG, "qc_record_create: out is NULL");
+    *out = nullptr;
+    if (int rc = use_device(device)) return rc;
+    if (B < 1 || read_length < 1 || coarse_grain < 1 || control_len < 1 || read_length % control_len != 0)
+        return set_error(QC_ERR_ARG, "qc_record_create: read_length must be a positive multiple of control_len (H/main_parallel.py:147-148,261)");
+    qc_record* r = new (std::nothrow) qc_record();
+    if (!r) return set_error(QC_ERR_CUDA, "out of host memory");
+    r->B = B; r->RL = read_length; r->cg = coarse_grain; r->CL = control_len; r->RLC = read_length + control_len; r->NF = read_length / control_len + 1; r->device = device;
+    if (cudaMalloc(&r->meas, sizeof(float) * (size_t)B * r->RLC) != cudaSuccess || cudaMalloc(&r->forces, sizeof(float) * (size_t)B * r->NF) != cudaSuccess) {
+        cudaGetLastError(); qc_record_destroy(r); return set_error(QC_ERR_CUDA, "cudaMalloc failed for the measurement record");
+    }
+    RO_CUDA(cudaMemset(r->meas, 0, sizeof(float) * (size_t)B * r->RLC));
+    RO_CUDA(cudaMemset(r->forces, 0, sizeof(float) * (size_t)B * r->NF));
+    *out = r;
+    return QC_OK;
+}
+
+extern "C" int qc_record_destroy(qc_record* r) {
+    if (!r) return QC_OK;
+    cudaSetDevice(r->device);
+    cudaFree(r->meas); cudaFree(r->forces);
+    delete r;
+    return QC_OK;
+}
+
+extern "C" int64_t qc_record_row_len(const qc_record* r) { return r ? (int64_t)r->RLC + r->NF : set_error(QC_ERR_ARG, "qc_record_row_len: NULL handle"); }
+
+extern "C" int qc_record_reset(qc_record* r, const uint8_t* mask, void* stream) {
+    if (!r) return set_error(QC_ERR_ARG, "qc_record_reset: NULL handle");
+    RO_CUDA(cudaSetDevice(r->device));
+    record_reset_kernel<<<blocks_for(r->B * (r->RLC + r->NF), 256), 256, 0, (cudaStream_t)stream>>>(r->meas, r->forces, r->B, r->RLC, r->NF, mask);
+    RO_CUDA(cudaGetLastError());
+    return QC_OK;
+}
+
+extern "C" int qc_record_push(qc_record* r, const double* q, int32_t n_sub, const double* force, double input_scaling, void* stream) {
+    if (!r || !q || !force) return set_error(QC_ERR_ARG, "qc_record_push: NULL argument");
+    if (n_sub != r->CL * r->cg) return set_error(QC_ERR_ARG, "qc_record_push: n_sub must equal control_len * coarse_grain");
+    RO_CUDA(cudaSetDevice(r->device));
+    record_push_kernel<<<blocks_for(r->B * r->CL, 256), 256, 0, (cudaStream_t)stream>>>(r->meas, r->forces, r->B, r->RLC, r->NF, r->head, r->head_f, q, n_sub, r->cg, r->CL,
+                                                                                      force, input_scaling);
+    RO_CUDA(cudaGetLastError());
+    r->head = (r->head + r->CL) % r->RLC; r->head_f = (r->head_f + 1) % r->NF;
+    return QC_OK;
+}
+
+extern "C" int qc_record_window(qc_record* r, float* out, void* stream) {
+    if (!r || !out) return set_error(QC_ERR_ARG, "qc_record_window: NULL argument");
+    RO_CUDA(cudaSetDevice(r->device));
+    record_window_kernel<<<blocks_for(r->B * r->RL, 256), 256, 0, (cudaStream_t)stream>>>(r->meas, r->forces, r->B, r->RL, r->RLC, r->NF, r->CL, r->head, r->head_f, out);
+    RO_CUDA(cudaGetLastError());
+    return QC_OK;
+}
+
+extern "C" int qc_record_experience(qc_record* r, float* out, void* stream) {
+    if (!r || !out) return set_error(QC_ERR_ARG, "qc_record_experience: NULL argument");
+    RO_CUDA(cudaSetDevice(r->device));
+    record_experience_kernel<<<blocks_for(r->B * (r->RLC + r->NF), 256), 256, 0, (cudaStream_t)stream>>>(r->meas, r->forces, r->B, r->RLC, r->NF, r->head, r->head_f, out);
+    RO_CUDA(cudaGetLastError());
+    return QC_OK;
+}

@@ -33,8 +33,8 @@ class QuantumCartpoleEnv:
         return self.torch.full((self.B,), int(value), dtype=self.torch.int32, device=self.dev)
 
     def _obs(self, out):
-        # get_data_xp: float32 moments * input_scaling (quartic main_parallel.py:128-131,210)
-        return (out["moments"] * self.input_scaling).to(self.torch.float32)
+        # get_data_xp returns float32, then `* args.input_scaling` in float32 (quartic main_parallel.py:128-131,210)
+        return out["moments"].to(self.torch.float32) * self.input_scaling
 
     def observation_size(self):
         return self.K

@@ -193,6 +193,58 @@ def make_controller_fixture():
     print("wrote controllers_reference_python.npz")
 
 
+def extract_classes(path, names, namespace):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tree = ast.parse(open(path).read())
+    picked = [node for node in tree.body if isinstance(node, ast.ClassDef) and node.name in names]
+    assert len(picked) == len(names), names
+    exec(compile(ast.Module(body=picked, type_ignores=[]), path, "exec"), namespace)
+    return namespace
+
+
+def make_policy_fixture():
+    """The reference's own `direct_DQN` (quartic oscillator/RL.py:81-112; RL.py itself imports numba/termcolor and cannot be imported, so
+    the class is extracted by AST) on top of its own layers.py (imported as is), evaluated in float32 on the CPU with the synthetic
+    state_dict of oracle/rollout_oracle.py:policy_state_dict.  Stores inputs, the noise the reference drew, and its outputs."""
+    import importlib.util
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from oracle import rollout_oracle as RO
+    spec = importlib.util.spec_from_file_location("layers", os.path.join(REF, "quartic oscillator", "layers.py"))
+    layers = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(layers)
+    ns = {"nn": nn, "F": F, "torch": torch, "layers": layers, "F_max": 5., "print": lambda *a, **k: None}
+    extract_classes(os.path.join(REF, "quartic oscillator", "RL.py"), ["direct_DQN"], ns)
+    out = {}
+    for tag, n_in, noisy_layers, seed in (("grid", 20, 2, 101), ("fock", 5, 2, 102)):     # noisy_layers < 2 does not run in the reference (RL.py:103 unpacks a tuple)
+        torch.manual_seed(seed)
+        net = ns["direct_DQN"](n_in, noisy_layers=noisy_layers)
+        sd = RO.policy_state_dict(seed, n_in=n_in, noisy_layers=noisy_layers)
+        net.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+        net.eval()
+        rng = np.random.Generator(np.random.PCG64(seed + 1))
+        B = 6                                                        # not a multiple of 128 -> per-sample noise branch (layers.py:41-57)
+        x = (rng.standard_normal((B, n_in)) * 2.0).astype(np.float32)
+        with torch.no_grad():
+            action, mean, _ = net(torch.as_tensor(x))
+        out[tag + "_x"] = x
+        out[tag + "_action_values"] = action.numpy()
+        out[tag + "_mean"] = mean.numpy()
+        out[tag + "_argmax"] = action.max(1)[1].numpy()
+        if noisy_layers == 2:
+            for name in ("fc31", "fc41"):
+                layer = getattr(net, name)
+                i = layer.randbuffer_pointer - B
+                out["%s_%s_rand_in" % (tag, name)] = layer.randbuffer_in[i:i + B, 0, :].numpy()
+                out["%s_%s_rand_out" % (tag, name)] = layer.randbuffer_out[i:i + B, :, 0].numpy()
+            # (`noisy = False` makes FactorizedNoisy return a bare tensor, which RL.py:103 cannot unpack: the reference always acts with noise on)
+        out[tag + "_force_of_action"] = np.array([net.convert_to_force(int(a)) for a in range(21)])
+    np.savez_compressed(os.path.join(HERE, "policy_reference_python.npz"), **out)
+    print("wrote policy_reference_python.npz")
+
+
 if __name__ == "__main__":
     from deepreinforcementlearningcontrolofquantumcartpoles_b200 import configs
     make_grid_fixture("grid_reference_python_quartic.npz", "quartic oscillator", configs.quartic())
@@ -201,3 +253,4 @@ if __name__ == "__main__":
     make_oracle_fixture()
     make_reference_build_fixture()
     make_controller_fixture()
+    make_policy_fixture()

@@ -1,4 +1,4 @@
-"""The C-ABI library loads on a CPU-only box and exports every symbol include/qcart.h declares; compute entry points fail loudly
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/*.h declare; compute entry points fail loudly
 without a device (no CPU fallback)."""
 import ctypes as C
 import os
@@ -12,9 +12,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    txt = open(os.path.join(ROOT, "include", "qcart.h")).read()
-    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(qc_[a-z0-9_]+)\s*\(", txt)))
+    names = set()
+    for header in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if not header.endswith(".h"):
+            continue
+        txt = open(os.path.join(ROOT, "include", header)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        names.update(re.findall(r"\b(qc_[a-z0-9_]+)\s*\(", txt))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
