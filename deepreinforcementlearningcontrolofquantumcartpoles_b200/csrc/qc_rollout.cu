@@ -2,16 +2,17 @@
 // reference's direct_DQN policy on the whole batch, epsilon-greedy action selection, the experience-row ring and the measurement record.
 //
 // The policy is GEMM-shaped but small (0.55 MFMA per trajectory, 2-8 % of the SSE step's time) and the reference evaluates it in fp32
-// (torch modules, no TF32), so it runs as fp32 FMA on the CUDA cores: a 64x64x16 register-tiled kernel per hidden layer with the bias /
-// ReLU / factorised-noise epilogue fused, and one warp per trajectory for the n_actions-wide output layer + argmax.  A noisy layer
+// (torch modules, no TF32), so it runs as fp32 FMA on the CUDA cores: a 64x64x16 register-tiled kernel with an in-CTA split over K per hidden layer
+// and a warp-per-trajectory kernel (lane = action) for the n_actions-wide output layer + argmax.  A noisy layer
 // (layers.py:42-57, per-sample noise) is evaluated WITHOUT materialising the per-sample weight matrix w = u_w + sigma_w * (e_out e_in^T):
 //     y = x u_w^T + u_b + e_out * ((x * e_in) sigma_w^T + sigma_b)
-// i.e. a second accumulator over the same tiles.
+// i.e. two GEMMs over the same inputs (blockIdx.z) whose halves are combined where the next layer loads its input.
 #include "qc_internal.h"
 #include "qc_philox.cuh"
 #include "../../include/qcart_rollout.h"
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -42,71 +43,74 @@ __global__ void obs_kernel(const double* __restrict__ m, int64_t count, float sc
     if (i < count) obs[i] = (float)m[i] * scale;
 }
 
-// h[b, o] = relu(b1[o] + sum_i W1[o, i] x[b, i]);  n_in is small (20 grid moments / 5 Fock moments): one CTA per 32 rows
-__global__ void __launch_bounds__(256) fc1_kernel(const float* __restrict__ obs, const float* __restrict__ W, const float* __restrict__ bias,
+// h[b, o] = relu(b1[o] + sum_i W1[o, i] x[b, i]);  n_in is small (20 grid moments / 5 Fock moments): one CTA per 8 rows, one thread per output
+constexpr int FC1_ROWS = 8;
+__global__ void __launch_bounds__(512) fc1_kernel(const float* __restrict__ obs, const float* __restrict__ W, const float* __restrict__ bias,
                                                   float* __restrict__ h, int64_t B, int n_in, int n_out) {
-    constexpr int ROWS = 32;
-    extern __shared__ float xs[];                      // [ROWS][n_in]
-    const int64_t m0 = (int64_t)blockIdx.x * ROWS;
-    const int rows = (int)min((int64_t)ROWS, B - m0);
-    for (int e = threadIdx.x; e < ROWS * n_in; e += blockDim.x) xs[e] = (e < rows * n_in) ? obs[m0 * n_in + e] : 0.0f;
+    extern __shared__ float xs[];                      // [FC1_ROWS][n_in]
+    const int64_t m0 = (int64_t)blockIdx.x * FC1_ROWS;
+    const int rows = (int)min((int64_t)FC1_ROWS, B - m0);
+    for (int e = threadIdx.x; e < FC1_ROWS * n_in; e += blockDim.x) xs[e] = (e < rows * n_in) ? obs[m0 * n_in + e] : 0.0f;
     __syncthreads();
     for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+        float acc[FC1_ROWS];
         const float b0 = bias[o];
-        for (int r0 = 0; r0 < rows; r0 += 8) {
-            float acc[8];
 #pragma unroll
-            for (int r = 0; r < 8; r++) acc[r] = b0;
-            for (int i = 0; i < n_in; i++) {
-                const float w = __ldg(&W[(size_t)o * n_in + i]);
+        for (int r = 0; r < FC1_ROWS; r++) acc[r] = b0;
+        for (int i = 0; i < n_in; i++) {
+            const float w = __ldg(&W[(size_t)o * n_in + i]);
 #pragma unroll
-                for (int r = 0; r < 8; r++) acc[r] = fmaf(xs[(r0 + r) * n_in + i], w, acc[r]);
-            }
-#pragma unroll
-            for (int r = 0; r < 8; r++) if (r0 + r < rows) h[(m0 + r0 + r) * n_out + o] = fmaxf(acc[r], 0.0f);
+            for (int r = 0; r < FC1_ROWS; r++) acc[r] = fmaf(xs[r * n_in + i], w, acc[r]);
         }
+#pragma unroll
+        for (int r = 0; r < FC1_ROWS; r++) if (r < rows) h[(m0 + r) * n_out + o] = fmaxf(acc[r], 0.0f);
     }
 }
 
-// C[M, N] = act(A[M, K] W[N, K]^T + bias (+ eo * ((A * ei) S[N, K]^T + sbias)))      N % 64 == 0, K % 16 == 0
+// C_z[M, N] = A_z[M, K] W_z[N, K]^T   (N % 64 == 0, K % 16 == 0), z = blockIdx.z:
+//   z = 0: A_0 = A,  W_0 = W, optional epilogue relu(. + bias), optional second output C2 = C * ei (the input-noise-scaled copy the
+//          sigma_w half of the NEXT noisy layer consumes: fused here so that no GEMM has to touch the noise inside its K loop)
+//   z = 1: A_1 = A2, W_1 = S, written to C + M*N                      (the sigma_w half of a noisy layer)
+// One 64x64 output tile per CTA, 4x4 per thread, 256 threads per K-group.  NG = 1: the whole K range in one group, several CTAs resident
+// per SM (large batches).  NG = 4: the K range split over four groups of 256 threads that synchronise on their own named barrier and are
+// summed through shared memory in a fixed order (deterministic) -- at the reference's batch sizes (1e3 trajectories) a hidden layer is
+// only ~128 tiles, too few warps to hide the LDS / L2 latency on 148 SMs, and splitting K over CTAs would need a second pass over C.
 struct GemmArgs {
-    const float* A; const float* W; const float* S; const float* bias; const float* sbias;
-    const float* ei; const float* eo; int ldn;          // per-sample noise rows: ei[m * ldn + k], eo[m * ldn + n]
-    float* C; int M, N, K;
+    const float* A; const float* A2; const float* W; const float* S; const float* bias;
+    const float* ei; int ldn;                            // per-sample noise rows: ei[m * ldn + n]  (epilogue only)
+    float* C; float* C2; int M, N, K; int relu_bias;
 };
 constexpr int BM = 64, BN = 64, BK = 16, LDT = BM + 4;
+constexpr int TILE_FLOATS = 2 * BK * LDT;               // As + Ws of one group
 
-template <bool NOISY, bool RELU>
-__global__ void __launch_bounds__(256) gemm_tn_kernel(const GemmArgs g) {
-    __shared__ __align__(16) float As[BK][LDT], Ws[BK][LDT];
-    __shared__ __align__(16) float A2s[NOISY ? BK : 1][LDT], Ss[NOISY ? BK : 1][LDT];
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+template <int NG>
+__global__ void __launch_bounds__(NG * 256, NG == 1 ? 4 : 1) gemm_splitk_kernel(const GemmArgs g) {
+    extern __shared__ __align__(16) float gsm[];
+    const int gi = threadIdx.x >> 8, tid = threadIdx.x & 255, ty = tid >> 4, tx = tid & 15;
+    float (*As)[LDT] = reinterpret_cast<float (*)[LDT]>(gsm + gi * TILE_FLOATS);
+    float (*Ws)[LDT] = reinterpret_cast<float (*)[LDT]>(gsm + gi * TILE_FLOATS + BK * LDT);
+    float* red = gsm + NG * TILE_FLOATS;                 // [(NG-1)][64*64]
+    const int z = blockIdx.z;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int lrow = tid >> 2, lk = (tid & 3) * 4;                // this thread's float4 of the A / W tile
+    const int lrow = tid >> 2, lk = (tid & 3) * 4;       // this thread's float4 of the A / W tile
     const bool arow_ok = (m0 + lrow) < g.M;
-    const float* ap = g.A + (size_t)(m0 + lrow) * g.K + lk;
-    const float* wp = g.W + (size_t)(n0 + lrow) * g.K + lk;
-    const float* sp = NOISY ? g.S + (size_t)(n0 + lrow) * g.K + lk : nullptr;
-    const float* ep = NOISY ? g.ei + (size_t)(m0 + lrow) * g.ldn + lk : nullptr;
-    float acc[4][4], acc2[NOISY ? 4 : 1][4];
+    const float* ap = (z == 0 ? g.A : g.A2) + (size_t)(m0 + lrow) * g.K + lk;
+    const float* wp = (z == 0 ? g.W : g.S) + (size_t)(n0 + lrow) * g.K + lk;
+    float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) { acc[i][j] = 0.0f; if constexpr (NOISY) acc2[i][j] = 0.0f; }
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 ra = arow_ok ? *reinterpret_cast<const float4*>(ap) : z4, rw = *reinterpret_cast<const float4*>(wp), re = z4, rs = z4;
-    if constexpr (NOISY) { re = arow_ok ? *reinterpret_cast<const float4*>(ep) : z4; rs = *reinterpret_cast<const float4*>(sp); }
-    for (int k0 = 0; k0 < g.K; k0 += BK) {
+    int k0 = gi * BK;
+    float4 ra = z4, rw = z4;
+    if (k0 < g.K) { ra = arow_ok ? *reinterpret_cast<const float4*>(ap + k0) : z4; rw = *reinterpret_cast<const float4*>(wp + k0); }
+    for (; k0 < g.K; k0 += NG * BK) {
         As[lk + 0][lrow] = ra.x; As[lk + 1][lrow] = ra.y; As[lk + 2][lrow] = ra.z; As[lk + 3][lrow] = ra.w;
         Ws[lk + 0][lrow] = rw.x; Ws[lk + 1][lrow] = rw.y; Ws[lk + 2][lrow] = rw.z; Ws[lk + 3][lrow] = rw.w;
-        if constexpr (NOISY) {
-            A2s[lk + 0][lrow] = ra.x * re.x; A2s[lk + 1][lrow] = ra.y * re.y; A2s[lk + 2][lrow] = ra.z * re.z; A2s[lk + 3][lrow] = ra.w * re.w;
-            Ss[lk + 0][lrow] = rs.x; Ss[lk + 1][lrow] = rs.y; Ss[lk + 2][lrow] = rs.z; Ss[lk + 3][lrow] = rs.w;
-        }
-        __syncthreads();
-        if (k0 + BK < g.K) {                                       // prefetch the next tile into registers while this one is consumed
-            ra = arow_ok ? *reinterpret_cast<const float4*>(ap + k0 + BK) : z4; rw = *reinterpret_cast<const float4*>(wp + k0 + BK);
-            if constexpr (NOISY) { re = arow_ok ? *reinterpret_cast<const float4*>(ep + k0 + BK) : z4; rs = *reinterpret_cast<const float4*>(sp + k0 + BK); }
+        asm volatile("bar.sync %0, 256;" ::"r"(gi + 1) : "memory");
+        if (k0 + NG * BK < g.K) {                        // next tile -> registers while this one is consumed
+            ra = arow_ok ? *reinterpret_cast<const float4*>(ap + k0 + NG * BK) : z4; rw = *reinterpret_cast<const float4*>(wp + k0 + NG * BK);
         }
 #pragma unroll
         for (int k = 0; k < BK; k++) {
@@ -116,70 +120,115 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const GemmArgs g) {
             for (int i = 0; i < 4; i++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
-            if constexpr (NOISY) {
-                const float4 a2 = *reinterpret_cast<const float4*>(&A2s[k][ty * 4]), s = *reinterpret_cast<const float4*>(&Ss[k][tx * 4]);
-                const float a2v[4] = {a2.x, a2.y, a2.z, a2.w}, sv[4] = {s.x, s.y, s.z, s.w};
+        }
+        asm volatile("bar.sync %0, 256;" ::"r"(gi + 1) : "memory");
+    }
+    if (NG > 1) {
+        if (gi > 0) {
 #pragma unroll
-                for (int i = 0; i < 4; i++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) acc2[i][j] = fmaf(a2v[i], sv[j], acc2[i][j]);
-            }
+            for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(&red[(size_t)(gi - 1) * BM * BN + (ty * 4 + i) * BN + tx * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
         __syncthreads();
+        if (gi > 0) return;
+#pragma unroll
+        for (int h = 0; h < NG - 1; h++)                 // fixed order: deterministic
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float4 r = *reinterpret_cast<const float4*>(&red[(size_t)h * BM * BN + (ty * 4 + i) * BN + tx * 4]);
+                acc[i][0] += r.x; acc[i][1] += r.y; acc[i][2] += r.z; acc[i][3] += r.w;
+            }
     }
     const int n = n0 + tx * 4;
-    const float4 b4 = *reinterpret_cast<const float4*>(g.bias + n);
-    const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
-    float sbv[4] = {0.f, 0.f, 0.f, 0.f};
-    if constexpr (NOISY) { const float4 s4 = *reinterpret_cast<const float4*>(g.sbias + n); sbv[0] = s4.x; sbv[1] = s4.y; sbv[2] = s4.z; sbv[3] = s4.w; }
+    const bool epi = g.relu_bias && z == 0;
+    float4 b4 = z4;
+    if (epi) b4 = *reinterpret_cast<const float4*>(g.bias + n);
+    float* C = g.C + (size_t)z * g.M * g.N;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int m = m0 + ty * 4 + i;
         if (m >= g.M) continue;
-        float v[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            v[j] = acc[i][j] + bv[j];
-            if constexpr (NOISY) v[j] = fmaf(g.eo[(size_t)m * g.ldn + n + j], acc2[i][j] + sbv[j], v[j]);
-            if (RELU) v[j] = fmaxf(v[j], 0.0f);
+        float4 s = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (epi) { s.x = fmaxf(s.x + b4.x, 0.0f); s.y = fmaxf(s.y + b4.y, 0.0f); s.z = fmaxf(s.z + b4.z, 0.0f); s.w = fmaxf(s.w + b4.w, 0.0f); }
+        *reinterpret_cast<float4*>(C + (size_t)m * g.N + n) = s;
+        if (g.C2 != nullptr && z == 0) {
+            const float4 e = *reinterpret_cast<const float4*>(g.ei + (size_t)m * g.ldn + n);
+            *reinterpret_cast<float4*>(g.C2 + (size_t)m * g.N + n) = make_float4(s.x * e.x, s.y * e.y, s.z * e.z, s.w * e.w);
         }
-        *reinterpret_cast<float4*>(g.C + (size_t)m * g.N + n) = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
-// Output layer (K = 256 inputs, A <= 32 outputs) + argmax: one warp per trajectory, inputs in registers.
-template <bool NOISY>
-__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ x, const float* __restrict__ U, const float* __restrict__ S,
-                                                   const float* __restrict__ ub, const float* __restrict__ sb, const float* __restrict__ ei,
-                                                   const float* __restrict__ eo, int ldn, int A, float* __restrict__ q, int32_t* __restrict__ greedy, int64_t B) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= B) return;
-    float xv[H3 / 32], x2[H3 / 32];
-#pragma unroll
-    for (int t = 0; t < H3 / 32; t++) {
-        xv[t] = x[row * H3 + lane + 32 * t];
-        if constexpr (NOISY) x2[t] = xv[t] * ei[row * ldn + lane + 32 * t]; else x2[t] = 0.0f;
+// Output layer + argmax.  Input: the two raw halves y1 = h2 u_w31^T, y2 = (h2 * e_in31) sigma_w31^T of the (noisy) fc31 layer; this kernel
+// first forms  x = relu(y1 + u_b31 + e_out31 * (y2 + sigma_b31))  (layers.py:52-56), then the n_actions-wide noisy layer fc41 and the argmax.
+// The transposed u_w41 / sigma_w41 are staged in shared memory once per CTA; lane o of a warp owns output o, a warp handles HR rows at a time.
+struct HeadArgs {
+    const float* y1; const float* y2;                   // [B, 256] each (y2 unused when !noisy31)
+    const float* ub31; const float* sb31;
+    const float* U; const float* S; const float* ub; const float* sb;     // fc41: [A, 256], [A]
+    const float* nz; int ldn;                           // per-sample noise rows: eo31 at +512, ei41 at +768, eo41 at +1024
+    int A; int noisy31, noisy41;
+    float* q; int32_t* greedy; int64_t B;
+};
+constexpr int HR = 4, HEAD_WARPS = 8;
+
+__global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs h) {
+    extern __shared__ __align__(16) float hsm[];
+    float* Ut = hsm;                                     // [256][32]  (u_w41 transposed, outputs padded to 32)
+    float* St = hsm + H3 * 32;                           // [256][32]
+    float* xrow = hsm + 2 * H3 * 32;                     // [HEAD_WARPS][HR][2][256]: x and x * e_in41
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < H3 * 32; e += blockDim.x) {
+        const int i = e >> 5, o = e & 31;
+        Ut[e] = (o < h.A) ? __ldg(&h.U[(size_t)o * H3 + i]) : 0.0f;
+        St[e] = (o < h.A && h.noisy41) ? __ldg(&h.S[(size_t)o * H3 + i]) : 0.0f;
     }
-    float best = 0.0f; int besti = 0;
-    for (int o = 0; o < A; o++) {
-        float d1 = 0.0f, d2 = 0.0f;
+    __syncthreads();
+    float* xs = xrow + (size_t)wid * HR * 2 * H3;
+    const float ubo = (lane < h.A) ? h.ub[lane] : 0.0f, sbo = (lane < h.A && h.noisy41) ? h.sb[lane] : 0.0f;
+    const int64_t rows_per_cta = HEAD_WARPS * HR;
+    for (int64_t r0 = (int64_t)blockIdx.x * rows_per_cta + wid * HR; r0 < h.B; r0 += (int64_t)gridDim.x * rows_per_cta) {
+        __syncwarp();
 #pragma unroll
-        for (int t = 0; t < H3 / 32; t++) {
-            d1 = fmaf(xv[t], __ldg(&U[(size_t)o * H3 + lane + 32 * t]), d1);
-            if constexpr (NOISY) d2 = fmaf(x2[t], __ldg(&S[(size_t)o * H3 + lane + 32 * t]), d2);
+        for (int r = 0; r < HR; r++) {
+            const int64_t row = r0 + r;
+#pragma unroll
+            for (int t = 0; t < H3 / 32; t++) {
+                const int i = lane + 32 * t;
+                float x = 0.0f, x2 = 0.0f;
+                if (row < h.B) {
+                    x = h.y1[row * H3 + i] + h.ub31[i];
+                    if (h.noisy31) x = fmaf(h.nz[row * h.ldn + H2 + i], h.y2[row * H3 + i] + h.sb31[i], x);
+                    x = fmaxf(x, 0.0f);
+                    if (h.noisy41) x2 = x * h.nz[row * h.ldn + H2 + H3 + i];
+                }
+                xs[(r * 2 + 0) * H3 + i] = x; xs[(r * 2 + 1) * H3 + i] = x2;
+            }
+        }
+        __syncwarp();
+        float d1[HR], d2[HR];
+#pragma unroll
+        for (int r = 0; r < HR; r++) { d1[r] = 0.0f; d2[r] = 0.0f; }
+#pragma unroll 4
+        for (int i = 0; i < H3; i++) {
+            const float u = Ut[i * 32 + lane], s = St[i * 32 + lane];
+#pragma unroll
+            for (int r = 0; r < HR; r++) { d1[r] = fmaf(xs[(r * 2 + 0) * H3 + i], u, d1[r]); d2[r] = fmaf(xs[(r * 2 + 1) * H3 + i], s, d2[r]); }
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            d1 += __shfl_xor_sync(0xffffffffu, d1, off);
-            if constexpr (NOISY) d2 += __shfl_xor_sync(0xffffffffu, d2, off);
+        for (int r = 0; r < HR; r++) {
+            const int64_t row = r0 + r;
+            if (row >= h.B) continue;                    // uniform over the warp
+            float v = d1[r] + ubo;
+            if (h.noisy41) v = fmaf(h.nz[row * h.ldn + H2 + H3 + H3 + min(lane, h.A - 1)], d2[r] + sbo, v);
+            if (lane < h.A && h.q) h.q[row * h.A + lane] = v;
+            float best = (lane < h.A) ? v : -INFINITY; int besti = lane;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {     // first maximum, like torch.max(1)[1]
+                const float ob = __shfl_xor_sync(0xffffffffu, best, off); const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
+                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            }
+            if (lane == 0 && h.greedy) h.greedy[row] = besti;
         }
-        float v = d1 + ub[o];
-        if constexpr (NOISY) v = fmaf(eo[row * ldn + o], d2 + sb[o], v);
-        if (o == 0 || v > best) { best = v; besti = o; }           // first maximum, like torch.max(1)[1]
-        if (lane == 0 && q) q[row * A + o] = v;
     }
-    if (lane == 0 && greedy) greedy[row] = besti;
 }
 
 // value[b] = b42 + sum_i W42[i] v[b, i]   (fc42, 128 -> 1)
@@ -334,7 +383,7 @@ struct qc_policy {
     float* param[QC_P_COUNT] = {};
     int64_t psize[QC_P_COUNT] = {};
     bool pset[QC_P_COUNT] = {};
-    float *h1 = nullptr, *h2 = nullptr, *a3 = nullptr, *hv = nullptr, *noise = nullptr;
+    float *h1 = nullptr, *h2 = nullptr, *h2n = nullptr, *a3 = nullptr, *hv = nullptr, *noise = nullptr;
     int64_t cap = 0;
     int64_t launches = 0;
 };
@@ -376,7 +425,7 @@ extern "C" int qc_policy_destroy(qc_policy* p) {
     if (!p) return QC_OK;
     cudaSetDevice(p->device);
     for (int i = 0; i < QC_P_COUNT; i++) cudaFree(p->param[i]);
-    cudaFree(p->h1); cudaFree(p->h2); cudaFree(p->a3); cudaFree(p->hv); cudaFree(p->noise);
+    cudaFree(p->h1); cudaFree(p->h2); cudaFree(p->h2n); cudaFree(p->a3); cudaFree(p->hv); cudaFree(p->noise);
     delete p;
     return QC_OK;
 }
@@ -403,17 +452,30 @@ extern "C" int qc_policy_set_param(qc_policy* p, int32_t which, const float* hos
     return QC_OK;
 }
 
-template <bool RELU>
-static void launch_gemm(bool noisy, const GemmArgs& g, cudaStream_t st) {
-    const dim3 grid(g.N / BN, (g.M + BM - 1) / BM);
-    if (noisy) gemm_tn_kernel<true, RELU><<<grid, 256, 0, st>>>(g);
-    else gemm_tn_kernel<false, RELU><<<grid, 256, 0, st>>>(g);
+constexpr size_t GEMM_SMEM_1 = sizeof(float) * (size_t)TILE_FLOATS;
+constexpr size_t GEMM_SMEM_4 = sizeof(float) * ((size_t)4 * TILE_FLOATS + (size_t)3 * BM * BN);
+constexpr size_t HEAD_SMEM = sizeof(float) * ((size_t)2 * H3 * 32 + (size_t)HEAD_WARPS * HR * 2 * H3);
+
+static int launch_gemm(const GemmArgs& g, int nz, cudaStream_t st) {
+    static thread_local bool attr_set[64] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        RO_CUDA(cudaFuncSetAttribute(gemm_splitk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_4));
+        RO_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM));
+        attr_set[dev] = true;
+    }
+    const dim3 grid(g.N / BN, (g.M + BM - 1) / BM, nz);
+    static const int force_ng = getenv("QCART_GEMM_NG") ? atoi(getenv("QCART_GEMM_NG")) : 0;
+    const bool small = force_ng ? force_ng == 4 : (size_t)grid.x * grid.y * grid.z < 4 * 148;      // fewer tiles than 4 per SM: split K inside the CTA
+    if (small) gemm_splitk_kernel<4><<<grid, 4 * 256, GEMM_SMEM_4, st>>>(g);
+    else gemm_splitk_kernel<1><<<grid, 256, GEMM_SMEM_1, st>>>(g);
+    return QC_OK;
 }
 
 extern "C" int qc_policy_forward(qc_policy* p, const float* obs, int64_t B, int32_t noise_mode, const float* noise, uint64_t seed,
                                  int64_t traj_offset, uint64_t counter, float* q, float* value, int32_t* greedy, void* stream) {
     if (!p || !obs) return set_error(QC_ERR_ARG, "qc_policy_forward: NULL handle or observation pointer");
-    if (B < 0 || B > (int64_t)1 << 24) return set_error(QC_ERR_ARG, "qc_policy_forward: batch out of range");
+    if (B < 0 || B > (int64_t)1 << 22) return set_error(QC_ERR_ARG, "qc_policy_forward: batch out of range");
     if (noise_mode < QC_NOISE_OFF || noise_mode > QC_NOISE_PHILOX) return set_error(QC_ERR_ARG, "qc_policy_forward: unknown noise_mode");
     if (noise_mode == QC_NOISE_GIVEN && !noise) return set_error(QC_ERR_ARG, "qc_policy_forward: noise_mode GIVEN needs the noise rows");
     for (int i = 0; i < QC_P_COUNT; i++) if (!p->pset[i]) return set_error(QC_ERR_STATE, "qc_policy_forward: parameter tensor " + std::to_string(i) + " was never set");
@@ -422,10 +484,11 @@ extern "C" int qc_policy_forward(qc_policy* p, const float* obs, int64_t B, int3
     cudaStream_t st = (cudaStream_t)stream;
     const int NW = (int)qc_policy_noise_width(p);
     if (p->cap < B) {
-        cudaFree(p->h1); cudaFree(p->h2); cudaFree(p->a3); cudaFree(p->hv); cudaFree(p->noise);
-        p->h1 = p->h2 = p->a3 = p->hv = p->noise = nullptr; p->cap = 0;
+        cudaFree(p->h1); cudaFree(p->h2); cudaFree(p->h2n); cudaFree(p->a3); cudaFree(p->hv); cudaFree(p->noise);
+        p->h1 = p->h2 = p->h2n = p->a3 = p->hv = p->noise = nullptr; p->cap = 0;
         RO_CUDA(cudaMalloc(&p->h1, sizeof(float) * (size_t)B * H1)); RO_CUDA(cudaMalloc(&p->h2, sizeof(float) * (size_t)B * H2));
-        RO_CUDA(cudaMalloc(&p->a3, sizeof(float) * (size_t)B * H3)); RO_CUDA(cudaMalloc(&p->hv, sizeof(float) * (size_t)B * HV));
+        RO_CUDA(cudaMalloc(&p->h2n, sizeof(float) * (size_t)B * H2));
+        RO_CUDA(cudaMalloc(&p->a3, sizeof(float) * (size_t)B * H3 * 2)); RO_CUDA(cudaMalloc(&p->hv, sizeof(float) * (size_t)B * HV));
         RO_CUDA(cudaMalloc(&p->noise, sizeof(float) * ((size_t)B * NW + 4)));
         p->cap = B;
     }
@@ -438,27 +501,29 @@ extern "C" int qc_policy_forward(qc_policy* p, const float* obs, int64_t B, int3
             nz = p->noise;
         } else nz = noise;
     }
-    fc1_kernel<<<blocks_for(B, 32), 256, sizeof(float) * 32 * p->n_in, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], p->h1, B, p->n_in, H1);
+    fc1_kernel<<<blocks_for(B, FC1_ROWS), 512, sizeof(float) * FC1_ROWS * p->n_in, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], p->h1, B, p->n_in, H1);
     GemmArgs g{};
-    g.A = p->h1; g.W = p->param[QC_P_FC2_W]; g.bias = p->param[QC_P_FC2_B]; g.C = p->h2; g.M = (int)B; g.N = H2; g.K = H1; g.ldn = NW;
-    launch_gemm<true>(false, g, st);
     const bool n31 = any_noise && p->noisy_layers >= 2, n41 = any_noise && p->noisy_layers >= 1;
-    g = GemmArgs{};
-    g.A = p->h2; g.W = p->param[QC_P_FC31_UW]; g.S = p->param[QC_P_FC31_SW]; g.bias = p->param[QC_P_FC31_UB]; g.sbias = p->param[QC_P_FC31_SB];
-    g.ei = nz; g.eo = nz ? nz + H2 : nullptr; g.ldn = NW; g.C = p->a3; g.M = (int)B; g.N = H3; g.K = H2;
-    launch_gemm<true>(n31, g, st);
+    g.A = p->h1; g.W = p->param[QC_P_FC2_W]; g.bias = p->param[QC_P_FC2_B]; g.C = p->h2; g.M = (int)B; g.N = H2; g.K = H1; g.ldn = NW; g.relu_bias = 1;
+    if (n31) { g.C2 = p->h2n; g.ei = nz; }              // h2 * e_in31 for the sigma_w half of fc31
+    if (int rc = launch_gemm(g, 1, st)) return rc;
+    g = GemmArgs{};                                     // fc31: raw halves y1 (z = 0) and y2 (z = 1); combined by the head kernel
+    g.A = p->h2; g.A2 = p->h2n; g.W = p->param[QC_P_FC31_UW]; g.S = p->param[QC_P_FC31_SW]; g.ldn = NW; g.C = p->a3; g.M = (int)B; g.N = H3; g.K = H2; g.relu_bias = 0;
+    if (int rc = launch_gemm(g, n31 ? 2 : 1, st)) return rc;
     p->launches += 3;
     if (q || greedy) {
-        const unsigned nb = blocks_for(B, 8);
-        if (n41) head_kernel<true><<<nb, 256, 0, st>>>(p->a3, p->param[QC_P_FC41_UW], p->param[QC_P_FC41_SW], p->param[QC_P_FC41_UB], p->param[QC_P_FC41_SB],
-                                                        nz + H2 + H3, nz + H2 + H3 + H3, NW, p->n_actions, q, greedy, B);
-        else head_kernel<false><<<nb, 256, 0, st>>>(p->a3, p->param[QC_P_FC41_UW], nullptr, p->param[QC_P_FC41_UB], nullptr, nullptr, nullptr, NW, p->n_actions, q, greedy, B);
+        HeadArgs h{};
+        h.y1 = p->a3; h.y2 = p->a3 + (size_t)B * H3; h.ub31 = p->param[QC_P_FC31_UB]; h.sb31 = p->param[QC_P_FC31_SB];
+        h.U = p->param[QC_P_FC41_UW]; h.S = p->param[QC_P_FC41_SW]; h.ub = p->param[QC_P_FC41_UB]; h.sb = p->param[QC_P_FC41_SB];
+        h.nz = nz; h.ldn = NW; h.A = p->n_actions; h.noisy31 = n31 ? 1 : 0; h.noisy41 = n41 ? 1 : 0; h.q = q; h.greedy = greedy; h.B = B;
+        const unsigned nb = (unsigned)std::min<int64_t>((B + HEAD_WARPS * HR - 1) / (HEAD_WARPS * HR), 148 * 2);
+        head_kernel<<<nb, HEAD_WARPS * 32, HEAD_SMEM, st>>>(h);
         p->launches++;
     }
     if (value) {
         g = GemmArgs{};
-        g.A = p->h2; g.W = p->param[QC_P_FC32_W]; g.bias = p->param[QC_P_FC32_B]; g.C = p->hv; g.M = (int)B; g.N = HV; g.K = H2; g.ldn = NW;
-        launch_gemm<true>(false, g, st);
+        g.A = p->h2; g.W = p->param[QC_P_FC32_W]; g.bias = p->param[QC_P_FC32_B]; g.C = p->hv; g.M = (int)B; g.N = HV; g.K = H2; g.ldn = NW; g.relu_bias = 1;
+        if (int rc = launch_gemm(g, 1, st)) return rc;
         value_kernel<<<blocks_for(B, 8), 256, 0, st>>>(p->hv, p->param[QC_P_FC42_W], p->param[QC_P_FC42_B], value, B);
         p->launches += 2;
     }
