@@ -168,6 +168,48 @@ def run_reference(args, task, params):
     print(json.dumps(line), flush=True)
 
 
+def closed_loop_rate(sim, params, B, steps, warmup, out):
+    """SURVEY 8f rows 2-3 measured beside the SSE step: observation -> direct_DQN (noisy nets, in-kernel Philox noise) -> epsilon-greedy ->
+    SSE control step -> experience row, everything resident on the device (random-init weights of the reference's architecture)."""
+    import numpy as np
+    import torch
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200 import rollout as R, _lib as L
+    rng = np.random.default_rng(0)
+    pol = R.DirectDQNPolicy(sim.K, params["n_levels"])
+    for idx, name in enumerate(L.POLICY_PARAMS):
+        size = int(pol.lib.qc_policy_param_size(pol.h, idx))
+        lo, hi = (0.01, 0.03) if name.endswith(("SW", "SB")) else (-0.05, 0.05)
+        pol.set_param(name, rng.uniform(lo, hi, size).astype(np.float32))
+    ring = R.ReplayRing(sim.K, max(4 * B, 1 << 16))
+    obs = R.observation(out["moments"], 1.0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = pol.launch_count()
+    for i in range(warmup + steps):
+        if i == warmup:
+            torch.cuda.synchronize()
+            e0.record()
+        greedy = pol.forward(obs, noise="philox", seed=0, traj_offset=sim.traj_offset, counter=i, want_q=False)["greedy"]
+        action, _ = pol.epsilon_greedy(greedy, 0.05, seed=0, traj_offset=sim.traj_offset, counter=i)
+        sim.step(action, out=out)
+        obs2 = R.observation(out["moments"], 1.0)
+        ring.push(obs, obs2, action, out["aux"], reward_scale=-1.0, reward_stride=L.QC_AUX_COUNT)
+        obs = obs2
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    p0.record()
+    for i in range(steps):
+        greedy = pol.forward(obs, noise="philox", seed=0, traj_offset=sim.traj_offset, counter=i, want_q=False)["greedy"]
+        pol.epsilon_greedy(greedy, 0.05, seed=0, traj_offset=sim.traj_offset, counter=i)
+    p1.record()
+    torch.cuda.synchronize()
+    return {"value": B / (ms * 1e-3), "unit": "traj-control-steps/s", "ms_per_step": ms, "policy_ms_per_step": p0.elapsed_time(p1) / steps,
+            "policy": "direct_DQN %d-512-512-256-%d, factorised noisy layers, fp32 FMA kernels" % (sim.K, params["n_levels"]),
+            "policy_launches_per_step": (pol.launch_count() - l0) / (warmup + 2 * steps) + 1, "experience_rows": ring.total(),
+            "note": "no L2 flush; device-resident loop, no host synchronisation inside the timed region"}
+
+
 def workload_name(task, B, n, n_sub):
     return "%s SSE control step: %d trajectories/GPU, N=%d complex128, %d substeps/control step, 21 force levels" % (task, B, n, n_sub)
 
@@ -183,6 +225,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-traj-per-thread", type=int, default=0, help="0 = sized for ~2 s of CPU work per timed step")
     ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--no-closed-loop", action="store_true", help="skip the policy + experience-row closed-loop measurement (N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -286,6 +329,10 @@ def main():
         e2e_s = float(t.item())
     e2e_value = world * B * K_steps / e2e_s
 
+    closed_loop = None
+    if world == 1 and not args.no_closed_loop:
+        closed_loop = closed_loop_rate(sim, params, B, K_steps, min(W_steps, 10), out)
+
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -336,7 +383,7 @@ def main():
                        "parallelism": "%d rank(s), trajectories sharded, all-gather of [B,%d] f64 block per step" % (world, sim.K + 5) if world > 1 else "1 rank"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": "traj-control-steps/s", "h2d_bytes_per_step": B * 4,
                                       "d2h_bytes_per_step": B * (sim.K * 8 + L.QC_AUX_COUNT * 8 + 1)},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "closed_loop": closed_loop,
             "check": {"max_norm_deviation": norm_dev, "wall_s_timed_region": t_wall}}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(NG * 256, NG == 1 ? 4 : 1) gemm_splitk_kernel(
 
 // Output layer + argmax.  Input: the two raw halves y1 = h2 u_w31^T, y2 = (h2 * e_in31) sigma_w31^T of the (noisy) fc31 layer; this kernel
 // first forms  x = relu(y1 + u_b31 + e_out31 * (y2 + sigma_b31))  (layers.py:52-56), then the n_actions-wide noisy layer fc41 and the argmax.
-// The transposed u_w41 / sigma_w41 are staged in shared memory once per CTA; lane o of a warp owns output o, a warp handles HR rows at a time.
+// The transposed u_w41 / sigma_w41 are staged in shared memory once per CTA; lane o of a warp owns output o, one trajectory per warp at a time.
 struct HeadArgs {
     const float* y1; const float* y2;                   // [B, 256] each (y2 unused when !noisy31)
     const float* ub31; const float* sb31;
@@ -168,66 +168,54 @@ struct HeadArgs {
     int A; int noisy31, noisy41;
     float* q; int32_t* greedy; int64_t B;
 };
-constexpr int HR = 4, HEAD_WARPS = 8;
+constexpr int HEAD_WARPS = 8, HLD = 33;                 // transposed weight rows padded to 33 floats: conflict-free staging and reads
 
 __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs h) {
     extern __shared__ __align__(16) float hsm[];
-    float* Ut = hsm;                                     // [256][32]  (u_w41 transposed, outputs padded to 32)
-    float* St = hsm + H3 * 32;                           // [256][32]
-    float* xrow = hsm + 2 * H3 * 32;                     // [HEAD_WARPS][HR][2][256]: x and x * e_in41
+    float* Ut = hsm;                                     // [256][33]  (u_w41 transposed)
+    float* St = hsm + H3 * HLD;                          // [256][33]
+    float* xrow = hsm + 2 * H3 * HLD;                    // [HEAD_WARPS][2][256]: x and x * e_in41
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int e = threadIdx.x; e < H3 * 32; e += blockDim.x) {
-        const int i = e >> 5, o = e & 31;
-        Ut[e] = (o < h.A) ? __ldg(&h.U[(size_t)o * H3 + i]) : 0.0f;
-        St[e] = (o < h.A && h.noisy41) ? __ldg(&h.S[(size_t)o * H3 + i]) : 0.0f;
+        const int o = e >> 8, i = e & (H3 - 1);          // coalesced along i
+        Ut[i * HLD + o] = (o < h.A) ? __ldg(&h.U[(size_t)o * H3 + i]) : 0.0f;
+        St[i * HLD + o] = (o < h.A && h.noisy41) ? __ldg(&h.S[(size_t)o * H3 + i]) : 0.0f;
     }
     __syncthreads();
-    float* xs = xrow + (size_t)wid * HR * 2 * H3;
+    float* xs = xrow + (size_t)wid * 2 * H3;
     const float ubo = (lane < h.A) ? h.ub[lane] : 0.0f, sbo = (lane < h.A && h.noisy41) ? h.sb[lane] : 0.0f;
-    const int64_t rows_per_cta = HEAD_WARPS * HR;
-    for (int64_t r0 = (int64_t)blockIdx.x * rows_per_cta + wid * HR; r0 < h.B; r0 += (int64_t)gridDim.x * rows_per_cta) {
+    for (int64_t row = (int64_t)blockIdx.x * HEAD_WARPS + wid; row < h.B; row += (int64_t)gridDim.x * HEAD_WARPS) {
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < HR; r++) {
-            const int64_t row = r0 + r;
-#pragma unroll
-            for (int t = 0; t < H3 / 32; t++) {
-                const int i = lane + 32 * t;
-                float x = 0.0f, x2 = 0.0f;
-                if (row < h.B) {
-                    x = h.y1[row * H3 + i] + h.ub31[i];
-                    if (h.noisy31) x = fmaf(h.nz[row * h.ldn + H2 + i], h.y2[row * H3 + i] + h.sb31[i], x);
-                    x = fmaxf(x, 0.0f);
-                    if (h.noisy41) x2 = x * h.nz[row * h.ldn + H2 + H3 + i];
-                }
-                xs[(r * 2 + 0) * H3 + i] = x; xs[(r * 2 + 1) * H3 + i] = x2;
-            }
+        for (int t = 0; t < H3 / 32; t++) {
+            const int i = lane + 32 * t;
+            float x = h.y1[row * H3 + i] + h.ub31[i];
+            if (h.noisy31) x = fmaf(h.nz[row * h.ldn + H2 + i], h.y2[row * H3 + i] + h.sb31[i], x);
+            x = fmaxf(x, 0.0f);
+            xs[i] = x; xs[H3 + i] = h.noisy41 ? x * h.nz[row * h.ldn + H2 + H3 + i] : 0.0f;
         }
         __syncwarp();
-        float d1[HR], d2[HR];
-#pragma unroll
-        for (int r = 0; r < HR; r++) { d1[r] = 0.0f; d2[r] = 0.0f; }
+        float d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};          // four interleaved partial sums per output (ILP), fixed order
 #pragma unroll 4
-        for (int i = 0; i < H3; i++) {
-            const float u = Ut[i * 32 + lane], s = St[i * 32 + lane];
+        for (int i = 0; i < H3; i += 4) {
+            const float4 xa = *reinterpret_cast<const float4*>(&xs[i]), xb = *reinterpret_cast<const float4*>(&xs[H3 + i]);
+            const float xav[4] = {xa.x, xa.y, xa.z, xa.w}, xbv[4] = {xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-            for (int r = 0; r < HR; r++) { d1[r] = fmaf(xs[(r * 2 + 0) * H3 + i], u, d1[r]); d2[r] = fmaf(xs[(r * 2 + 1) * H3 + i], s, d2[r]); }
-        }
-#pragma unroll
-        for (int r = 0; r < HR; r++) {
-            const int64_t row = r0 + r;
-            if (row >= h.B) continue;                    // uniform over the warp
-            float v = d1[r] + ubo;
-            if (h.noisy41) v = fmaf(h.nz[row * h.ldn + H2 + H3 + H3 + min(lane, h.A - 1)], d2[r] + sbo, v);
-            if (lane < h.A && h.q) h.q[row * h.A + lane] = v;
-            float best = (lane < h.A) ? v : -INFINITY; int besti = lane;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {     // first maximum, like torch.max(1)[1]
-                const float ob = __shfl_xor_sync(0xffffffffu, best, off); const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
-                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            for (int c = 0; c < 4; c++) {
+                d1[c] = fmaf(xav[c], Ut[(i + c) * HLD + lane], d1[c]);
+                d2[c] = fmaf(xbv[c], St[(i + c) * HLD + lane], d2[c]);
             }
-            if (lane == 0 && h.greedy) h.greedy[row] = besti;
         }
+        float v = ((d1[0] + d1[1]) + (d1[2] + d1[3])) + ubo;
+        if (h.noisy41) v = fmaf(h.nz[row * h.ldn + H2 + H3 + H3 + min(lane, h.A - 1)], ((d2[0] + d2[1]) + (d2[2] + d2[3])) + sbo, v);
+        if (lane < h.A && h.q) h.q[row * h.A + lane] = v;
+        float best = (lane < h.A) ? v : -INFINITY; int besti = lane;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {         // first maximum, like torch.max(1)[1]
+            const float ob = __shfl_xor_sync(0xffffffffu, best, off); const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (lane == 0 && h.greedy) h.greedy[row] = besti;
     }
 }
 
@@ -454,7 +442,7 @@ extern "C" int qc_policy_set_param(qc_policy* p, int32_t which, const float* hos
 
 constexpr size_t GEMM_SMEM_1 = sizeof(float) * (size_t)TILE_FLOATS;
 constexpr size_t GEMM_SMEM_4 = sizeof(float) * ((size_t)4 * TILE_FLOATS + (size_t)3 * BM * BN);
-constexpr size_t HEAD_SMEM = sizeof(float) * ((size_t)2 * H3 * 32 + (size_t)HEAD_WARPS * HR * 2 * H3);
+constexpr size_t HEAD_SMEM = sizeof(float) * ((size_t)2 * H3 * HLD + (size_t)HEAD_WARPS * 2 * H3);
 
 static int launch_gemm(const GemmArgs& g, int nz, cudaStream_t st) {
     static thread_local bool attr_set[64] = {};
@@ -516,7 +504,7 @@ extern "C" int qc_policy_forward(qc_policy* p, const float* obs, int64_t B, int3
         h.y1 = p->a3; h.y2 = p->a3 + (size_t)B * H3; h.ub31 = p->param[QC_P_FC31_UB]; h.sb31 = p->param[QC_P_FC31_SB];
         h.U = p->param[QC_P_FC41_UW]; h.S = p->param[QC_P_FC41_SW]; h.ub = p->param[QC_P_FC41_UB]; h.sb = p->param[QC_P_FC41_SB];
         h.nz = nz; h.ldn = NW; h.A = p->n_actions; h.noisy31 = n31 ? 1 : 0; h.noisy41 = n41 ? 1 : 0; h.q = q; h.greedy = greedy; h.B = B;
-        const unsigned nb = (unsigned)std::min<int64_t>((B + HEAD_WARPS * HR - 1) / (HEAD_WARPS * HR), 148 * 2);
+        const unsigned nb = (unsigned)std::min<int64_t>((B + HEAD_WARPS - 1) / HEAD_WARPS, 148 * 2);
         head_kernel<<<nb, HEAD_WARPS * 32, HEAD_SMEM, st>>>(h);
         p->launches++;
     }
