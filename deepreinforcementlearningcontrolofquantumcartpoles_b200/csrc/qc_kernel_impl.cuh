@@ -729,18 +729,34 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
                     const double xa = xl[r + 2], xb = xl[r + 1];     // xl_r, xl_{r-1}
                     rel0[r + 1] = mk2(xa * pe[r + 3].x + xb * pe[r + 1].x - xbar * pe[r + 2].x, xa * pe[r + 3].y + xb * pe[r + 1].y - xbar * pe[r + 2].y);
                 }
-                double2 yp[L], ym[L], sq0[L];
+                // psi~ minus the Horner terms is a linear combination, with scalar coefficients, of
+                //     psi, (x-<x>)psi, (x-<x>)^2 psi,  Y+, xY+, x^2 Y+,  Y-, xY-, x^2 Y-
+                // because Phi+- = (1 +- sig (x - <x>_Y+)) Y+ and every "relative" vector is a polynomial in x applied to Y+-:
+                //     (x-c) Y = xY - cY,   (x-c)^2 Y = x^2 Y - 2c xY + c^2 Y,
+                //     b(Phi+) - b(Phi-) = gs [ (xfm - xfp) Y+ + sig (2 (x-xbp)^2 Y+ + (2 xbp - xfp - xfm)(x-xbp) Y+) ].
+                // The un-normalised <x> of Phi+- (Q:605-615) follow from <Y+, x^k Y+>, k = 1..3 (x is real symmetric):
+                //     <Phi+-, x Phi+-> = M1 +- 2 sig (M2 - xbp M1) + sig^2 (M3 - 2 xbp M2 + xbp^2 M1),
+                // so ONE reduction per substep suffices here and Phi+- are never formed.  Terms whose coefficients do not depend on the
+                // reduction results are folded into accA before it, which keeps the live register set small.
+                const double c_rel0 = gs * (dW - 2.0 * k4), c_sq0 = -2.0 * k2 * g4;
+                const double c_sqp = 2.0 * k5 * gs * sig - g4 * (k1 + k2), c_sqm = g4 * (k1 - k2), c_relm = gs * (k4 - k3 + k5);
+                const double cvb = 2.0 * sdt * (k1 - k6) * gs, cvp = 2.0 * k2;
+                double2 yp[L], ym[L];
 #pragma unroll
                 for (int j = 0; j < L; j++) {
                     psi[j] = pe[j + 2];
                     const double xa = xl[j + 2], xb = xl[j + 1];
-                    sq0[j] = mk2(xa * rel0[j + 2].x + xb * rel0[j].x - xbar * rel0[j + 1].x, xa * rel0[j + 2].y + xb * rel0[j].y - xbar * rel0[j + 1].y);
+                    const double2 r0 = rel0[j + 1];
+                    const double2 sq0 = mk2(xa * rel0[j + 2].x + xb * rel0[j].x - xbar * r0.x, xa * rel0[j + 2].y + xb * rel0[j].y - xbar * r0.y);
                     // H0 psi on own points (halo HB <= 2)
                     const double2 h = ops.h0(pe + (2 - HB), j);
-                    a[j] = mk2(h.y - g4 * sq0[j].x, -h.x - g4 * sq0[j].y);
+                    a[j] = mk2(h.y - g4 * sq0.x, -h.x - g4 * sq0.y);
                     const double ux = fma(dt, a[j].x, psi[j].x), uy = fma(dt, a[j].y, psi[j].y);
-                    yp[j] = mk2(fma(sig, rel0[j + 1].x, ux), fma(sig, rel0[j + 1].y, uy));
-                    ym[j] = mk2(fma(-sig, rel0[j + 1].x, ux), fma(-sig, rel0[j + 1].y, uy));
+                    yp[j] = mk2(fma(sig, r0.x, ux), fma(sig, r0.y, uy));
+                    ym[j] = mk2(fma(-sig, r0.x, ux), fma(-sig, r0.y, uy));
+                    acc[j] = mk2(fma(c_sq0, sq0.x, fma(c_rel0, r0.x, psi[j].x)), fma(c_sq0, sq0.y, fma(c_rel0, r0.y, psi[j].y)));
+                    const double tvx = fma(cvb, r0.x, cvp * psi[j].x), tvy = fma(cvb, r0.y, cvp * psi[j].y);
+                    v1[j] = mk2(tvy, -tvx);
                 }
                 // exchange Y+ (-> V) and Y- (-> X3) with halo 2
 #pragma unroll
@@ -749,63 +765,46 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
                     if constexpr (VAR == QC_INV_HARMONIC) A4[j * Gp + GUARD + g] = a[j];     // left halo of a for the HERMITIAN-descriptor term below
                 }
                 traj_sync<MULTI>(bar_id, G);
-                double2 ype[L + 4], yme[L + 4];
+                double2 u1p[L], u1m[L];                  // x Y+- on the own points
+                double m[4] = {0.0, 0.0, 0.0, 0.0};      // <Y+,xY+>, <Y+,x^2 Y+>, <Y+,x^3 Y+>, <Y-,xY->
+                {
+                    double2 ype[L + 4], yme[L + 4];
 #pragma unroll
-                for (int r = -2; r < L + 2; r++) {
-                    ype[r + 2] = (r >= 0 && r < L) ? yp[r] : ld_rel<L>(V, g, Gp, r);
-                    yme[r + 2] = (r >= 0 && r < L) ? ym[r] : ld_rel<L>(X3, g, Gp, r);
-                }
-                double2 xyp[L + 2], xym[L + 2];          // x Y+- on [-1, L]
-                double m[2] = {0.0, 0.0};
+                    for (int r = -2; r < L + 2; r++) {
+                        ype[r + 2] = (r >= 0 && r < L) ? yp[r] : ld_rel<L>(V, g, Gp, r);
+                        yme[r + 2] = (r >= 0 && r < L) ? ym[r] : ld_rel<L>(X3, g, Gp, r);
+                    }
+                    double2 xyp[L + 2], xym[L + 2];      // x Y+- on [-1, L]
 #pragma unroll
-                for (int r = -1; r <= L; r++) {
-                    const double xa = xl[r + 2], xb = xl[r + 1];
-                    xyp[r + 1] = mk2(xa * ype[r + 3].x + xb * ype[r + 1].x, xa * ype[r + 3].y + xb * ype[r + 1].y);
-                    xym[r + 1] = mk2(xa * yme[r + 3].x + xb * yme[r + 1].x, xa * yme[r + 3].y + xb * yme[r + 1].y);
-                    if (r >= 0 && r < L) {
-                        m[0] += ype[r + 2].x * xyp[r + 1].x + ype[r + 2].y * xyp[r + 1].y;
-                        m[1] += yme[r + 2].x * xym[r + 1].x + yme[r + 2].y * xym[r + 1].y;
+                    for (int r = -1; r <= L; r++) {
+                        const double xa = xl[r + 2], xb = xl[r + 1];
+                        xyp[r + 1] = mk2(xa * ype[r + 3].x + xb * ype[r + 1].x, xa * ype[r + 3].y + xb * ype[r + 1].y);
+                        xym[r + 1] = mk2(xa * yme[r + 3].x + xb * yme[r + 1].x, xa * yme[r + 3].y + xb * yme[r + 1].y);
+                    }
+#pragma unroll
+                    for (int j = 0; j < L; j++) {
+                        const double xa = xl[j + 2], xb = xl[j + 1];
+                        u1p[j] = xyp[j + 1]; u1m[j] = xym[j + 1];
+                        const double2 u2p = mk2(xa * xyp[j + 2].x + xb * xyp[j].x, xa * xyp[j + 2].y + xb * xyp[j].y);     // x^2 Y+
+                        const double2 u2m = mk2(xa * xym[j + 2].x + xb * xym[j].x, xa * xym[j + 2].y + xb * xym[j].y);     // x^2 Y-
+                        m[0] += yp[j].x * u1p[j].x + yp[j].y * u1p[j].y;
+                        m[1] += u1p[j].x * u1p[j].x + u1p[j].y * u1p[j].y;
+                        m[2] += u1p[j].x * u2p.x + u1p[j].y * u2p.y;
+                        m[3] += ym[j].x * u1m[j].x + ym[j].y * u1m[j].y;
+                        acc[j].x = fma(c_sqm, u2m.x, fma(c_sqp, u2p.x, acc[j].x)); acc[j].y = fma(c_sqm, u2m.y, fma(c_sqp, u2p.y, acc[j].y));
                     }
                 }
-                traj_reduce<2, MULTI>(m, red, red_phase, wq, nwarps, lane, bar_id, G);
-                const double xbp = p.w * m[0], xbm = p.w * m[1];
-                double2 relp[L + 2], relm[L + 2], php[L + 2], phm[L + 2];
-#pragma unroll
-                for (int r = -1; r <= L; r++) {
-                    relp[r + 1] = mk2(xyp[r + 1].x - xbp * ype[r + 2].x, xyp[r + 1].y - xbp * ype[r + 2].y);
-                    relm[r + 1] = mk2(xym[r + 1].x - xbm * yme[r + 2].x, xym[r + 1].y - xbm * yme[r + 2].y);
-                    php[r + 1] = mk2(fma(sig, relp[r + 1].x, ype[r + 2].x), fma(sig, relp[r + 1].y, ype[r + 2].y));     // Phi+ (Q:612)
-                    phm[r + 1] = mk2(fma(-sig, relp[r + 1].x, ype[r + 2].x), fma(-sig, relp[r + 1].y, ype[r + 2].y));   // Phi- (Q:606-608)
-                }
-                double2 xfp_[L], xfm_[L];
-                double mf[2] = {0.0, 0.0};
+                traj_reduce<4, MULTI>(m, red, red_phase, wq, nwarps, lane, bar_id, G);
+                const double xbp = p.w * m[0], xbm = p.w * m[3];                       // un-normalised <x> of Y+-  (D1ImRe, Q:457-460)
+                const double t1 = m[1] - xbp * m[0], t2 = m[2] - 2.0 * xbp * m[1] + xbp * xbp * m[0];
+                const double xfp = p.w * (m[0] + 2.0 * sig * t1 + sig * sig * t2), xfm = p.w * (m[0] - 2.0 * sig * t1 + sig * sig * t2);
+                const double c_relp = gs * (k3 + k4 - k5 + k5 * sig * (2.0 * xbp - xfp - xfm)), c_yp = k5 * gs * (xfm - xfp);
+                const double PY = c_yp - xbp * c_relp + xbp * xbp * c_sqp, PU1 = c_relp - 2.0 * xbp * c_sqp;
+                const double MY = xbm * xbm * c_sqm - xbm * c_relm, MU1 = c_relm - 2.0 * xbm * c_sqm;
 #pragma unroll
                 for (int j = 0; j < L; j++) {
-                    const double xa = xl[j + 2], xb = xl[j + 1];
-                    xfp_[j] = mk2(xa * php[j + 2].x + xb * php[j].x, xa * php[j + 2].y + xb * php[j].y);
-                    xfm_[j] = mk2(xa * phm[j + 2].x + xb * phm[j].x, xa * phm[j + 2].y + xb * phm[j].y);
-                    mf[0] += php[j + 1].x * xfp_[j].x + php[j + 1].y * xfp_[j].y;
-                    mf[1] += phm[j + 1].x * xfm_[j].x + phm[j + 1].y * xfm_[j].y;
-                }
-                traj_reduce<2, MULTI>(mf, red, red_phase, wq, nwarps, lane, bar_id, G);
-                const double xfp = p.w * mf[0], xfm = p.w * mf[1];
-                const double cvb = 2.0 * sdt * (k1 - k6) * gs, cvp = 2.0 * k2;
-#pragma unroll
-                for (int j = 0; j < L; j++) {
-                    const double xa = xl[j + 2], xb = xl[j + 1];
-                    // (x-<x>)^2 Y+-  -> aRe(Y+-) = -gamma/4 * that  (D1ImRe, Q:468-469)
-                    const double sqpx = xa * relp[j + 2].x + xb * relp[j].x - xbp * relp[j + 1].x, sqpy = xa * relp[j + 2].y + xb * relp[j].y - xbp * relp[j + 1].y;
-                    const double sqmx = xa * relm[j + 2].x + xb * relm[j].x - xbm * relm[j + 1].x, sqmy = xa * relm[j + 2].y + xb * relm[j].y - xbm * relm[j + 1].y;
-                    const double arpx = -g4 * sqpx, arpy = -g4 * sqpy, armx = -g4 * sqmx, army = -g4 * sqmy;
-                    const double ar0x = -g4 * sq0[j].x, ar0y = -g4 * sq0[j].y;
-                    const double b0x = gs * rel0[j + 1].x, b0y = gs * rel0[j + 1].y;
-                    const double bpx = gs * relp[j + 1].x, bpy = gs * relp[j + 1].y, bmx = gs * relm[j + 1].x, bmy = gs * relm[j + 1].y;
-                    const double bfpx = gs * (xfp_[j].x - xfp * php[j + 1].x), bfpy = gs * (xfp_[j].y - xfp * php[j + 1].y);
-                    const double bfmx = gs * (xfm_[j].x - xfm * phm[j + 1].x), bfmy = gs * (xfm_[j].y - xfm * phm[j + 1].y);
-                    acc[j] = mk2(psi[j].x + dW * b0x + k1 * (arpx - armx) + k2 * (arpx + armx + 2.0 * ar0x) + k3 * (bpx - bmx) + k4 * (bpx + bmx - 2.0 * b0x) + k5 * (bfpx - bfmx - bpx + bmx),
-                                 psi[j].y + dW * b0y + k1 * (arpy - army) + k2 * (arpy + army + 2.0 * ar0y) + k3 * (bpy - bmy) + k4 * (bpy + bmy - 2.0 * b0y) + k5 * (bfpy - bfmy - bpy + bmy));
-                    const double tvx = cvb * rel0[j + 1].x + cvp * psi[j].x, tvy = cvb * rel0[j + 1].y + cvp * psi[j].y;
-                    v1[j] = mk2(tvy, -tvx);
+                    acc[j].x = fma(MU1, u1m[j].x, fma(MY, ym[j].x, fma(PU1, u1p[j].x, fma(PY, yp[j].x, acc[j].x))));
+                    acc[j].y = fma(MU1, u1m[j].y, fma(MY, ym[j].y, fma(PU1, u1p[j].y, fma(PY, yp[j].y, acc[j].y))));
                 }
             }
             if constexpr (VAR == QC_INV_HARMONIC) {
