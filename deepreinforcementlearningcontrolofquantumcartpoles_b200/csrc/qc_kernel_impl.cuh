@@ -180,77 +180,91 @@ __device__ __forceinline__ void solve_traj(const StepParams& p, double2* __restr
     const int col0 = lane * mult;
     const bool act = lane < p.P;
     double nrm = 0.0, sx = 0.0, cen = 0.0;
-    // Row = what one recurrence step needs: the vector entry and the factor row of its point.  Loads run PF steps ahead of the
-    // arithmetic through a small register ring (explicit software pipelining: with one or two warps per scheduler nothing else hides
-    // the shared-memory latency of this serial loop).
-    struct Row { double2 v; double2 cf[BA + 2]; };
+    // Both substitutions run in "scatter" form: as soon as an unknown is final its contribution is subtracted from the (at most BA) rows
+    // that still wait for it, so the loop-carried dependency per row is ONE complex multiply-add (two dependent DFMAs) and the updates of the
+    // other BA-1 pending rows fill the latency.  (The earlier gather form -- one 2 BA-deep FMA chain per row -- ran at ~160 cycles per row
+    // for the single solver warp: 46 % of an inverted-quartic substep, profiles/README.md.)  The forward sweep accumulates each row in exactly
+    // the order of the gather form (oldest history first), so y is bit-identical to it.
+    // A Slot is what one step needs; loads run PF steps ahead of the arithmetic through a small register ring (explicit software
+    // pipelining: with one or two warps per scheduler nothing else hides the shared-memory latency of this serial loop).
+    struct Slot { double2 v; double2 cf[BA]; double2 e; };
     constexpr int PF = (L % 3 == 0) ? 2 : 0, NR = PF + 1;
-    auto load_row = [&](Row& r, const double2* __restrict__ buf, int col, int j, bool bwd) {
+    auto entry = [&](int col, int j, int k) -> double2 {            // k-th entry of the factor row of point (col, j): l_1..l_BA, 1/d, [xl]
         const int tc = min(max(col, 0), G - 1);
-        r.v = buf[j * Gp + GUARD + col];
+        if (k == BA + 1) return TABS ? tab[(j * CS + BA + 1) * G + tc] : mk2(__ldg(&p.x[min(tc * L + j, n - 1)]), 0.0);
+        return TABS ? tab[(j * CS + k) * G + tc] : __ldg(&fac[(size_t)(tc * L + j) * (BA + 1) + k]);
+    };
+    // forward slot of row i = (col, j): rhs of row i+BA (enters the window), l_{i+1+m, m} for the BA rows that wait for y_i, 1/d_i
+    auto load_fwd = [&](Slot& s, int col, int j) {
+        { const int t = j + BA; s.v = U[(t % L) * Gp + GUARD + col + t / L]; }
 #pragma unroll
-        for (int k = 0; k <= BA; k++) {
-            if (bwd && k == BA) { if (VAR != QC_QUARTIC) r.cf[BA] = TABS ? tab[(j * CS + BA + 1) * G + tc] : mk2(__ldg(&p.x[min(tc * L + j, n - 1)]), 0.0); }
-            else r.cf[k] = TABS ? tab[(j * CS + k) * G + tc] : __ldg(&fac[(size_t)(tc * L + j) * (BA + 1) + k]);
-        }
+        for (int m = 0; m < BA; m++) { const int t = j + 1 + m; s.cf[m] = entry(col + t / L, t % L, m); }
+        s.e = entry(col, j, BA);
+    };
+    // backward slot of row i = (col, j): z of row i-BA (enters the window), row i of L (its entries update rows i-1..i-BA), [xl_i]
+    auto load_bwd = [&](Slot& s, int col, int j) {
+        { const int t = j - BA + 8 * L; s.v = V[(t % L) * Gp + GUARD + col + t / L - 8]; }
+#pragma unroll
+        for (int m = 0; m < BA; m++) s.cf[m] = entry(col, j, m);
+        if (VAR != QC_QUARTIC) s.e = entry(col, j, BA + 1);
     };
     if (act) {
         // ---- forward: L y = rhs, z = D^{-1} y --------------------------------------------------------------
-        double2 y[BA];
-#pragma unroll
-        for (int k = 0; k < BA; k++) y[k] = mk2(0.0, 0.0);
-        Row ring[NR];
         int col = col0 - wb;
+        double2 acc[BA];                               // acc[m]: row i+m of the window, rhs minus the history terms applied so far
 #pragma unroll
-        for (int q = 0; q < PF; q++) load_row(ring[q], U, col, q, false);
+        for (int m = 0; m < BA; m++) acc[m] = U[(m % L) * Gp + GUARD + col + m / L];
+        Slot ring[NR];
+#pragma unroll
+        for (int q = 0; q < PF; q++) load_fwd(ring[q], col + q / L, q % L);
         for (int b = 0; b < wb + mult; b++, col++) {
             const bool own = b >= wb;
             double2* __restrict__ vb = V + GUARD + col;
 #pragma unroll
             for (int j = 0; j < L; j++) {
-                if (j + PF < L) load_row(ring[(j + PF) % NR], U, col, j + PF, false);
-                else load_row(ring[(j + PF) % NR], U, col + 1, j + PF - L, false);        // next column (guard / clamped past the end)
-                const Row& r = ring[j % NR];
-                double re = r.v.x, im = r.v.y;
+                load_fwd(ring[(j + PF) % NR], col + (j + PF) / L, (j + PF) % L);
+                const Slot& s = ring[j % NR];
+                const double2 y = acc[0];
 #pragma unroll
-                for (int k = BA - 1; k >= 0; k--) {   // far history first: the newest value (k = 0) closes the dependency chain
-                    re = fma(-r.cf[k].x, y[k].x, re); re = fma(r.cf[k].y, y[k].y, re);
-                    im = fma(-r.cf[k].x, y[k].y, im); im = fma(-r.cf[k].y, y[k].x, im);
+                for (int m = 0; m + 1 < BA; m++) acc[m] = acc[m + 1];
+                acc[BA - 1] = s.v;
+#pragma unroll
+                for (int m = 0; m < BA; m++) {         // m = 0 first: it closes the loop-carried dependency
+                    acc[m].x = fma(-s.cf[m].x, y.x, acc[m].x); acc[m].x = fma(s.cf[m].y, y.y, acc[m].x);
+                    acc[m].y = fma(-s.cf[m].x, y.y, acc[m].y); acc[m].y = fma(-s.cf[m].y, y.x, acc[m].y);
                 }
-#pragma unroll
-                for (int k = BA - 1; k > 0; k--) y[k] = y[k - 1];
-                y[0] = mk2(re, im);
-                if (own) vb[j * Gp] = mk2(re * r.cf[BA].x - im * r.cf[BA].y, re * r.cf[BA].y + im * r.cf[BA].x);
+                if (own) vb[j * Gp] = mk2(y.x * s.e.x - y.y * s.e.y, y.x * s.e.y + y.y * s.e.x);
             }
         }
     }
     __syncwarp();
     if (act) {
-        // ---- backward: L^T x = z, column oriented (row i of L again) ------------------------------------------
-        double2 pend[BA];
+        // ---- backward: L^T x = z (row i of L again: x_i updates the BA rows before it) ---------------------------
+        int col = col0 + mult + wb - 1;
+        double2 q[BA];                                 // q[m]: row i-m of the window, z minus the updates applied so far; q[0] is final
 #pragma unroll
-        for (int k = 0; k < BA; k++) pend[k] = mk2(0.0, 0.0);
+        for (int m = 0; m < BA; m++) { const int t = L - 1 - m + 8 * L; q[m] = V[(t % L) * Gp + GUARD + col + t / L - 8]; }
         double2 xprev = mk2(0.0, 0.0);
         const bool do_cen = (VAR == QC_QUARTIC) && (p.cen_hi > p.cen_lo);
-        Row ring[NR];
-        int col = col0 + mult + wb - 1;
+        Slot ring[NR];
 #pragma unroll
-        for (int q = 0; q < PF; q++) load_row(ring[q], V, col, L - 1 - q, true);
+        for (int r = 0; r < PF; r++) { const int t = L - 1 - r + 8 * L; load_bwd(ring[r], col + t / L - 8, t % L); }
         for (int b = 0; b < wb + mult; b++, col--) {
             const bool own = b >= wb;
             double2* __restrict__ ub = U + GUARD + col;
 #pragma unroll
             for (int jr = 0; jr < L; jr++) {          // jr-th step of the column, point j = L-1-jr
                 const int j = L - 1 - jr;
-                if (jr + PF < L) load_row(ring[(jr + PF) % NR], V, col, L - 1 - (jr + PF), true);
-                else load_row(ring[(jr + PF) % NR], V, col - 1, L - 1 - (jr + PF - L), true);
-                const Row& r = ring[jr % NR];
-                const double xr = r.v.x + pend[0].x, xi = r.v.y + pend[0].y;
+                { const int t = j - PF + 8 * L; load_bwd(ring[(jr + PF) % NR], col + t / L - 8, t % L); }
+                const Slot& s = ring[jr % NR];
+                const double xr = q[0].x, xi = q[0].y;
 #pragma unroll
-                for (int k = 0; k < BA; k++) {
-                    const double pr = (k + 1 < BA) ? pend[k + 1].x : 0.0, pi = (k + 1 < BA) ? pend[k + 1].y : 0.0;
-                    pend[k].x = fma(-xr, r.cf[k].x, fma(xi, r.cf[k].y, pr));
-                    pend[k].y = fma(-xr, r.cf[k].y, fma(-xi, r.cf[k].x, pi));
+                for (int m = 0; m + 1 < BA; m++) q[m] = q[m + 1];
+                q[BA - 1] = s.v;
+#pragma unroll
+                for (int m = 0; m < BA; m++) {
+                    q[m].x = fma(-xr, s.cf[m].x, fma(xi, s.cf[m].y, q[m].x));
+                    q[m].y = fma(-xr, s.cf[m].y, fma(-xi, s.cf[m].x, q[m].y));
                 }
                 if (own) {
                     ub[j * Gp] = mk2(xr, xi);
@@ -261,7 +275,7 @@ __device__ __forceinline__ void solve_traj(const StepParams& p, double2* __restr
                         sx = fma(p.h * (double)(i - p.half), a2, sx);
                         if (do_cen && i >= p.cen_lo && i < p.cen_hi) cen += a2;
                     } else {
-                        sx = fma(2.0 * r.cf[BA].x, xr * xprev.x + xi * xprev.y, sx);     // 2 xl_i Re(conj(x_i) x_{i+1})
+                        sx = fma(2.0 * s.e.x, xr * xprev.x + xi * xprev.y, sx);     // 2 xl_i Re(conj(x_i) x_{i+1})
                     }
                 }
                 xprev = mk2(xr, xi);
@@ -476,7 +490,12 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     // warp w of the CTA serves trajectory (w % T) as its (w / T)-th warp: the first warps of all trajectories (which also run the serial
     // part, the implicit solve) get consecutive warp ids and therefore spread over the four SM sub-partitions
     const int lane = tid & 31, nwarps = G >> 5;
-    const int t = (tid >> 5) % p.T, wq = (tid >> 5) / p.T, g = wq * 32 + lane;
+    // When T is a multiple of 4 that layout would put ALL warps of a trajectory on one SM sub-partition (warp id mod 4): while its first
+    // warp runs the serial solve the other two only wait, and that scheduler idles while the others are oversubscribed.  Rotating the
+    // trajectory index by the warp row spreads each trajectory over the sub-partitions (QCART_DEBUG bit 32 restores the plain layout).
+    const int wq = (tid >> 5) / p.T;
+    const bool rotate = MULTI && (p.T % 4 == 0) && !(p.debug & 32);
+    const int t = rotate ? ((tid >> 5) % p.T + 32 * p.T - wq) % p.T : (tid >> 5) % p.T, g = wq * 32 + lane;
     const int bar_id = 1 + t;
     // Work list: without binning position == trajectory.  With binning (p.order) trajectories are grouped by factor slot (= force level),
     // every CTA holds trajectories of ONE slot (bins padded with -1) and stages that slot's factor table once for all of them.
