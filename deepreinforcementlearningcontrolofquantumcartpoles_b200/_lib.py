@@ -20,7 +20,7 @@ class QcConfig(C.Structure):
                 ("lambda_", C.c_double), ("mass", C.c_double), ("omega", C.c_double), ("dt", C.c_double),
                 ("gamma", C.c_double), ("n_sub", C.c_int32), ("f_max", C.c_double), ("n_levels", C.c_int32),
                 ("moment_order", C.c_int32), ("x_threshold", C.c_double), ("herm_mode", C.c_int32),
-                ("device", C.c_int32)]
+                ("device", C.c_int32), ("solve_tol", C.c_double)]
 
 
 class QcartError(RuntimeError):

@@ -76,7 +76,10 @@ static int add_slot(qc_sim* s, double F, int* slot_out) {
     int rc = m.factor(F, tab);
     if (rc == QC_ERR_PIVOT) return fail(rc, "implicit matrix would need row pivoting for this force (outside the reference's stable parameter range)");
     if (rc) return fail(rc, "factorisation failed");
-    const int W = m.decay_width(tab, 1e-18);
+    // truncation threshold of the parallel solve (qc_config.solve_tol; QCART_SOLVE_TOL overrides it for experiments)
+    static const double env_tol = getenv("QCART_SOLVE_TOL") ? atof(getenv("QCART_SOLVE_TOL")) : 0.0;
+    const double solve_tol = env_tol > 0.0 ? env_tol : (m.cfg.solve_tol > 0.0 ? m.cfg.solve_tol : 0x1p-48);
+    const int W = m.decay_width(tab, solve_tol);
     if (W > s->W_needed) { s->W_needed = W; s->batch.plan_nsub = -1; s->one.plan_nsub = -1; }
     const size_t row = (size_t)m.n * (m.ba + 1);
     QC_CUDA(cudaMemcpy(s->d_fac + row * s->n_slots, tab.data(), sizeof(zc) * row, cudaMemcpyHostToDevice));

@@ -18,6 +18,8 @@ int build_model(const qc_config& c, Model& m, std::string& err) {
     m.cfg = c;
     if (c.dt <= 0 || c.gamma <= 0) { err = "dt and gamma must be positive"; return QC_ERR_ARG; }
     if (c.n_levels < 1 || (c.n_levels % 2) == 0) { err = "n_levels must be odd (a zero-force level in the middle)"; return QC_ERR_ARG; }
+    if (!(c.solve_tol >= 0.0) || c.solve_tol > 1e-9) { err = "solve_tol must be in [0, 1e-9] (0 = default 2^-48)"; return QC_ERR_ARG; }
+    if (c.solve_tol == 0.0) m.cfg.solve_tol = 0x1p-48;
     if (c.variant == QC_QUARTIC) {
         if (c.grid_size <= 0 || c.x_max <= 0 || c.mass <= 0) { err = "grid needs x_max, grid_size, mass > 0"; return QC_ERR_ARG; }
         const double h = c.grid_size;

@@ -29,6 +29,7 @@ def make_config(params, device=0):
     c.dt, c.gamma, c.n_sub = params["dt"], params["gamma"], params["n_sub"]
     c.f_max, c.n_levels = params["f_max"], params.get("n_levels", 21)
     c.device = device
+    c.solve_tol = float(params.get("solve_tol", 0.0))      # 0 = library default (2^-48)
     return c
 
 

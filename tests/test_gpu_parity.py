@@ -309,3 +309,36 @@ def test_force_binning_is_bitwise_neutral(monkeypatch):
     orc = oracle_for(params)
     ref, _, _ = oracle_control_step(orc, params, psi0[:8], actions[:8], noise[:8])
     assert rel_err(res[1][0][:8], ref) < TOL_STEP
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["quartic", "inverted_harmonic"])
+def test_solve_truncation_threshold_is_below_rounding_noise(task):
+    """qc_config.solve_tol: the default (2^-48) and a 1000x stricter threshold give the same state to rounding noise, and both are
+    within the 1e-10 control-step tolerance of the exact band solve of the oracle."""
+    import torch
+    params = configs.PRESETS[task]()
+    B, n_sub = 6, params["n_sub"]
+    rng = np.random.default_rng(17)
+    psi0 = initial_states(params, B, 3)
+    actions = rng.integers(0, params["n_levels"], B).astype(np.int32)
+    noise = rng.standard_normal((B, n_sub, 2))
+    ref, _, _ = oracle_control_step(oracle_for(params), params, psi0, actions, noise)
+    got = {}
+    for tol in (0.0, 1e-18):
+        sim = BatchedSim(dict(params, solve_tol=tol), batch=B)
+        assert sim.cfg.solve_tol == (2.0 ** -48 if tol == 0.0 else tol)
+        sim.set_state(psi0)
+        sim.step(torch.as_tensor(actions, device="cuda"), noise=torch.as_tensor(noise, device="cuda"))
+        got[tol] = sim.get_state()
+        err = np.max(np.linalg.norm(got[tol] - ref, axis=1) / np.linalg.norm(ref, axis=1))
+        assert err < 1e-10, (tol, err)
+    diff = np.max(np.linalg.norm(got[0.0] - got[1e-18], axis=1) / np.linalg.norm(ref, axis=1))
+    assert diff < 1e-13, diff
+
+
+@pytest.mark.gpu
+def test_bad_solve_tol_is_rejected():
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200 import QcartError
+    with pytest.raises(QcartError):
+        BatchedSim(dict(configs.quartic(), solve_tol=1e-3), batch=4)
