@@ -16,7 +16,7 @@
 //       psi~ = acc + H0 ( v1 + H0 ( c2 a + H0 ( c3 a + H0 ( c4 a + H0 c5 a ) ) ) )
 //     which equals  k(aIm(Y+) - aIm(Y-)) + 2 k2 aIm(psi) + C a  of simple_sum_up because aIm is linear;
 //   * the implicit solve (I + i dt/2 H0) psi' = psi~ is the one serial recurrence.  With the pivot-free L D L^T factors precomputed per
-//     force level, L^{-1} decays below 1e-18 within W points (measured at create time), so a substitution that starts W points early
+//     force level, L^{-1} decays below qc_config.solve_tol (default 2^-48) within W points (measured at create time), so a substitution that starts W points early
 //     with zero history equals the sequential solve to round-off.  Two formulations of that truncation:
 //       solve_traj_jacobi  one-warp trajectories: factor rows in registers, K = W/L + 1 passes over the lane's own L points,
 //                          boundary values handed to the neighbour lane by shuffle (FP64-issue bound);
