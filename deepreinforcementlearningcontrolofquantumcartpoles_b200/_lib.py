@@ -63,6 +63,13 @@ SYMBOLS = [
     ("qc_measure_smem_peak", C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     ("qc_launch_count", _i64, [_vp]),
     ("qc_kernel_info", C.c_char_p, [_vp]),
+    ("qc_peer_alloc", C.c_int, [C.c_int32, C.c_uint64, C.POINTER(_vp), _vp]),
+    ("qc_peer_free", C.c_int, [C.c_int32, _vp]),
+    ("qc_peer_open", C.c_int, [C.c_int32, _vp, C.POINTER(_vp)]),
+    ("qc_peer_close", C.c_int, [C.c_int32, _vp]),
+    ("qc_set_gather", C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(_vp), C.POINTER(_vp)]),
+    ("qc_gather_seq", C.c_uint64, [_vp]),
+    ("qc_gather_wait", C.c_int, [_vp, C.c_uint64, _vp]),
     # ---- include/qcart_rollout.h ----
     ("qc_obs_f32", C.c_int, [_dp, _i64, C.c_double, _vp, _vp]),
     ("qc_policy_create", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),

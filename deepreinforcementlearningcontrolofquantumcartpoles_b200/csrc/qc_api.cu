@@ -49,6 +49,10 @@ struct qc_sim {
     double2* d_vglobal = nullptr; size_t vglobal_cap = 0;
     int64_t launches = 0;
     std::string info;
+    // fused result exchange (qc_set_gather)
+    int g_world = 0, g_rank = 0; uint64_t g_seq = 0;
+    double* g_peer[QC_MAX_PEERS] = {}; unsigned long long* g_flag[QC_MAX_PEERS] = {};
+    unsigned int* d_gdone = nullptr;
 };
 
 extern "C" const char* qc_last_error(void) { return g_err.c_str(); }
@@ -137,7 +141,7 @@ extern "C" int qc_destroy(qc_sim* s) {
     cudaSetDevice(s->device);
     cudaFree(s->raw_x); cudaFree(s->raw_hd); cudaFree(s->raw_h2); cudaFree(s->d_fac); cudaFree(s->d_slot_force); cudaFree(s->d_herm);
     cudaFree(s->batch.psi); cudaFree(s->batch.step); cudaFree(s->batch.flags);
-    cudaFree(s->d_vglobal); cudaFree(s->d_order); cudaFree(s->d_order_count); cudaFree(s->d_action); cudaFree(s->d_noise); cudaFree(s->d_mom); cudaFree(s->d_aux); cudaFree(s->d_flagout);
+    cudaFree(s->d_gdone); cudaFree(s->d_vglobal); cudaFree(s->d_order); cudaFree(s->d_order_count); cudaFree(s->d_action); cudaFree(s->d_noise); cudaFree(s->d_mom); cudaFree(s->d_aux); cudaFree(s->d_flagout);
     cudaFree(s->one.psi); cudaFree(s->one.step); cudaFree(s->one.flags); cudaFree(s->d_slot1); cudaFree(s->d_noise1); cudaFree(s->d_out1); cudaFree(s->d_flag1);
     if (s->stream) cudaStreamDestroy(s->stream);
     cudaGetLastError();
@@ -296,6 +300,12 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
     p.psi = b.psi; p.noise = noise; p.seed = s->seed; p.traj_offset = s->traj_offset; p.step_count = b.step; p.nsub_traj = nsub_traj;
     p.moments = moments; p.aux = aux; p.flags_out = flags; p.flags_latch = b.flags; p.q_out = q_out; p.xmean_out = xmean_out;
     p.moments_only = moments_only; p.jacobi = pl.jacobi; p.herm_smem = pl.herm_smem;
+    if (s->g_world > 0 && &b == &s->batch && !moments_only) {          // fused result exchange: rows + sequence flag to every rank
+        if (!moments || !aux || !flags) return fail(QC_ERR_ARG, "qc_set_gather is active: qc_step needs moments, aux and flags buffers");
+        if (nsub_traj) return fail(QC_ERR_ARG, "qc_set_gather is active: per-trajectory substep budgets are not exchanged");
+        p.g_world = s->g_world; p.g_rank = s->g_rank; p.g_seq = ++s->g_seq; p.g_done = s->d_gdone;
+        for (int r = 0; r < s->g_world; r++) { p.g_peer[r] = s->g_peer[r]; p.g_flag[r] = s->g_flag[r]; }
+    }
     { const char* d = getenv("QCART_DEBUG"); p.debug = d ? atoi(d) : 0; }
     std::string err;
     int rc = launch_step(pl, p, stream, err);
@@ -310,6 +320,73 @@ extern "C" int qc_step(qc_sim* s, const int32_t* action, const double* noise, in
     if (!s->batch.psi) return fail(QC_ERR_STATE, "qc_set_batch first");
     if (!action) return fail(QC_ERR_ARG, "null action array");
     return run(s, s->batch, action, noise, n_sub, nsub_traj, moments, aux, flags, q_out, xmean_out, 0, stream);
+}
+
+// ---- peer-visible memory and the fused result exchange (include/qcart.h) -------------------------------------------------------------
+static int use_dev_ordinal(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return fail(QC_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)"); }
+    if (device < 0 || device >= ndev) return fail(QC_ERR_ARG, "device ordinal out of range");
+    QC_CUDA(cudaSetDevice(device));
+    return QC_OK;
+}
+
+extern "C" int qc_peer_alloc(int32_t device, uint64_t bytes, void** ptr, unsigned char* handle64) {
+    if (!ptr || !handle64 || bytes == 0) return fail(QC_ERR_ARG, "qc_peer_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    int rc = use_dev_ordinal(device); if (rc) return rc;
+    void* d = nullptr;
+    QC_CUDA(cudaMalloc(&d, (size_t)bytes));
+    if (cudaMemset(d, 0, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return fail(QC_ERR_CUDA, "cudaMemset failed"); }
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, d);
+    if (e != cudaSuccess) { cudaGetLastError(); cudaFree(d); return fail(QC_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    memcpy(handle64, &h, 64);
+    *ptr = d;
+    return QC_OK;
+}
+
+extern "C" int qc_peer_free(int32_t device, void* ptr) {
+    int rc = use_dev_ordinal(device); if (rc) return rc;
+    QC_CUDA(cudaFree(ptr));
+    return QC_OK;
+}
+
+extern "C" int qc_peer_open(int32_t device, const unsigned char* handle64, void** ptr) {
+    if (!ptr || !handle64) return fail(QC_ERR_ARG, "qc_peer_open: bad argument");
+    int rc = use_dev_ordinal(device); if (rc) return rc;
+    cudaIpcMemHandle_t h; memcpy(&h, handle64, 64);
+    void* d = nullptr;
+    QC_CUDA(cudaIpcOpenMemHandle(&d, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr = d;
+    return QC_OK;
+}
+
+extern "C" int qc_peer_close(int32_t device, void* ptr) {
+    int rc = use_dev_ordinal(device); if (rc) return rc;
+    QC_CUDA(cudaIpcCloseMemHandle(ptr));
+    return QC_OK;
+}
+
+extern "C" int qc_set_gather(qc_sim* s, int32_t rank, int32_t world, void* const* gather_ptrs, void* const* flag_ptrs) {
+    int rc = use_device(s); if (rc) return rc;
+    if (world == 0) { s->g_world = 0; return QC_OK; }
+    if (world < 1 || world > QC_MAX_PEERS || rank < 0 || rank >= world || !gather_ptrs || !flag_ptrs) return fail(QC_ERR_ARG, "qc_set_gather: need 1 <= world <= 8, 0 <= rank < world and the pointer arrays");
+    for (int r = 0; r < world; r++) if (!gather_ptrs[r] || !flag_ptrs[r]) return fail(QC_ERR_ARG, "qc_set_gather: NULL peer pointer");
+    if (!s->d_gdone) { QC_CUDA(cudaMalloc(&s->d_gdone, sizeof(unsigned int))); QC_CUDA(cudaMemset(s->d_gdone, 0, sizeof(unsigned int))); }
+    for (int r = 0; r < world; r++) { s->g_peer[r] = (double*)gather_ptrs[r]; s->g_flag[r] = (unsigned long long*)flag_ptrs[r]; }
+    s->g_world = world; s->g_rank = rank;
+    return QC_OK;
+}
+
+extern "C" uint64_t qc_gather_seq(const qc_sim* s) { return s ? s->g_seq : 0; }
+
+extern "C" int qc_gather_wait(qc_sim* s, uint64_t seq, void* stream) {
+    int rc = use_device(s); if (rc) return rc;
+    if (s->g_world <= 0) return fail(QC_ERR_STATE, "qc_gather_wait: qc_set_gather first");
+    if (launch_gather_wait(s->g_flag[s->g_rank], s->g_world, seq, stream)) return fail(QC_ERR_CUDA, "wait kernel launch failed");
+    s->launches++;
+    return QC_OK;
 }
 
 static int ensure_out(qc_sim* s) {

@@ -47,6 +47,8 @@ int build_model(const qc_config& cfg, Model& m, std::string& err);
 
 // ------------------------------------------------------------------------------------------------------
 // Kernel parameters (passed by value).
+#define QC_MAX_PEERS 8      // ranks of one NVSwitch node
+
 struct StepParams {
     // geometry
     int n, B, T, G, P, chunk, W, NP, n_sub, K, M;
@@ -81,6 +83,13 @@ struct StepParams {
     int jacobi;              // 1: register-resident chunk-Jacobi solve (one-warp trajectories, chunk == L)
     int debug;               // development only (QCART_DEBUG): 1 = skip the implicit solve, 2 = skip the explicit part; results are then wrong
     int moments_only;        // 1: skip the substep loop, only compute moments/aux of the resident state
+    // fused result exchange (qc_set_gather): every trajectory's row [moments K | aux 4 | flags 1] goes to row g_rank*B + traj of buffer
+    // (g_seq & 1) of EVERY rank's gather area (peer memory over NVLink), then the last CTA publishes g_seq in every rank's flag array
+    int g_world, g_rank;     // 0 = off
+    unsigned long long g_seq;
+    double* g_peer[QC_MAX_PEERS];                 // [2][g_world * B][K + 5] on each rank
+    unsigned long long* g_flag[QC_MAX_PEERS];     // [g_world] on each rank
+    unsigned int* g_done;    // device-local CTA counter (zero between launches)
 };
 
 struct LaunchPlan {
@@ -94,6 +103,7 @@ int launch_step(const LaunchPlan& plan, const StepParams& p, void* stream, std::
 int launch_bin(const int32_t* slot, int B, int n_slots, int T, int32_t* order, int32_t* order_count, void* stream);
 int launch_init_packets(double2* psi, int B, int n, double h, int half, const double* k, const double* mean, double stdv, void* stream);
 int launch_init_fock(double2* psi, int B, int n, const double* alpha, void* stream);
+int launch_gather_wait(const unsigned long long* flags, int world, unsigned long long seq, void* stream);
 int measure_fp64_peak(int device, double* flops);
 int measure_smem_peak(int device, double* bps);
 

@@ -478,6 +478,37 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
     traj_sync<MULTI>(bar_id, G);                           // the whole result is in U
 }
 
+// Fused result exchange (include/qcart.h, qc_set_gather): the first warp of the trajectory copies the row it has just written to the
+// local outputs -- [moments K | aux 4 | flags 1] as doubles -- into row (rank * B + traj) of the current buffer of every rank's gather area.
+// Peer buffers are ordinary global pointers (CUDA IPC mappings over NVLink); one coalesced 8 (K + 5)-byte store per rank.
+__device__ __forceinline__ void publish_row(const StepParams& p, int traj, int lane) {
+    __syncwarp();                                     // lane 0 wrote moments / aux / flags_out of this trajectory
+    const int cols = p.K + QC_AUX_COUNT + 1;
+    if (lane < cols) {
+        double v;
+        if (lane < p.K) v = p.moments[(size_t)traj * p.K + lane];
+        else if (lane < p.K + QC_AUX_COUNT) v = p.aux[(size_t)traj * QC_AUX_COUNT + (lane - p.K)];
+        else v = (double)p.flags_out[traj];
+        const size_t row = (size_t)(p.g_seq & 1ull) * (size_t)p.g_world * p.B + (size_t)p.g_rank * p.B + traj;
+        for (int r = 0; r < p.g_world; r++) p.g_peer[r][row * cols + lane] = v;
+        __threadfence_system();                       // the rows must be visible system-wide before the flag below
+    }
+}
+// Last CTA of the launch: publish the sequence number in slot `rank` of every rank's flag array (release at system scope).
+__device__ __forceinline__ void publish_done(const StepParams& p) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int ticket = atomicAdd(p.g_done, 1u);
+        if (ticket == gridDim.x - 1) {
+            *p.g_done = 0u;                           // ready for the next launch (stream-ordered)
+            __threadfence_system();
+            for (int r = 0; r < p.g_world; r++)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.g_flag[r] + p.g_rank), "l"(p.g_seq) : "memory");
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 template <int VAR, int L, int GC, int MAXT, bool TABS>
 __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
@@ -1042,6 +1073,10 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
                 ax[QC_AUX_ENERGY] = v0[6]; ax[QC_AUX_XMEAN] = v0[1]; ax[QC_AUX_OUTSIDE] = 0.0; ax[QC_AUX_NORM] = v0[0];
             }
         }
+    }
+    if (p.g_world > 0) {                              // uniform over the grid
+        if (have && g < 32) publish_row(p, traj, lane);
+        publish_done(p);
     }
 }
 

@@ -218,6 +218,18 @@ __global__ void fp64_peak_kernel(double* out, int iters, double seed) {
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+// Consumer side of the fused result exchange: thread r spins (acquire, system scope) until rank r has published sequence number `seq`.
+__global__ void gather_wait_kernel(const unsigned long long* __restrict__ flags, int world, unsigned long long seq) {
+    if ((int)threadIdx.x < world) {
+        unsigned long long v;
+        do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory"); if (v < seq) __nanosleep(200); } while (v < seq);
+    }
+}
+int launch_gather_wait(const unsigned long long* flags, int world, unsigned long long seq, void* stream) {
+    gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, world, seq);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 int measure_fp64_peak(int device, double* flops) {
     if (cudaSetDevice(device) != cudaSuccess) return QC_ERR_CUDA;
     int n_sm = 0; cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);

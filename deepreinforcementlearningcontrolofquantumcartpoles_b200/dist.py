@@ -1,4 +1,5 @@
-"""Multi-GPU plumbing: one process per GPU, trajectories sharded over ranks, one all-gather per control step.
+"""Multi-GPU plumbing: one process per GPU, trajectories sharded over ranks, one result exchange per control step -- fused into the
+SSE kernel over peer memory (FusedGather) or as a separate NCCL all-gather (pack_block / all_gather_block).
 
 The reference has no distributed code: its only parallelism is one OS process per trajectory
 (`num_of_actors` forked actors, quartic main_parallel.py:254-369).  Here the batch axis shards over ranks with NO data-path
@@ -59,3 +60,103 @@ def all_gather_block(block, world, out=None):
         out = torch.empty((world * block.shape[0], block.shape[1]), dtype=block.dtype, device=block.device)
     dist.all_gather_into_tensor(out, block)
     return out
+
+
+# ---- fused result exchange over peer memory (include/qcart.h: qc_set_gather) ---------------------------------------------------------
+class _DeviceArray:
+    """Raw device memory as a __cuda_array_interface__ object, so that torch can view it without owning it."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class FusedGather:
+    """The per-control-step result block [world * B, K + 5] assembled on every rank by the SSE kernel itself: each rank's kernel stores its
+    rows into all ranks' gather areas (CUDA-IPC peer memory over NVLink) and publishes a sequence flag; `wait()` enqueues the consumer-side
+    spin kernel.  Replaces pack_block + all_gather_block (one NCCL collective and three small kernels per control step).
+
+    Multi-process use (one rank per GPU, torch.distributed initialised):   fg = FusedGather(sim, rank, world)
+    Single-process use (tests; several sims acting as ranks on one device): fgs = FusedGather.local_group(sims)
+    """
+
+    def __init__(self, sim, rank, world, _wire=True):
+        import ctypes as C
+        from . import _lib as L
+        self.sim, self.rank, self.world, self.lib = sim, int(rank), int(world), L.load()
+        self.cols, self.rows = sim.K + L.QC_AUX_COUNT + 1, self.world * sim.B
+        self._C, self._L = C, L
+        self.gather_ptr, self.gather_handle = self._alloc(2 * self.rows * self.cols * 8)
+        self.flag_ptr, self.flag_handle = self._alloc(max(self.world, 1) * 8)
+        self.peer_g, self.peer_f, self._opened = [None] * self.world, [None] * self.world, []
+        self.peer_g[self.rank], self.peer_f[self.rank] = self.gather_ptr, self.flag_ptr
+        if _wire:
+            if self.world > 1:
+                import torch.distributed as dist
+                handles = [None] * self.world
+                dist.all_gather_object(handles, (self.gather_handle, self.flag_handle))
+                for r, (hg, hf) in enumerate(handles):
+                    if r != self.rank:
+                        self.peer_g[r], self.peer_f[r] = self._open(hg), self._open(hf)
+            self._activate()
+
+    def _alloc(self, nbytes):
+        C = self._C
+        ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        self._L.check(self.lib.qc_peer_alloc(self.sim.device, int(nbytes), C.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def _open(self, handle):
+        C = self._C
+        ptr = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._L.check(self.lib.qc_peer_open(self.sim.device, buf, C.byref(ptr)))
+        self._opened.append(ptr.value)
+        return ptr.value
+
+    def _activate(self):
+        C = self._C
+        g = (C.c_void_p * self.world)(*self.peer_g)
+        f = (C.c_void_p * self.world)(*self.peer_f)
+        self._L.check(self.lib.qc_set_gather(self.sim.h, self.rank, self.world, g, f))
+
+    @classmethod
+    def local_group(cls, sims):
+        """Several sims on the devices of ONE process play the ranks (no IPC: the pointers are passed directly)."""
+        fgs = [cls(s, r, len(sims), _wire=False) for r, s in enumerate(sims)]
+        for a in fgs:
+            for r, b in enumerate(fgs):
+                a.peer_g[r], a.peer_f[r] = b.gather_ptr, b.flag_ptr
+            a._activate()
+        return fgs
+
+    def seq(self):
+        return int(self.lib.qc_gather_seq(self.sim.h))
+
+    def wait(self, seq=None):
+        """Enqueue (on the current stream) the wait for every rank's rows of control step `seq` (default: the last qc_step of this rank)."""
+        self._L.check(self.lib.qc_gather_wait(self.sim.h, self.seq() if seq is None else int(seq), self.sim._stream()))
+
+    def block(self, seq=None):
+        """[world * B, K + 5] float64 view of the buffer holding control step `seq`; valid after wait(seq) in stream order."""
+        import torch
+        seq = self.seq() if seq is None else int(seq)
+        off = (seq & 1) * self.rows * self.cols * 8
+        return torch.as_tensor(_DeviceArray(self.gather_ptr + off, (self.rows, self.cols), "<f8"), device="cuda:%d" % self.sim.device)
+
+    def close(self):
+        import torch
+        if getattr(self, "sim", None) is None:
+            return
+        torch.cuda.synchronize(self.sim.device)
+        if self.world > 1 and self._opened:
+            import torch.distributed as dist
+            dist.barrier()                           # nobody may still be storing into a mapping that is about to go away
+        self.lib.qc_set_gather(self.sim.h, 0, 0, None, None)
+        for p in self._opened:
+            self.lib.qc_peer_close(self.sim.device, self._C.c_void_p(p))
+        if self.world > 1 and self._opened:
+            import torch.distributed as dist
+            dist.barrier()
+        self.lib.qc_peer_free(self.sim.device, self._C.c_void_p(self.gather_ptr))
+        self.lib.qc_peer_free(self.sim.device, self._C.c_void_p(self.flag_ptr))
+        self.sim = None

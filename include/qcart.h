@@ -163,6 +163,27 @@ int qc_x_expectation1(qc_sim *sim, const double *psi, double *out);
 /* The (r0, r1) pair the kernel draws for (seed, global trajectory id, substep counter): host restatement of the
  * in-kernel Philox4x32-10 + Box-Muller, for verification. */
 void qc_philox_normals(uint64_t seed, uint64_t traj, uint64_t step, double *out2);
+/* ---- multi-GPU: fused result exchange over peer memory ------------------------------------------------------
+ * Trajectories shard over ranks with no data-path collective; the only exchange is the per-control-step result block.  Instead of a
+ * separate pack + all-gather, the SSE kernel itself stores every trajectory's row [moments K | aux 4 | flags 1] (float64) into row
+ * rank*B + b of the current buffer of EVERY rank's gather area -- ordinary stores to CUDA-IPC mapped peer memory over NVLink /
+ * NVSwitch, issued from the kernel's epilogue -- and its last CTA publishes a sequence number in every rank's flag array
+ * (st.release.sys).  qc_gather_wait enqueues the consumer side: a one-warp kernel that spins (ld.acquire.sys) until all ranks have
+ * published that sequence number.  Gather area per rank: double[2][world * B][K + 5] (buffers alternate with the parity of the sequence
+ * number), flag array: uint64[world], both zero-initialised by qc_peer_alloc.
+ *
+ * qc_peer_alloc / qc_peer_open wrap cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle; the 64-byte handles travel between the
+ * rank processes by any host channel (the Python mirror uses torch.distributed.all_gather_object). */
+int qc_peer_alloc(int32_t device, uint64_t bytes, void **ptr, unsigned char *handle64);
+int qc_peer_free(int32_t device, void *ptr);
+int qc_peer_open(int32_t device, const unsigned char *handle64, void **ptr);
+int qc_peer_close(int32_t device, void *ptr);
+/* gather_ptrs[r] / flag_ptrs[r]: rank r's gather area / flag array as seen from THIS process (own allocation for r == rank).
+ * world = 0 switches the exchange off.  While it is on, qc_step requires moments, aux and flags output buffers. */
+int qc_set_gather(qc_sim *sim, int32_t rank, int32_t world, void *const *gather_ptrs, void *const *flag_ptrs);
+uint64_t qc_gather_seq(const qc_sim *sim);        /* sequence number of the last qc_step (1, 2, ...); its rows are in buffer seq & 1 */
+int qc_gather_wait(qc_sim *sim, uint64_t seq, void *stream);
+
 /* Micro-benchmarks used by bench.py for the roofline denominators (not in MEASURED_PEAKS.json):
  * dependent-free DFMA loop on all SMs -> FLOP/s; conflict-free 128-bit shared-memory load loop -> bytes/s. */
 int qc_measure_fp64_peak(int device, double *flops_per_s);

@@ -174,3 +174,37 @@ def test_env_reset_step_protocol(task):
             if bool(done.all()):
                 break
         assert bool(done.all()) and float(reward.max()) == -1.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["quartic", "harmonic"])
+def test_fused_result_exchange_single_process_ranks(task):
+    """qc_set_gather: three sims on one device play three ranks; every rank's gather area ends up with all rows, in rank order, equal to
+    pack_block of each rank's own outputs, for two consecutive control steps (both buffers), and the wait kernel lets the stream pass."""
+    import torch
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200 import dist as qdist
+    params = configs.PRESETS[task](n_sub=8)
+    B, world = 40, 3
+    sims = [BatchedSim(params, batch=B, seed=3, traj_offset=r * B) for r in range(world)]
+    for r, s in enumerate(sims):
+        s.set_state(initial_states(params, B, seed=10 + r))
+    fgs = qdist.FusedGather.local_group(sims)
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    for step in range(1, 3):
+        packed = []
+        for s in sims:
+            act = torch.randint(0, params["n_levels"], (B,), device="cuda", dtype=torch.int32, generator=g)
+            out = s.step(act)
+            packed.append(qdist.pack_block(out["moments"], out["aux"], out["flags"]))
+        expect = torch.cat(packed, dim=0)
+        for fg in fgs:
+            assert fg.seq() == step
+            fg.wait()
+            torch.cuda.synchronize()
+            assert torch.equal(fg.block(), expect)
+    with pytest.raises(L.QcartError):                      # the exchange needs all three output buffers
+        L.check(sims[0].lib.qc_step(sims[0].h, act.data_ptr(), None, 8, None, None, None, None, None, None, sims[0]._stream()))
+    for fg in fgs:
+        fg.close()
+    out = sims[0].step(act)                                     # exchange switched off again: plain step works
+    assert torch.isfinite(out["moments"]).all()
