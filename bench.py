@@ -225,6 +225,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-traj-per-thread", type=int, default=0, help="0 = sized for ~2 s of CPU work per timed step")
     ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N>1: how the per-step result block reaches every rank: stored by the SSE kernel into peer memory (fused) or pack + NCCL all-gather")
     ap.add_argument("--no-closed-loop", action="store_true", help="skip the policy + experience-row closed-loop measurement (N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -258,6 +260,27 @@ def main():
     actions = torch.randint(0, params["n_levels"], (W_steps + K_steps, B), device=dev, dtype=torch.int32, generator=g)   # redrawn each control step
     out = sim.alloc_outputs()
     gathered = torch.empty((world * B, sim.K + 5), dtype=torch.float64, device=dev) if world > 1 else None
+    fused, gather_mode = None, ("nccl" if world > 1 else None)
+    if world > 1 and args.gather == "fused":
+        try:                                            # CUDA IPC can be unavailable in some containers: then every rank uses the NCCL path
+            fused = qdist.FusedGather(sim, rank, world)
+            ok = torch.ones(1, device=dev)
+        except Exception as e:                          # noqa: BLE001
+            sys.stderr.write("rank %d: fused result exchange unavailable (%s); using NCCL all-gather\n" % (rank, e))
+            ok = torch.zeros(1, device=dev)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        if ok.item() < 1:
+            if fused is not None:
+                fused.close()
+            fused = None
+        gather_mode = "fused" if fused is not None else "nccl (fused unavailable)"
+
+    def exchange():
+        """Every rank obtains the [world*B, K+5] result block of this control step."""
+        if fused is not None:
+            fused.wait()                                # rows were stored by the kernel itself; this only waits for the other ranks' flags
+        elif world > 1:
+            qdist.all_gather_block(qdist.pack_block(out["moments"], out["aux"], out["flags"]), world, gathered)
     flush_buf = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     # roofline denominators measured in-process (MEASURED_PEAKS.json has no FP64 / shared-memory entry)
@@ -265,8 +288,7 @@ def main():
 
     def one_step(i):
         sim.step(actions[i], out=out)
-        if world > 1:
-            qdist.all_gather_block(qdist.pack_block(out["moments"], out["aux"], out["flags"]), world, gathered)
+        exchange()
 
     for i in range(W_steps):
         one_step(i)
@@ -289,8 +311,7 @@ def main():
         kev[i][0].record()
         sim.step(actions[W_steps + i], out=out)
         kev[i][1].record()
-        if world > 1:
-            qdist.all_gather_block(qdist.pack_block(out["moments"], out["aux"], out["flags"]), world, gathered)
+        exchange()
         e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -307,6 +328,12 @@ def main():
         ms_total = float(t.item())
     value = world * B * K_steps / (ms_total * 1e-3)
     norm_dev = float((out["aux"][:, L.QC_AUX_NORM] - 1).abs().max().item())
+    gather_ok = None
+    if fused is not None:                               # the fused block of the last step must equal a plain NCCL all-gather of the same outputs
+        qdist.all_gather_block(qdist.pack_block(out["moments"], out["aux"], out["flags"]), world, gathered)
+        gather_ok = bool(torch.equal(fused.block(), gathered))
+        fused.close()
+        sim.step(actions[0], out=out)                   # (the end-to-end leg below runs without the exchange)
 
     # ---- end-to-end through the host-buffer C-ABI call (pinned host memory, H2D + kernel + D2H per step) ----
     act_host = actions.cpu().pin_memory()
@@ -380,11 +407,12 @@ def main():
                        "state_len": n, "n_sub": params["n_sub"], "noise": "in-kernel Philox4x32-10 + Box-Muller",
                        "actions": "uniform over 21 levels, redrawn every control step (torch.Generator seed 0)",
                        "l2": "inputs (2.8 MB/GPU) fit L2; L2 flushed with a 256 MiB write between timed steps, per-step CUDA events summed" if flush_buf is not None else "no flush",
-                       "parallelism": "%d rank(s), trajectories sharded, all-gather of [B,%d] f64 block per step" % (world, sim.K + 5) if world > 1 else "1 rank"},
+                       "parallelism": ("%d rank(s), trajectories sharded, [B,%d] f64 result block per step %s" % (world, sim.K + 5,
+                                        "stored by the SSE kernel into every rank's peer memory + flag wait (fused)" if gather_mode == "fused" else "by pack + NCCL all-gather [%s]" % gather_mode)) if world > 1 else "1 rank"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": "traj-control-steps/s", "h2d_bytes_per_step": B * 4,
                                       "d2h_bytes_per_step": B * (sim.K * 8 + L.QC_AUX_COUNT * 8 + 1)},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "closed_loop": closed_loop,
-            "check": {"max_norm_deviation": norm_dev, "wall_s_timed_region": t_wall}}
+            "check": {"max_norm_deviation": norm_dev, "wall_s_timed_region": t_wall, "fused_gather_equals_nccl": gather_ok}}
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
