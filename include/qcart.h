@@ -163,6 +163,7 @@ int qc_x_expectation1(qc_sim *sim, const double *psi, double *out);
 /* The (r0, r1) pair the kernel draws for (seed, global trajectory id, substep counter): host restatement of the
  * in-kernel Philox4x32-10 + Box-Muller, for verification. */
 void qc_philox_normals(uint64_t seed, uint64_t traj, uint64_t step, double *out2);
+
 /* ---- multi-GPU: fused result exchange over peer memory ------------------------------------------------------
  * Trajectories shard over ranks with no data-path collective; the only exchange is the per-control-step result block.  Instead of a
  * separate pack + all-gather, the SSE kernel itself stores every trajectory's row [moments K | aux 4 | flags 1] (float64) into row
