@@ -244,6 +244,11 @@ def main():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from common import initial_states
 
+    # stdout carries exactly ONE line, the JSON record: libraries that write to file descriptor 1 (NCCL prints its version there) are
+    # diverted to stderr for the whole run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     rank, local_rank, world = qdist.init_process_group()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the SSE hot path has no CPU fallback")
@@ -413,7 +418,8 @@ def main():
                                       "d2h_bytes_per_step": B * (sim.K * 8 + L.QC_AUX_COUNT * 8 + 1)},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "closed_loop": closed_loop,
             "check": {"max_norm_deviation": norm_dev, "wall_s_timed_region": t_wall, "fused_gather_equals_nccl": gather_ok}}
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         torch.distributed.destroy_process_group()
 
