@@ -81,6 +81,7 @@ SYMBOLS = [
     ("qc_epsilon_greedy", C.c_int, [_vp, _i64, C.c_int32, C.c_double, C.c_uint64, _i64, C.c_uint64, _vp, _vp, C.c_int32, _vp]),
     ("qc_action_forces", C.c_int, [_vp, _i64, C.c_int32, C.c_double, _vp, C.c_int32, _vp]),
     ("qc_policy_launch_count", _i64, [_vp]),
+    ("qc_policy_set_gemm", C.c_int, [_vp, C.c_int32]),
     ("qc_replay_create", C.c_int, [C.c_int32, _i64, C.c_int32, C.POINTER(_vp)]),
     ("qc_replay_destroy", C.c_int, [_vp]),
     ("qc_replay_push", C.c_int, [_vp, _vp, _vp, C.c_int32, _vp, _vp, _i64, C.c_double, _vp, _i64, _vp]),

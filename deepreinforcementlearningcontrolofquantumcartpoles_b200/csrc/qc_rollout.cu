@@ -157,6 +157,164 @@ __global__ void __launch_bounds__(NG * 256, NG == 1 ? 4 : 1) gemm_splitk_kernel(
     }
 }
 
+// ---- tensor-core variant of the same GEMM (tcgen05, sm_100a) -----------------------------------------------------------------------
+// C_z[M, N] = A_z[M, K] W_z[N, K]^T with the 5th-generation tensor cores: one CTA owns a 128 x NT output tile whose fp32 accumulator
+// lives in tensor memory (NT columns x 128 lanes), operands are staged by the CTA's 128 threads into shared memory in the K-major,
+// no-swizzle canonical layout (8 rows x 16 B core matrices; LBO = distance of adjacent K chunks, SBO = 128 B between 8-row groups) and one
+// elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = NT, K = 8 per instruction).  The stage buffers are double
+// buffered: tcgen05.commit arrives on the buffer's mbarrier when the MMAs reading it have retired, so global loads of stage s+1 overlap
+// the MMAs of stage s.
+// Precision: the reference evaluates the policy in fp32, and argmax decides the action, so every product is done as a 3xTF32 split
+//     a = a_hi + a_lo (a_hi = a with the low 13 mantissa bits cleared),   a w ~= a_lo w_hi + a_hi w_lo + a_hi w_hi,
+// which leaves ~2^-21 relative error per product (fp32 accumulation in tensor memory) instead of TF32's 2^-11.
+constexpr int UM = 128, UK = 32;                          // rows per CTA, K floats per stage (4 MMA k-steps)
+constexpr int UQ = 4;                                     // separate tensor-memory accumulators over K quarters, summed in fp32 (round to nearest)
+                                                          // by the epilogue: the tensor core's accumulation truncates, and a 4x shorter chain
+                                                          // keeps its bias (measured -7e-6 relative with one accumulator over K = 512) 4x smaller
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(128) gemm_umma_kernel(const GemmArgs g) {
+    extern __shared__ __align__(128) unsigned char usm[];
+    constexpr int A_FLOATS = UM * UK, W_FLOATS = NT * UK, STAGE_FLOATS = 2 * (A_FLOATS + W_FLOATS);     // hi and lo copies
+    float* stage0 = reinterpret_cast<float*>(usm);
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int z = blockIdx.z, m0 = blockIdx.y * UM, n0 = blockIdx.x * NT;
+    const float* Ag = (z == 0 ? g.A : g.A2);
+    const float* Wg = (z == 0 ? g.W : g.S);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"((uint32_t)(UQ * NT)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[0])), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[1])), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = tmem_base;
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+    const bool arow_ok = (m0 + tid) < g.M;
+    const float* arow = Ag + (size_t)(m0 + tid) * g.K;
+    // W tile: NT rows; thread t stages row t % NT, chunks [(t / NT) * CPT, +CPT)
+    constexpr int WT = 128 / NT, CPT = 8 / WT;           // threads per W row, chunks per thread (NT = 32: 4 x 2, 64: 2 x 4, 128: 1 x 8)
+    const int wrow = tid % NT, wc0 = (tid / NT) * CPT;
+    const float* wrowp = Wg + (size_t)(n0 + wrow) * g.K;
+    const int nstages = g.K / UK, per_q = (nstages + UQ - 1) / UQ;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 ra[8], rw[CPT];                               // global data of the NEXT stage: in flight while this stage is split, stored and issued
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) ra[c] = arow_ok ? *reinterpret_cast<const float4*>(arow + k0 + 4 * c) : z4;
+#pragma unroll
+        for (int cc = 0; cc < CPT; cc++) rw[cc] = *reinterpret_cast<const float4*>(wrowp + k0 + 4 * (wc0 + cc));
+    };
+    auto hi4 = [](const float4& a) {
+        return make_float4(__uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u),
+                           __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u));
+    };
+    fetch(0);
+    for (int s = 0; s < nstages; s++) {
+        const int b = s & 1;
+        float* A_hi = stage0 + (size_t)b * STAGE_FLOATS; float* A_lo = A_hi + A_FLOATS; float* W_hi = A_lo + A_FLOATS; float* W_lo = W_hi + W_FLOATS;
+        if (s >= 2) mbar_wait(smem_u32(&mbar[b]), (uint32_t)(((s >> 1) - 1) & 1));       // the MMAs of stage s-2 have finished reading this buffer
+#pragma unroll
+        for (int c = 0; c < 8; c++) {                     // A: thread = row, 8 chunks of 4 floats; chunk-major canonical layout
+            const float4 a = ra[c], hi = hi4(a);
+            const int off = ((c * (UM / 8) + (tid >> 3)) * 8 + (tid & 7)) * 4;
+            *reinterpret_cast<float4*>(A_hi + off) = hi;
+            *reinterpret_cast<float4*>(A_lo + off) = make_float4(a.x - hi.x, a.y - hi.y, a.z - hi.z, a.w - hi.w);
+        }
+#pragma unroll
+        for (int cc = 0; cc < CPT; cc++) {
+            const int c = wc0 + cc;
+            const float4 w = rw[cc], hi = hi4(w);
+            const int off = ((c * (NT / 8) + (wrow >> 3)) * 8 + (wrow & 7)) * 4;
+            *reinterpret_cast<float4*>(W_hi + off) = hi;
+            *reinterpret_cast<float4*>(W_lo + off) = make_float4(w.x - hi.x, w.y - hi.y, w.z - hi.z, w.w - hi.w);
+        }
+        if (s + 1 < nstages) fetch((s + 1) * UK);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core's async proxy
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ah = smem_u32(A_hi), al = smem_u32(A_lo), wh = smem_u32(W_hi), wl = smem_u32(W_lo);
+#pragma unroll
+            for (int ks = 0; ks < UK / 8; ks++) {
+                const uint32_t ao = ks * 2 * (UM / 8) * 128, wo = ks * 2 * (NT / 8) * 128;
+                const uint64_t d_ah = umma_desc(ah + ao, (UM / 8) * 128, 128), d_al = umma_desc(al + ao, (UM / 8) * 128, 128);
+                const uint64_t d_wh = umma_desc(wh + wo, (NT / 8) * 128, 128), d_wl = umma_desc(wl + wo, (NT / 8) * 128, 128);
+                const uint32_t first = (s % per_q != 0 || ks > 0) ? 1u : 0u;        // each K quarter starts a fresh accumulator
+                const uint32_t tacc = taddr + (uint32_t)((s / per_q) * NT);
+#define QC_UMMA(DA, DB, ACC)                                                                                                   \
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                                   \
+                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"                  \
+                             ::"r"(tacc), "l"(DA), "l"(DB), "r"(idesc), "r"(ACC), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory")
+                QC_UMMA(d_al, d_wh, first);               // small terms first
+                QC_UMMA(d_ah, d_wl, 1u);
+                QC_UMMA(d_ah, d_wh, 1u);
+#undef QC_UMMA
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[b])) : "memory");
+        }
+    }
+    {   // all MMAs retire in order: the last stage's commit covers everything
+        const int s = nstages - 1;
+        mbar_wait(smem_u32(&mbar[s & 1]), (uint32_t)((s >> 1) & 1));
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: thread = output row (tensor-memory lane), NT columns in groups of 8
+    const int m = m0 + tid;
+    const bool epi = g.relu_bias && z == 0;
+    float* C = g.C + (size_t)z * g.M * g.N;
+    const int nq = (nstages + per_q - 1) / per_q;        // accumulators actually used
+    for (int c0 = 0; c0 < NT; c0 += 8) {
+        float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int qd = 0; qd < nq; qd++) {
+            uint32_t t[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
+                         : "r"(taddr + ((uint32_t)(warp * 32) << 16) + (uint32_t)(qd * NT + c0)) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] += __uint_as_float(t[j]);
+        }
+        if (m < g.M) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = r[j];
+            const int n = n0 + c0;
+            if (epi) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j] + __ldg(&g.bias[n + j]), 0.0f);
+            }
+            *reinterpret_cast<float4*>(C + (size_t)m * g.N + n) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(C + (size_t)m * g.N + n + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            if (g.C2 != nullptr && z == 0) {
+                const float4 e0 = *reinterpret_cast<const float4*>(g.ei + (size_t)m * g.ldn + n), e1 = *reinterpret_cast<const float4*>(g.ei + (size_t)m * g.ldn + n + 4);
+                *reinterpret_cast<float4*>(g.C2 + (size_t)m * g.N + n) = make_float4(v[0] * e0.x, v[1] * e0.y, v[2] * e0.z, v[3] * e0.w);
+                *reinterpret_cast<float4*>(g.C2 + (size_t)m * g.N + n + 4) = make_float4(v[4] * e1.x, v[5] * e1.y, v[6] * e1.z, v[7] * e1.w);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"((uint32_t)(UQ * NT)) : "memory");
+}
+
 // Output layer + argmax.  Input: the two raw halves y1 = h2 u_w31^T, y2 = (h2 * e_in31) sigma_w31^T of the (noisy) fc31 layer; this kernel
 // first forms  x = relu(y1 + u_b31 + e_out31 * (y2 + sigma_b31))  (layers.py:52-56), then the n_actions-wide noisy layer fc41 and the argmax.
 // The transposed u_w41 / sigma_w41 are staged in shared memory once per CTA; lane o of a warp owns output o, one trajectory per warp at a time.
@@ -374,6 +532,7 @@ struct qc_policy {
     float *h1 = nullptr, *h2 = nullptr, *h2n = nullptr, *a3 = nullptr, *hv = nullptr, *noise = nullptr;
     int64_t cap = 0;
     int64_t launches = 0;
+    int gemm_kind = 0;       // 0: tcgen05 3xTF32 kernel (default), 1: CUDA-core fp32 kernel (cross-check; QCART_GEMM_SIMT=1 makes it the default)
 };
 
 extern "C" int qc_obs_f32(const double* moments, int64_t count, double input_scaling, float* obs, void* stream) {
@@ -394,6 +553,7 @@ extern "C" int qc_policy_create(int32_t n_in, int32_t n_actions, int32_t noisy_l
     qc_policy* p = new (std::nothrow) qc_policy();
     if (!p) return set_error(QC_ERR_CUDA, "out of host memory");
     p->n_in = n_in; p->n_actions = n_actions; p->noisy_layers = noisy_layers; p->device = device;
+    p->gemm_kind = getenv("QCART_GEMM_SIMT") ? 1 : 0;
     int64_t* z = p->psize;
     z[QC_P_FC1_W] = (int64_t)H1 * n_in; z[QC_P_FC1_B] = H1; z[QC_P_FC2_W] = (int64_t)H2 * H1; z[QC_P_FC2_B] = H2;
     z[QC_P_FC31_UW] = (int64_t)H3 * H2; z[QC_P_FC31_UB] = H3;
@@ -430,6 +590,12 @@ extern "C" int64_t qc_policy_noise_width(const qc_policy* p) {
 
 extern "C" int64_t qc_policy_launch_count(const qc_policy* p) { return p ? p->launches : 0; }
 
+extern "C" int qc_policy_set_gemm(qc_policy* p, int32_t kind) {
+    if (!p || kind < 0 || kind > 1) return set_error(QC_ERR_ARG, "qc_policy_set_gemm: kind must be 0 (tcgen05 3xTF32) or 1 (CUDA-core fp32)");
+    p->gemm_kind = kind;
+    return QC_OK;
+}
+
 extern "C" int qc_policy_set_param(qc_policy* p, int32_t which, const float* host, int64_t count) {
     if (!p || which < 0 || which >= QC_P_COUNT || !host) return set_error(QC_ERR_ARG, "qc_policy_set_param: bad handle, index or pointer");
     if (p->psize[which] == 0) return set_error(QC_ERR_ARG, "qc_policy_set_param: this tensor does not exist for the policy's noisy_layers");
@@ -444,13 +610,29 @@ constexpr size_t GEMM_SMEM_1 = sizeof(float) * (size_t)TILE_FLOATS;
 constexpr size_t GEMM_SMEM_4 = sizeof(float) * ((size_t)4 * TILE_FLOATS + (size_t)3 * BM * BN);
 constexpr size_t HEAD_SMEM = sizeof(float) * ((size_t)2 * H3 * HLD + (size_t)HEAD_WARPS * 2 * H3);
 
-static int launch_gemm(const GemmArgs& g, int nz, cudaStream_t st) {
+static int launch_gemm(const GemmArgs& g, int nz, cudaStream_t st, bool use_umma) {
     static thread_local bool attr_set[64] = {};
     int dev = 0; cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
         RO_CUDA(cudaFuncSetAttribute(gemm_splitk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_4));
         RO_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM));
         attr_set[dev] = true;
+    }
+    if (use_umma && g.K % UK == 0 && g.N % 64 == 0) {
+        constexpr size_t smem64 = sizeof(float) * 2 * 2 * (size_t)(UM * UK + 64 * UK), smem32 = sizeof(float) * 2 * 2 * (size_t)(UM * UK + 32 * UK);
+        static thread_local bool umma_attr[64] = {};
+        if (dev < 64 && !umma_attr[dev]) {
+            RO_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+            RO_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+            umma_attr[dev] = true;
+        }
+        const int mt = (g.M + UM - 1) / UM;
+        if ((size_t)(g.N / 64) * mt * nz < 2 * 148) {     // small batches: narrower tiles so that the grid covers the SMs
+            gemm_umma_kernel<32><<<dim3(g.N / 32, mt, nz), 128, smem32, st>>>(g);
+        } else {
+            gemm_umma_kernel<64><<<dim3(g.N / 64, mt, nz), 128, smem64, st>>>(g);
+        }
+        return QC_OK;
     }
     const dim3 grid(g.N / BN, (g.M + BM - 1) / BM, nz);
     static const int force_ng = getenv("QCART_GEMM_NG") ? atoi(getenv("QCART_GEMM_NG")) : 0;
@@ -494,10 +676,10 @@ extern "C" int qc_policy_forward(qc_policy* p, const float* obs, int64_t B, int3
     const bool n31 = any_noise && p->noisy_layers >= 2, n41 = any_noise && p->noisy_layers >= 1;
     g.A = p->h1; g.W = p->param[QC_P_FC2_W]; g.bias = p->param[QC_P_FC2_B]; g.C = p->h2; g.M = (int)B; g.N = H2; g.K = H1; g.ldn = NW; g.relu_bias = 1;
     if (n31) { g.C2 = p->h2n; g.ei = nz; }              // h2 * e_in31 for the sigma_w half of fc31
-    if (int rc = launch_gemm(g, 1, st)) return rc;
+    if (int rc = launch_gemm(g, 1, st, p->gemm_kind == 0)) return rc;
     g = GemmArgs{};                                     // fc31: raw halves y1 (z = 0) and y2 (z = 1); combined by the head kernel
     g.A = p->h2; g.A2 = p->h2n; g.W = p->param[QC_P_FC31_UW]; g.S = p->param[QC_P_FC31_SW]; g.ldn = NW; g.C = p->a3; g.M = (int)B; g.N = H3; g.K = H2; g.relu_bias = 0;
-    if (int rc = launch_gemm(g, n31 ? 2 : 1, st)) return rc;
+    if (int rc = launch_gemm(g, n31 ? 2 : 1, st, p->gemm_kind == 0)) return rc;
     p->launches += 3;
     if (q || greedy) {
         HeadArgs h{};
@@ -511,7 +693,7 @@ extern "C" int qc_policy_forward(qc_policy* p, const float* obs, int64_t B, int3
     if (value) {
         g = GemmArgs{};
         g.A = p->h2; g.W = p->param[QC_P_FC32_W]; g.bias = p->param[QC_P_FC32_B]; g.C = p->hv; g.M = (int)B; g.N = HV; g.K = H2; g.ldn = NW; g.relu_bias = 1;
-        if (int rc = launch_gemm(g, 1, st)) return rc;
+        if (int rc = launch_gemm(g, 1, st, p->gemm_kind == 0)) return rc;
         value_kernel<<<blocks_for(B, 8), 256, 0, st>>>(p->hv, p->param[QC_P_FC42_W], p->param[QC_P_FC42_B], value, B);
         p->launches += 2;
     }

@@ -135,6 +135,10 @@ class DirectDQNPolicy:
     def launch_count(self):
         return int(self.lib.qc_policy_launch_count(self.h))
 
+    def set_gemm(self, kind):
+        """"tcgen05" (default: 3xTF32 on the tensor cores) or "simt" (fp32 FMA on the CUDA cores, the cross-check)."""
+        L.check(self.lib.qc_policy_set_gemm(self.h, {"tcgen05": 0, "simt": 1}[kind]))
+
 
 def observation(moments, input_scaling=1.0):
     """float32(moments) * input_scaling on the device (`get_data(state)*args.input_scaling`, quartic main_parallel.py:128-131,210)."""

@@ -61,7 +61,8 @@ int64_t qc_policy_noise_width(const qc_policy *p);
 
 /* One batched forward pass (Q/main_parallel.py:357-358: `action_values, avg_value, _ = net(network_input); actions = action_values.max(1)[1]`).
  * obs [B, n_in] float32.  Outputs (each may be NULL): q [B, n_actions], value [B] (mean-prediction head), greedy [B] int32 argmax.
- * Arithmetic is fp32 FMA on the CUDA cores with fp32 accumulation, like the reference's fp32 torch modules. */
+ * Arithmetic: fp32 like the reference's torch modules -- the two 512-wide layers as 3xTF32 products on the tcgen05 tensor cores with fp32
+ * accumulation (error ~2^-21 per product), the input and output layers as fp32 FMA. */
 int qc_policy_forward(qc_policy *p, const float *obs, int64_t B, int32_t noise_mode, const float *noise, uint64_t seed,
                       int64_t traj_offset, uint64_t counter, float *q, float *value, int32_t *greedy, void *stream);
 
@@ -74,6 +75,9 @@ int qc_epsilon_greedy(const int32_t *greedy, int64_t B, int32_t n_actions, doubl
 int qc_action_forces(const int32_t *action, int64_t B, int32_t n_levels, double f_max, double *force, int32_t device, void *stream);
 
 int64_t qc_policy_launch_count(const qc_policy *p);
+/* Hidden-layer GEMM kernel: 0 (default) = tcgen05 tensor cores with a 3xTF32 split (fp32-level accuracy, fp32 accumulation in tensor memory),
+ * 1 = fp32 FMA on the CUDA cores (the cross-check; bit-for-bit fp32 products). */
+int qc_policy_set_gemm(qc_policy *p, int32_t kind);
 
 /* ---- experience rows --------------------------------------------------------------------------------------------------------
  * A ring of float32 rows [capacity, row_len].  qc_replay_push appends, for every trajectory with keep[b] != 0 and in trajectory order,

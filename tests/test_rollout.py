@@ -112,6 +112,26 @@ def test_policy_matches_oracle_ragged_batches(B):
 
 
 @pytest.mark.gpu
+def test_tensor_core_and_cuda_core_gemm_agree():
+    """The tcgen05 3xTF32 kernel and the fp32 CUDA-core kernel give the same action values to fp32 round-off, both within tolerance of the oracle."""
+    import torch
+    pol, sd = _policy(11)
+    B = 700                                                       # ragged: 5 full 128-row tiles + 60 rows
+    rng = np.random.Generator(np.random.PCG64(77))
+    x = (rng.standard_normal((B, 20)) * 1.5).astype(np.float32)
+    n = [RO.noisy_f(rng.standard_normal(s)).astype(np.float32) for s in ((B, 512), (B, 256), (B, 256), (B, 21))]
+    a, m = RO.direct_dqn_forward(sd, x, (n[0], n[1]), (n[2], n[3]))
+    res = {}
+    for kind in ("tcgen05", "simt"):
+        pol.set_gemm(kind)
+        out = pol.forward(torch.as_tensor(x, device="cuda"), noise=pol.pack_noise(*n), want_value=True)
+        res[kind] = out["q"].cpu().numpy()
+        _agree(res[kind], a, out["greedy"].cpu().numpy())
+        assert np.abs(out["value"].cpu().numpy() - m).max() <= QTOL * max(1.0, np.abs(m).max())
+    assert np.abs(res["tcgen05"] - res["simt"]).max() <= 0.25 * QTOL * max(1.0, np.abs(a).max()), np.abs(res["tcgen05"] - res["simt"]).max()
+
+
+@pytest.mark.gpu
 def test_policy_unset_parameter_and_bad_sizes_are_errors():
     pol = R.DirectDQNPolicy(20)
     import torch
