@@ -185,7 +185,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 template <int NT>
 __global__ void __launch_bounds__(128) gemm_umma_kernel(const GemmArgs g) {
     extern __shared__ __align__(128) unsigned char usm[];
-    constexpr int A_FLOATS = UM * UK, W_FLOATS = NT * UK, STAGE_FLOATS = 2 * (A_FLOATS + W_FLOATS);     // hi and lo copies
+    // one K chunk (4 floats = 16 B) of all rows forms a plane; planes are padded by 16 B so that the staging stores (8 lanes = 8 chunks of one
+    // row) spread over the banks.  LBO = plane stride, SBO = 128 B (8 rows of 16 B).
+    constexpr int A_PLANE = (UM + 1) * 4, W_PLANE = (NT + 1) * 4;                                     // floats
+    constexpr int A_FLOATS = 8 * A_PLANE, W_FLOATS = 8 * W_PLANE, STAGE_FLOATS = 2 * (A_FLOATS + W_FLOATS);     // hi and lo copies
     float* stage0 = reinterpret_cast<float*>(usm);
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ uint32_t tmem_base;
@@ -207,46 +210,44 @@ __global__ void __launch_bounds__(128) gemm_umma_kernel(const GemmArgs g) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t taddr = tmem_base;
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
-    const bool arow_ok = (m0 + tid) < g.M;
-    const float* arow = Ag + (size_t)(m0 + tid) * g.K;
-    // W tile: NT rows; thread t stages row t % NT, chunks [(t / NT) * CPT, +CPT)
-    constexpr int WT = 128 / NT, CPT = 8 / WT;           // threads per W row, chunks per thread (NT = 32: 4 x 2, 64: 2 x 4, 128: 1 x 8)
-    const int wrow = tid % NT, wc0 = (tid / NT) * CPT;
-    const float* wrowp = Wg + (size_t)(n0 + wrow) * g.K;
+    // staging map: 8 consecutive threads move the 8 chunks (128 contiguous bytes) of one row -> fully used cache lines; thread t handles
+    // chunk t & 7 of rows (t >> 3) + 16 i
+    const int sc = tid & 7, sr = tid >> 3;
+    constexpr int AR = UM / 16, WR = NT / 16;            // rows per thread
+    const float* abase = Ag + (size_t)(m0 + sr) * g.K + 4 * sc;
+    const float* wbase = Wg + (size_t)(n0 + sr) * g.K + 4 * sc;
     const int nstages = g.K / UK, per_q = (nstages + UQ - 1) / UQ;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 ra[8], rw[CPT];                               // global data of the NEXT stage: in flight while this stage is split, stored and issued
-    auto fetch = [&](int k0) {
+    // Global data of the next TWO stages is in flight (two explicit register sets) while the current stage is split, stored and issued.
+    auto fetch = [&](float4 (&ra)[AR], float4 (&rw)[WR], int k0) {
 #pragma unroll
-        for (int c = 0; c < 8; c++) ra[c] = arow_ok ? *reinterpret_cast<const float4*>(arow + k0 + 4 * c) : z4;
+        for (int i = 0; i < AR; i++) ra[i] = (m0 + sr + 16 * i < g.M) ? *reinterpret_cast<const float4*>(abase + (size_t)(16 * i) * g.K + k0) : z4;
 #pragma unroll
-        for (int cc = 0; cc < CPT; cc++) rw[cc] = *reinterpret_cast<const float4*>(wrowp + k0 + 4 * (wc0 + cc));
+        for (int i = 0; i < WR; i++) rw[i] = *reinterpret_cast<const float4*>(wbase + (size_t)(16 * i) * g.K + k0);
     };
     auto hi4 = [](const float4& a) {
         return make_float4(__uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u),
                            __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u), __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u));
     };
-    fetch(0);
-    for (int s = 0; s < nstages; s++) {
+    auto run_stage = [&](int s, float4 (&ra)[AR], float4 (&rw)[WR]) {
         const int b = s & 1;
         float* A_hi = stage0 + (size_t)b * STAGE_FLOATS; float* A_lo = A_hi + A_FLOATS; float* W_hi = A_lo + A_FLOATS; float* W_lo = W_hi + W_FLOATS;
         if (s >= 2) mbar_wait(smem_u32(&mbar[b]), (uint32_t)(((s >> 1) - 1) & 1));       // the MMAs of stage s-2 have finished reading this buffer
 #pragma unroll
-        for (int c = 0; c < 8; c++) {                     // A: thread = row, 8 chunks of 4 floats; chunk-major canonical layout
-            const float4 a = ra[c], hi = hi4(a);
-            const int off = ((c * (UM / 8) + (tid >> 3)) * 8 + (tid & 7)) * 4;
+        for (int i = 0; i < AR; i++) {                    // canonical K-major layout: plane = chunk, 16 B per row inside a plane
+            const float4 a = ra[i], hi = hi4(a);
+            const int off = sc * A_PLANE + (sr + 16 * i) * 4;
             *reinterpret_cast<float4*>(A_hi + off) = hi;
             *reinterpret_cast<float4*>(A_lo + off) = make_float4(a.x - hi.x, a.y - hi.y, a.z - hi.z, a.w - hi.w);
         }
 #pragma unroll
-        for (int cc = 0; cc < CPT; cc++) {
-            const int c = wc0 + cc;
-            const float4 w = rw[cc], hi = hi4(w);
-            const int off = ((c * (NT / 8) + (wrow >> 3)) * 8 + (wrow & 7)) * 4;
+        for (int i = 0; i < WR; i++) {
+            const float4 w = rw[i], hi = hi4(w);
+            const int off = sc * W_PLANE + (sr + 16 * i) * 4;
             *reinterpret_cast<float4*>(W_hi + off) = hi;
             *reinterpret_cast<float4*>(W_lo + off) = make_float4(w.x - hi.x, w.y - hi.y, w.z - hi.z, w.w - hi.w);
         }
-        if (s + 1 < nstages) fetch((s + 1) * UK);
+        if (s + 2 < nstages) fetch(ra, rw, (s + 2) * UK);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core's async proxy
         __syncthreads();
         if (tid == 0) {
@@ -254,9 +255,9 @@ __global__ void __launch_bounds__(128) gemm_umma_kernel(const GemmArgs g) {
             const uint32_t ah = smem_u32(A_hi), al = smem_u32(A_lo), wh = smem_u32(W_hi), wl = smem_u32(W_lo);
 #pragma unroll
             for (int ks = 0; ks < UK / 8; ks++) {
-                const uint32_t ao = ks * 2 * (UM / 8) * 128, wo = ks * 2 * (NT / 8) * 128;
-                const uint64_t d_ah = umma_desc(ah + ao, (UM / 8) * 128, 128), d_al = umma_desc(al + ao, (UM / 8) * 128, 128);
-                const uint64_t d_wh = umma_desc(wh + wo, (NT / 8) * 128, 128), d_wl = umma_desc(wl + wo, (NT / 8) * 128, 128);
+                const uint32_t ao = ks * 2 * A_PLANE * 4, wo = ks * 2 * W_PLANE * 4;
+                const uint64_t d_ah = umma_desc(ah + ao, A_PLANE * 4, 128), d_al = umma_desc(al + ao, A_PLANE * 4, 128);
+                const uint64_t d_wh = umma_desc(wh + wo, W_PLANE * 4, 128), d_wl = umma_desc(wl + wo, W_PLANE * 4, 128);
                 const uint32_t first = (s % per_q != 0 || ks > 0) ? 1u : 0u;        // each K quarter starts a fresh accumulator
                 const uint32_t tacc = taddr + (uint32_t)((s / per_q) * NT);
 #define QC_UMMA(DA, DB, ACC)                                                                                                   \
@@ -270,6 +271,13 @@ __global__ void __launch_bounds__(128) gemm_umma_kernel(const GemmArgs g) {
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[b])) : "memory");
         }
+    };
+    float4 raA[AR], rwA[WR], raB[AR], rwB[WR];
+    fetch(raA, rwA, 0);
+    if (nstages > 1) fetch(raB, rwB, UK);
+    for (int s = 0; s < nstages; s += 2) {
+        run_stage(s, raA, rwA);
+        if (s + 1 < nstages) run_stage(s + 1, raB, rwB);
     }
     {   // all MMAs retire in order: the last stage's commit covers everything
         const int s = nstages - 1;
@@ -619,7 +627,7 @@ static int launch_gemm(const GemmArgs& g, int nz, cudaStream_t st, bool use_umma
         attr_set[dev] = true;
     }
     if (use_umma && g.K % UK == 0 && g.N % 64 == 0) {
-        constexpr size_t smem64 = sizeof(float) * 2 * 2 * (size_t)(UM * UK + 64 * UK), smem32 = sizeof(float) * 2 * 2 * (size_t)(UM * UK + 32 * UK);
+        constexpr size_t smem64 = sizeof(float) * 2 * 2 * 8 * (size_t)((UM + 1) * 4 + (64 + 1) * 4), smem32 = sizeof(float) * 2 * 2 * 8 * (size_t)((UM + 1) * 4 + (32 + 1) * 4);
         static thread_local bool umma_attr[64] = {};
         if (dev < 64 && !umma_attr[dev]) {
             RO_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
