@@ -205,7 +205,7 @@ def closed_loop_rate(sim, params, B, steps, warmup, out):
     p1.record()
     torch.cuda.synchronize()
     return {"value": B / (ms * 1e-3), "unit": "traj-control-steps/s", "ms_per_step": ms, "policy_ms_per_step": p0.elapsed_time(p1) / steps,
-            "policy": "direct_DQN %d-512-512-256-%d, factorised noisy layers, fp32 FMA kernels" % (sim.K, params["n_levels"]),
+            "policy": "direct_DQN %d-512-512-256-%d, factorised noisy layers; 512-wide layers as 3xTF32 on tcgen05 tensor cores, rest fp32 FMA" % (sim.K, params["n_levels"]),
             "policy_launches_per_step": (pol.launch_count() - l0) / (warmup + 2 * steps) + 1, "experience_rows": ring.total(),
             "note": "no L2 flush; device-resident loop, no host synchronisation inside the timed region"}
 
