@@ -276,7 +276,7 @@ def main():
         torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
         if ok.item() < 1:
             if fused is not None:
-                fused.close()
+                fused.close(collective=False)       # never used: no barriers (the failing ranks have nothing to close)
             fused = None
         gather_mode = "fused" if fused is not None else "nccl (fused unavailable)"
 

@@ -85,19 +85,35 @@ class FusedGather:
         self.sim, self.rank, self.world, self.lib = sim, int(rank), int(world), L.load()
         self.cols, self.rows = sim.K + L.QC_AUX_COUNT + 1, self.world * sim.B
         self._C, self._L = C, L
-        self.gather_ptr, self.gather_handle = self._alloc(2 * self.rows * self.cols * 8)
-        self.flag_ptr, self.flag_handle = self._alloc(max(self.world, 1) * 8)
         self.peer_g, self.peer_f, self._opened = [None] * self.world, [None] * self.world, []
-        self.peer_g[self.rank], self.peer_f[self.rank] = self.gather_ptr, self.flag_ptr
+        self.gather_ptr = self.flag_ptr = None
+        err = None
+        try:
+            self.gather_ptr, self.gather_handle = self._alloc(2 * self.rows * self.cols * 8)
+            self.flag_ptr, self.flag_handle = self._alloc(max(self.world, 1) * 8)
+            self.peer_g[self.rank], self.peer_f[self.rank] = self.gather_ptr, self.flag_ptr
+        except Exception as e:                      # noqa: BLE001  (still take part in the handle exchange below: it is a collective)
+            err = e
         if _wire:
             if self.world > 1:
                 import torch.distributed as dist
                 handles = [None] * self.world
-                dist.all_gather_object(handles, (self.gather_handle, self.flag_handle))
-                for r, (hg, hf) in enumerate(handles):
-                    if r != self.rank:
-                        self.peer_g[r], self.peer_f[r] = self._open(hg), self._open(hf)
+                dist.all_gather_object(handles, None if err is not None else (self.gather_handle, self.flag_handle))
+                if err is None and any(h is None for h in handles):
+                    err = RuntimeError("a peer rank could not allocate its gather area")
+                if err is None:
+                    try:
+                        for r, (hg, hf) in enumerate(handles):
+                            if r != self.rank:
+                                self.peer_g[r], self.peer_f[r] = self._open(hg), self._open(hf)
+                    except Exception as e:          # noqa: BLE001
+                        err = e
+            if err is not None:
+                self.close(collective=False)
+                raise err
             self._activate()
+        elif err is not None:
+            raise err
 
     def _alloc(self, nbytes):
         C = self._C
@@ -143,20 +159,24 @@ class FusedGather:
         off = (seq & 1) * self.rows * self.cols * 8
         return torch.as_tensor(_DeviceArray(self.gather_ptr + off, (self.rows, self.cols), "<f8"), device="cuda:%d" % self.sim.device)
 
-    def close(self):
+    def close(self, collective=True):
+        """collective=True (normal shutdown after steps ran): every rank must call it, two barriers keep mappings alive until nobody stores
+        into them any more.  collective=False: abort before the exchange was ever used (no barriers)."""
         import torch
         if getattr(self, "sim", None) is None:
             return
         torch.cuda.synchronize(self.sim.device)
-        if self.world > 1 and self._opened:
+        sync = collective and self.world > 1 and bool(self._opened)      # (single-process groups have no IPC mappings)
+        if sync:
             import torch.distributed as dist
             dist.barrier()                           # nobody may still be storing into a mapping that is about to go away
         self.lib.qc_set_gather(self.sim.h, 0, 0, None, None)
         for p in self._opened:
             self.lib.qc_peer_close(self.sim.device, self._C.c_void_p(p))
-        if self.world > 1 and self._opened:
+        if sync:
             import torch.distributed as dist
             dist.barrier()
-        self.lib.qc_peer_free(self.sim.device, self._C.c_void_p(self.gather_ptr))
-        self.lib.qc_peer_free(self.sim.device, self._C.c_void_p(self.flag_ptr))
+        for ptr in (self.gather_ptr, self.flag_ptr):
+            if ptr:
+                self.lib.qc_peer_free(self.sim.device, self._C.c_void_p(ptr))
         self.sim = None
