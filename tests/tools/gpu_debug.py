@@ -1,7 +1,7 @@
 """Development aid: run every task through the CUDA path for several launch geometries and print errors vs the oracle."""
 import os, sys, time, traceback
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from common import TASKS, oracle_for, initial_states, oracle_control_step, fock_observation

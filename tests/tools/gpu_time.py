@@ -1,7 +1,7 @@
 """Development aid: time the control-step kernel for a task over launch geometries (CUDA events)."""
 import os, sys, itertools
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from common import initial_states, oracle_for, oracle_control_step

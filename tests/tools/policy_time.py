@@ -1,7 +1,7 @@
 """Times the device-resident policy step (obs -> direct_DQN -> epsilon-greedy) for a batch; CUDA events, L2 not flushed (weights are meant to stay L2-resident)."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 from deepreinforcementlearningcontrolofquantumcartpoles_b200 import rollout as R

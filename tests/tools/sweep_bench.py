@@ -3,7 +3,7 @@ For every N the resident kernel supports: throughput (CUDA events), algorithmic 
 against the CPU oracle on a small batch.  Writes one JSON line per N."""
 import json, os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from common import initial_states, oracle_for, oracle_control_step

@@ -1,7 +1,7 @@
 """Accuracy/speed of the truncated implicit solve as a function of the decay tolerance (QCART_SOLVE_TOL, read at library load)."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from common import TASKS, oracle_for, initial_states, oracle_control_step
