@@ -2,8 +2,10 @@
 // reference's direct_DQN policy on the whole batch, epsilon-greedy action selection, the experience-row ring and the measurement record.
 //
 // The policy is GEMM-shaped but small (0.55 MFMA per trajectory, 2-8 % of the SSE step's time) and the reference evaluates it in fp32
-// (torch modules, no TF32), so it runs as fp32 FMA on the CUDA cores: a 64x64x16 register-tiled kernel with an in-CTA split over K per hidden layer
-// and a warp-per-trajectory kernel (lane = action) for the n_actions-wide output layer + argmax.  A noisy layer
+// (torch modules, no TF32); argmax decides the action, so fp32-level accuracy is part of parity.  The two 512-wide layers run on the
+// tcgen05 tensor cores as 3xTF32 products with the accumulators in tensor memory (gemm_umma_kernel); the same GEMM as fp32 FMA on the CUDA
+// cores (gemm_splitk_kernel, 64x64x16 register tiles with an in-CTA split over K) is kept as the cross-check; the small input layer and the
+// n_actions-wide output layer + argmax (warp per trajectory, lane = action) are fp32 FMA.  A noisy layer
 // (layers.py:42-57, per-sample noise) is evaluated WITHOUT materialising the per-sample weight matrix w = u_w + sigma_w * (e_out e_in^T):
 //     y = x u_w^T + u_b + e_out * ((x * e_in) sigma_w^T + sigma_b)
 // i.e. two GEMMs over the same inputs (blockIdx.z) whose halves are combined where the next layer loads its input.
