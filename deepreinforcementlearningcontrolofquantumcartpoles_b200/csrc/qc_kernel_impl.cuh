@@ -180,91 +180,77 @@ __device__ __forceinline__ void solve_traj(const StepParams& p, double2* __restr
     const int col0 = lane * mult;
     const bool act = lane < p.P;
     double nrm = 0.0, sx = 0.0, cen = 0.0;
-    // Both substitutions run in "scatter" form: as soon as an unknown is final its contribution is subtracted from the (at most BA) rows
-    // that still wait for it, so the loop-carried dependency per row is ONE complex multiply-add (two dependent DFMAs) and the updates of the
-    // other BA-1 pending rows fill the latency.  (The earlier gather form -- one 2 BA-deep FMA chain per row -- ran at ~160 cycles per row
-    // for the single solver warp: 46 % of an inverted-quartic substep, profiles/README.md.)  The forward sweep accumulates each row in exactly
-    // the order of the gather form (oldest history first), so y is bit-identical to it.
-    // A Slot is what one step needs; loads run PF steps ahead of the arithmetic through a small register ring (explicit software
-    // pipelining: with one or two warps per scheduler nothing else hides the shared-memory latency of this serial loop).
-    struct Slot { double2 v; double2 cf[BA]; double2 e; };
+    // Row = what one recurrence step needs: the vector entry and the factor row of its point.  Loads run PF steps ahead of the
+    // arithmetic through a small register ring (explicit software pipelining: with one or two warps per scheduler nothing else hides
+    // the shared-memory latency of this serial loop).
+    struct Row { double2 v; double2 cf[BA + 2]; };
     constexpr int PF = (L % 3 == 0) ? 2 : 0, NR = PF + 1;
-    auto entry = [&](int col, int j, int k) -> double2 {            // k-th entry of the factor row of point (col, j): l_1..l_BA, 1/d, [xl]
+    auto load_row = [&](Row& r, const double2* __restrict__ buf, int col, int j, bool bwd) {
         const int tc = min(max(col, 0), G - 1);
-        if (k == BA + 1) return TABS ? tab[(j * CS + BA + 1) * G + tc] : mk2(__ldg(&p.x[min(tc * L + j, n - 1)]), 0.0);
-        return TABS ? tab[(j * CS + k) * G + tc] : __ldg(&fac[(size_t)(tc * L + j) * (BA + 1) + k]);
-    };
-    // forward slot of row i = (col, j): rhs of row i+BA (enters the window), l_{i+1+m, m} for the BA rows that wait for y_i, 1/d_i
-    auto load_fwd = [&](Slot& s, int col, int j) {
-        { const int t = j + BA; s.v = U[(t % L) * Gp + GUARD + col + t / L]; }
+        r.v = buf[j * Gp + GUARD + col];
 #pragma unroll
-        for (int m = 0; m < BA; m++) { const int t = j + 1 + m; s.cf[m] = entry(col + t / L, t % L, m); }
-        s.e = entry(col, j, BA);
-    };
-    // backward slot of row i = (col, j): z of row i-BA (enters the window), row i of L (its entries update rows i-1..i-BA), [xl_i]
-    auto load_bwd = [&](Slot& s, int col, int j) {
-        { const int t = j - BA + 8 * L; s.v = V[(t % L) * Gp + GUARD + col + t / L - 8]; }
-#pragma unroll
-        for (int m = 0; m < BA; m++) s.cf[m] = entry(col, j, m);
-        if (VAR != QC_QUARTIC) s.e = entry(col, j, BA + 1);
+        for (int k = 0; k <= BA; k++) {
+            if (bwd && k == BA) { if (VAR != QC_QUARTIC) r.cf[BA] = TABS ? tab[(j * CS + BA + 1) * G + tc] : mk2(__ldg(&p.x[min(tc * L + j, n - 1)]), 0.0); }
+            else r.cf[k] = TABS ? tab[(j * CS + k) * G + tc] : __ldg(&fac[(size_t)(tc * L + j) * (BA + 1) + k]);
+        }
     };
     if (act) {
         // ---- forward: L y = rhs, z = D^{-1} y --------------------------------------------------------------
+        double2 y[BA];
+#pragma unroll
+        for (int k = 0; k < BA; k++) y[k] = mk2(0.0, 0.0);
+        Row ring[NR];
         int col = col0 - wb;
-        double2 acc[BA];                               // acc[m]: row i+m of the window, rhs minus the history terms applied so far
 #pragma unroll
-        for (int m = 0; m < BA; m++) acc[m] = U[(m % L) * Gp + GUARD + col + m / L];
-        Slot ring[NR];
-#pragma unroll
-        for (int q = 0; q < PF; q++) load_fwd(ring[q], col + q / L, q % L);
+        for (int q = 0; q < PF; q++) load_row(ring[q], U, col, q, false);
         for (int b = 0; b < wb + mult; b++, col++) {
             const bool own = b >= wb;
             double2* __restrict__ vb = V + GUARD + col;
 #pragma unroll
             for (int j = 0; j < L; j++) {
-                load_fwd(ring[(j + PF) % NR], col + (j + PF) / L, (j + PF) % L);
-                const Slot& s = ring[j % NR];
-                const double2 y = acc[0];
+                if (j + PF < L) load_row(ring[(j + PF) % NR], U, col, j + PF, false);
+                else load_row(ring[(j + PF) % NR], U, col + 1, j + PF - L, false);        // next column (guard / clamped past the end)
+                const Row& r = ring[j % NR];
+                double re = r.v.x, im = r.v.y;
 #pragma unroll
-                for (int m = 0; m + 1 < BA; m++) acc[m] = acc[m + 1];
-                acc[BA - 1] = s.v;
-#pragma unroll
-                for (int m = 0; m < BA; m++) {         // m = 0 first: it closes the loop-carried dependency
-                    acc[m].x = fma(-s.cf[m].x, y.x, acc[m].x); acc[m].x = fma(s.cf[m].y, y.y, acc[m].x);
-                    acc[m].y = fma(-s.cf[m].x, y.y, acc[m].y); acc[m].y = fma(-s.cf[m].y, y.x, acc[m].y);
+                for (int k = BA - 1; k >= 0; k--) {   // far history first: the newest value (k = 0) closes the dependency chain
+                    re = fma(-r.cf[k].x, y[k].x, re); re = fma(r.cf[k].y, y[k].y, re);
+                    im = fma(-r.cf[k].x, y[k].y, im); im = fma(-r.cf[k].y, y[k].x, im);
                 }
-                if (own) vb[j * Gp] = mk2(y.x * s.e.x - y.y * s.e.y, y.x * s.e.y + y.y * s.e.x);
+#pragma unroll
+                for (int k = BA - 1; k > 0; k--) y[k] = y[k - 1];
+                y[0] = mk2(re, im);
+                if (own) vb[j * Gp] = mk2(re * r.cf[BA].x - im * r.cf[BA].y, re * r.cf[BA].y + im * r.cf[BA].x);
             }
         }
     }
     __syncwarp();
     if (act) {
-        // ---- backward: L^T x = z (row i of L again: x_i updates the BA rows before it) ---------------------------
-        int col = col0 + mult + wb - 1;
-        double2 q[BA];                                 // q[m]: row i-m of the window, z minus the updates applied so far; q[0] is final
+        // ---- backward: L^T x = z, column oriented (row i of L again) ------------------------------------------
+        double2 pend[BA];
 #pragma unroll
-        for (int m = 0; m < BA; m++) { const int t = L - 1 - m + 8 * L; q[m] = V[(t % L) * Gp + GUARD + col + t / L - 8]; }
+        for (int k = 0; k < BA; k++) pend[k] = mk2(0.0, 0.0);
         double2 xprev = mk2(0.0, 0.0);
         const bool do_cen = (VAR == QC_QUARTIC) && (p.cen_hi > p.cen_lo);
-        Slot ring[NR];
+        Row ring[NR];
+        int col = col0 + mult + wb - 1;
 #pragma unroll
-        for (int r = 0; r < PF; r++) { const int t = L - 1 - r + 8 * L; load_bwd(ring[r], col + t / L - 8, t % L); }
+        for (int q = 0; q < PF; q++) load_row(ring[q], V, col, L - 1 - q, true);
         for (int b = 0; b < wb + mult; b++, col--) {
             const bool own = b >= wb;
             double2* __restrict__ ub = U + GUARD + col;
 #pragma unroll
             for (int jr = 0; jr < L; jr++) {          // jr-th step of the column, point j = L-1-jr
                 const int j = L - 1 - jr;
-                { const int t = j - PF + 8 * L; load_bwd(ring[(jr + PF) % NR], col + t / L - 8, t % L); }
-                const Slot& s = ring[jr % NR];
-                const double xr = q[0].x, xi = q[0].y;
+                if (jr + PF < L) load_row(ring[(jr + PF) % NR], V, col, L - 1 - (jr + PF), true);
+                else load_row(ring[(jr + PF) % NR], V, col - 1, L - 1 - (jr + PF - L), true);
+                const Row& r = ring[jr % NR];
+                const double xr = r.v.x + pend[0].x, xi = r.v.y + pend[0].y;
 #pragma unroll
-                for (int m = 0; m + 1 < BA; m++) q[m] = q[m + 1];
-                q[BA - 1] = s.v;
-#pragma unroll
-                for (int m = 0; m < BA; m++) {
-                    q[m].x = fma(-xr, s.cf[m].x, fma(xi, s.cf[m].y, q[m].x));
-                    q[m].y = fma(-xr, s.cf[m].y, fma(-xi, s.cf[m].x, q[m].y));
+                for (int k = 0; k < BA; k++) {
+                    const double pr = (k + 1 < BA) ? pend[k + 1].x : 0.0, pi = (k + 1 < BA) ? pend[k + 1].y : 0.0;
+                    pend[k].x = fma(-xr, r.cf[k].x, fma(xi, r.cf[k].y, pr));
+                    pend[k].y = fma(-xr, r.cf[k].y, fma(-xi, r.cf[k].x, pi));
                 }
                 if (own) {
                     ub[j * Gp] = mk2(xr, xi);
@@ -275,7 +261,7 @@ __device__ __forceinline__ void solve_traj(const StepParams& p, double2* __restr
                         sx = fma(p.h * (double)(i - p.half), a2, sx);
                         if (do_cen && i >= p.cen_lo && i < p.cen_hi) cen += a2;
                     } else {
-                        sx = fma(2.0 * s.e.x, xr * xprev.x + xi * xprev.y, sx);     // 2 xl_i Re(conj(x_i) x_{i+1})
+                        sx = fma(2.0 * r.cf[BA].x, xr * xprev.x + xi * xprev.y, sx);     // 2 xl_i Re(conj(x_i) x_{i+1})
                     }
                 }
                 xprev = mk2(xr, xi);
@@ -710,7 +696,7 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
                 // All per-point factors below are quadratics in x_j whose coefficients depend only on per-substep scalars: evaluate them as
                 // c0 + c1 x + c2 x^2 (2 FMA) instead of rebuilding (x - <x>) powers per point.
                 // (Only where registers allow: the 168-register instances keep the difference form, which has fewer live scalars.)
-                constexpr bool POLY = (MAXT <= 256);
+                constexpr bool POLY = (MAXT <= 256) || (MAXT >= 1024);     // (the 64-register big-grid instances spill either way and prefer fewer FLOPs)
                 const double Q0 = g4 * xbar * xbar, Q1 = -2.0 * g4 * xbar, G0 = -gs * xbar;
                 double m[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
