@@ -299,7 +299,7 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
     p.fac = s->d_fac; p.slot_force = s->d_slot_force; p.slot = slot_dev; p.n_slots = s->n_slots; p.herm_tab = s->d_herm;
     p.psi = b.psi; p.noise = noise; p.seed = s->seed; p.traj_offset = s->traj_offset; p.step_count = b.step; p.nsub_traj = nsub_traj;
     p.moments = moments; p.aux = aux; p.flags_out = flags; p.flags_latch = b.flags; p.q_out = q_out; p.xmean_out = xmean_out;
-    p.moments_only = moments_only; p.jacobi = pl.jacobi; p.herm_smem = pl.herm_smem;
+    p.moments_only = moments_only; p.jacobi = pl.jacobi; p.xfer = pl.xfer; p.herm_smem = pl.herm_smem;
     if (s->g_world > 0 && &b == &s->batch && !moments_only) {          // fused result exchange: rows + sequence flag to every rank
         if (!moments || !aux || !flags) return fail(QC_ERR_ARG, "qc_set_gather is active: qc_step needs moments, aux and flags buffers");
         if (nsub_traj) return fail(QC_ERR_ARG, "qc_set_gather is active: per-trajectory substep budgets are not exchanged");

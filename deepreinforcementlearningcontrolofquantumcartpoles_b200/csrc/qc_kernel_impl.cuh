@@ -295,10 +295,106 @@ __device__ __forceinline__ void solve_traj(const StepParams& p, double2* __restr
 // warm-up formulation above with W = (K-1) L -- but shared memory is touched only for the 5 L factor-row loads and the L result stores,
 // instead of ~11 L (K) loads: the shared-memory pipe, not the FP64 pipe, was the bound of the warm-up version (profiles/README.md).
 // rhs comes in registers (psi~ never goes through shared memory); returns the normalisation scale and <x> in registers.
+// One forward pass over the lane's own L rows: y = rhs - (history terms), given the BA incoming values h[m] = y_{-1-m} of the previous lane(s).
+// Scatter form inside the chunk: as soon as an unknown is final, its contributions to the (at most BA) later rows are subtracted from their
+// accumulators -- 2 BA independent two-FMA chains per step.  With in-order issue and one or two warps per scheduler this matters: the gather
+// form (one 2 BA-deep dependent chain per step) ran 3x slower (profiles/README.md).
+template <int L, int BA>
+__device__ __forceinline__ void jac_forward(const double2 (&rhs)[L], const double2 (&h)[BA], const double2 (&lr)[L][BA], double2 (&y)[L]) {
+    double2 acc[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) acc[j] = rhs[j];
+#pragma unroll
+    for (int j = 0; j < L && j < BA; j++) {                         // boundary gather: rows that still see the incoming history
+        double pr[BA], pi[BA];                                      // independent complex products, then a short sum (not one long chain)
+#pragma unroll
+        for (int k = j; k < BA; k++) {
+            pr[k] = fma(lr[j][k].y, h[k - j].y, -lr[j][k].x * h[k - j].x);
+            pi[k] = fma(-lr[j][k].y, h[k - j].x, -lr[j][k].x * h[k - j].y);
+        }
+        double sr = 0.0, si = 0.0;
+#pragma unroll
+        for (int k = j + 1; k < BA; k++) { sr += pr[k]; si += pi[k]; }           // far terms (available early)
+        acc[j].x += sr + pr[j]; acc[j].y += si + pi[j];
+    }
+#pragma unroll
+    for (int j = 0; j < L; j++) {                                   // in-chunk scatter
+        y[j] = acc[j];
+#pragma unroll
+        for (int k = 0; k < BA; k++) {
+            const int t = j + 1 + k;
+            if (t < L) {
+                acc[t].x = fma(-lr[t][k].x, y[j].x, acc[t].x); acc[t].x = fma(lr[t][k].y, y[j].y, acc[t].x);
+                acc[t].y = fma(-lr[t][k].x, y[j].y, acc[t].y); acc[t].y = fma(-lr[t][k].y, y[j].x, acc[t].y);
+            }
+        }
+    }
+}
+// outgoing history of a forward pass: my last values, then (L < BA) the tail of what I received
+template <int L, int BA>
+__device__ __forceinline__ void jac_forward_out(const double2 (&y)[L], const double2 (&h)[BA], double2 (&ho)[BA]) {
+#pragma unroll
+    for (int m = 0; m < BA; m++) ho[m] = (m < L) ? y[(m < L) ? L - 1 - m : 0] : h[(m >= L) ? m - L : 0];
+}
+// One backward pass (L^T x = z): pin[m] = pending update of my row L-1-m from the rows behind my chunk; po[m] = pending update of the row
+// (m+1) positions before my first row, handed to the lane in front.
+template <int L, int BA>
+__device__ __forceinline__ void jac_backward(const double2 (&z)[L], const double2 (&pin)[BA], const double2 (&lr)[L][BA], double2 (&x)[L], double2 (&po)[BA]) {
+    double2 acc[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) acc[j] = z[j];
+#pragma unroll
+    for (int m = 0; m < BA; m++) {
+        if (m < L) { acc[(m < L) ? L - 1 - m : 0].x += pin[m].x; acc[(m < L) ? L - 1 - m : 0].y += pin[m].y; }
+        po[m] = (m + L < BA) ? pin[(m + L < BA) ? m + L : 0] : mk2(0.0, 0.0);      // (L < BA) updates that only pass through my chunk
+    }
+#pragma unroll
+    for (int j = L - 1; j >= 0; j--) {
+        x[j] = acc[j];
+#pragma unroll
+        for (int k = 0; k < BA; k++) {
+            const int t = j - 1 - k;
+            if (t >= 0) {
+                acc[t].x = fma(-x[j].x, lr[j][k].x, fma(x[j].y, lr[j][k].y, acc[t].x));
+                acc[t].y = fma(-x[j].x, lr[j][k].y, fma(-x[j].y, lr[j][k].x, acc[t].y));
+            } else {
+                po[-t - 1].x = fma(-x[j].x, lr[j][k].x, fma(x[j].y, lr[j][k].y, po[-t - 1].x));
+                po[-t - 1].y = fma(-x[j].x, lr[j][k].y, fma(-x[j].y, lr[j][k].x, po[-t - 1].y));
+            }
+        }
+    }
+}
+
+// Boundary transfer matrices of one lane (interface iteration, see solve_traj_jacobi): T[m][k] = response of the outgoing forward value ho[m]
+// to a unit incoming value h[k]; S[m][k] = response of the outgoing pending update po[m] to a unit incoming pin[k].  They depend on the factor
+// rows only, i.e. on the force slot: computed once per launch and kept in shared memory, xf[((dir * BA + m) * BA + k) * G + g].
+template <int VAR, int L>
+__device__ __forceinline__ void jac_transfer_setup(const double2* __restrict__ tab, double2* __restrict__ xf, int g, int G) {
+    constexpr int BA = SolveTraits<VAR>::BA, CS = SolveTraits<VAR>::CS;
+    double2 lr[L][BA], zero[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) {
+        zero[j] = mk2(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < BA; k++) lr[j][k] = tab[(j * CS + k) * G + g];
+    }
+#pragma unroll
+    for (int k = 0; k < BA; k++) {
+        double2 e[BA], y[L], ho[BA], x[L], po[BA];
+#pragma unroll
+        for (int q = 0; q < BA; q++) e[q] = mk2(q == k ? 1.0 : 0.0, 0.0);
+        jac_forward<L, BA>(zero, e, lr, y);
+        jac_forward_out<L, BA>(y, e, ho);
+        jac_backward<L, BA>(zero, e, lr, x, po);
+#pragma unroll
+        for (int m = 0; m < BA; m++) { xf[((0 * BA + m) * BA + k) * G + g] = ho[m]; xf[((1 * BA + m) * BA + k) * G + g] = po[m]; }
+    }
+}
+
 template <int VAR, int L, bool MULTI>
 __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const double2 (&rhs)[L], double2* __restrict__ U, const double2* __restrict__ tab,
                                                   double2* __restrict__ mbox, double* red, int& red_phase, int* iflag, int g, int G, int Gp, int bar_id,
-                                                  double& sc_out, double& xbar_out) {
+                                                  double& sc_out, double& xbar_out, const double2* __restrict__ xf) {
     constexpr int BA = SolveTraits<VAR>::BA, CS = SolveTraits<VAR>::CS, GUARD = Guard<L>::v;
     const int n = p.n, K = (p.debug & 4) ? 1 : ((p.debug & 8) ? 3 : p.W / L + 1);      // debug bits 4/8: timing experiments only (wrong results)
     const int lane = g & 31, wq = g >> 5, nwarps = G >> 5;
@@ -313,117 +409,132 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
     // shared mailbox + the trajectory's named barrier between warps.  Lane 0 of the trajectory needs no masking in the forward sweep: the
     // factor entries that would multiply a value from before the first point are zero.  The last lane's incoming pending updates are
     // forced to zero (there is no lane behind it).
-    // Both sweeps are written in "scatter" form inside the chunk: as soon as an unknown is final, its contributions to the (at most BA)
-    // later rows are subtracted from their accumulators -- 2 BA independent two-FMA chains per step.  With in-order issue and one or two
-    // warps per scheduler this matters: the gather form (one 2 BA-deep dependent chain per step) ran 3x slower (profiles/README.md).
-    // ---- forward: L y = rhs --------------------------------------------------------------------------------------
-    double2 y[L], h[BA];                                            // h[m] = y_{-1-m}: last values of the previous lane(s)
+    const bool last_lane = (g == G - 1);
+    int xchg = 0;                                                   // mailbox parity (MULTI)
+    auto send_up = [&](const double2 (&ho)[BA], double2 (&h)[BA]) {            // h of lane g+1 <- ho of lane g
+        if constexpr (MULTI) {
+            double2* mb = mbox + (xchg & 1) * (nwarps * BA); xchg++;
+            if (lane == 31) {
 #pragma unroll
-    for (int k = 0; k < BA; k++) h[k] = mk2(0.0, 0.0);
-    for (int it = 0; it < K; it++) {
-        double2 acc[L];
-#pragma unroll
-        for (int j = 0; j < L; j++) acc[j] = rhs[j];
-#pragma unroll
-        for (int j = 0; j < L && j < BA; j++) {                     // boundary gather: rows that still see the incoming history
-            double pr[BA], pi[BA];                                  // independent complex products, then a short sum (not one long chain)
-#pragma unroll
-            for (int k = j; k < BA; k++) {
-                pr[k] = fma(lr[j][k].y, h[k - j].y, -lr[j][k].x * h[k - j].x);
-                pi[k] = fma(-lr[j][k].y, h[k - j].x, -lr[j][k].x * h[k - j].y);
+                for (int k = 0; k < BA; k++) mb[wq * BA + k] = ho[k];
             }
-            double sr = 0.0, si = 0.0;
-#pragma unroll
-            for (int k = j + 1; k < BA; k++) { sr += pr[k]; si += pi[k]; }       // far terms (available early)
-            acc[j].x += sr + pr[j]; acc[j].y += si + pi[j];
-        }
-#pragma unroll
-        for (int j = 0; j < L; j++) {                               // in-chunk scatter
-            y[j] = acc[j];
+            traj_sync<true>(bar_id, G);
 #pragma unroll
             for (int k = 0; k < BA; k++) {
-                const int t = j + 1 + k;
-                if (t < L) {
-                    acc[t].x = fma(-lr[t][k].x, y[j].x, acc[t].x); acc[t].x = fma(lr[t][k].y, y[j].y, acc[t].x);
-                    acc[t].y = fma(-lr[t][k].x, y[j].y, acc[t].y); acc[t].y = fma(-lr[t][k].y, y[j].x, acc[t].y);
-                }
+                const double2 up = (wq > 0) ? mb[(wq - 1) * BA + k] : mk2(0.0, 0.0);
+                const double sx_ = __shfl_up_sync(0xffffffffu, ho[k].x, 1), sy_ = __shfl_up_sync(0xffffffffu, ho[k].y, 1);
+                h[k] = (lane == 0) ? up : mk2(sx_, sy_);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < BA; k++) { h[k].x = __shfl_up_sync(0xffffffffu, ho[k].x, 1); h[k].y = __shfl_up_sync(0xffffffffu, ho[k].y, 1); }
+        }
+    };
+    auto send_down = [&](const double2 (&po)[BA], double2 (&pin)[BA]) {        // pin of lane g-1 <- po of lane g
+        if constexpr (MULTI) {
+            double2* mb = mbox + (xchg & 1) * (nwarps * BA); xchg++;
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < BA; k++) mb[wq * BA + k] = po[k];
+            }
+            traj_sync<true>(bar_id, G);
+#pragma unroll
+            for (int k = 0; k < BA; k++) {
+                const double2 dn = (wq + 1 < nwarps) ? mb[(wq + 1) * BA + k] : mk2(0.0, 0.0);
+                const double sx_ = __shfl_down_sync(0xffffffffu, po[k].x, 1), sy_ = __shfl_down_sync(0xffffffffu, po[k].y, 1);
+                pin[k] = (lane == 31) ? dn : mk2(sx_, sy_);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < BA; k++) {
+                const double sx_ = __shfl_down_sync(0xffffffffu, po[k].x, 1), sy_ = __shfl_down_sync(0xffffffffu, po[k].y, 1);
+                pin[k] = last_lane ? mk2(0.0, 0.0) : mk2(sx_, sy_);
             }
         }
-        if (it + 1 < K) {
-            double2 ho[BA];                                          // outgoing history: my last values, then (L < BA) the tail of what I received
+    };
+    // Interface iteration (xf != nullptr): both sweeps are affine in the incoming boundary values, ho = ho0 + T h and po = po0 + S pin, so the
+    // K - 2 middle passes of the block-Jacobi iteration only have to update the BA boundary values (a BA x BA complex mat-vec per lane) instead
+    // of the whole chunk; the first pass (zero history) gives ho0 / po0 and the last pass is a full one with the converged boundary values.
+    // In exact arithmetic this IS the K-pass iteration; it saves (K - 2) (L BA - BA^2) complex multiply-adds per sweep.
+    // Compiled for the Fock systems only (BA <= 2: the BA x BA matrices cost 4-16 registers); on the grid (BA = 4) they would take 64 registers
+    // from a kernel that is already register bound.
+    constexpr bool XF_OK = (BA <= 2);
+    const bool iface = XF_OK && (xf != nullptr) && K > 2;
+    // ---- forward: L y = rhs --------------------------------------------------------------------------------------
+    double2 y[L], h[BA], ho[BA];                                    // h[m] = y_{-1-m}: last values of the previous lane(s)
 #pragma unroll
-            for (int m = 0; m < BA; m++) ho[m] = (m < L) ? y[(m < L) ? L - 1 - m : 0] : h[(m >= L) ? m - L : 0];
-            if constexpr (MULTI) {
-                double2* mb = mbox + (it & 1) * (nwarps * BA);
-                if (lane == 31) {
+    for (int k = 0; k < BA; k++) h[k] = mk2(0.0, 0.0);
+    bool fwd_done = false;
+    if constexpr (XF_OK) { if (iface) {
+        fwd_done = true;
+        double2 T[BA][BA], ho0[BA];
 #pragma unroll
-                    for (int k = 0; k < BA; k++) mb[wq * BA + k] = ho[k];
-                }
-                traj_sync<true>(bar_id, G);
+        for (int m = 0; m < BA; m++)
+#pragma unroll
+            for (int k = 0; k < BA; k++) T[m][k] = xf[((0 * BA + m) * BA + k) * G + g];
+        jac_forward<L, BA>(rhs, h, lr, y);
+        jac_forward_out<L, BA>(y, h, ho0);
+#pragma unroll
+        for (int m = 0; m < BA; m++) ho[m] = ho0[m];
+        for (int it = 0; it < K - 2; it++) {
+            send_up(ho, h);
+#pragma unroll
+            for (int m = 0; m < BA; m++) {
+                double re = ho0[m].x, im = ho0[m].y;
 #pragma unroll
                 for (int k = 0; k < BA; k++) {
-                    const double2 up = (wq > 0) ? mb[(wq - 1) * BA + k] : mk2(0.0, 0.0);
-                    const double sx_ = __shfl_up_sync(0xffffffffu, ho[k].x, 1), sy_ = __shfl_up_sync(0xffffffffu, ho[k].y, 1);
-                    h[k] = (lane == 0) ? up : mk2(sx_, sy_);
+                    re = fma(T[m][k].x, h[k].x, re); re = fma(-T[m][k].y, h[k].y, re);
+                    im = fma(T[m][k].x, h[k].y, im); im = fma(T[m][k].y, h[k].x, im);
                 }
-            } else {
-#pragma unroll
-                for (int k = 0; k < BA; k++) { h[k].x = __shfl_up_sync(0xffffffffu, ho[k].x, 1); h[k].y = __shfl_up_sync(0xffffffffu, ho[k].y, 1); }
+                ho[m] = mk2(re, im);
             }
+        }
+        send_up(ho, h);
+        jac_forward<L, BA>(rhs, h, lr, y);
+    } }
+    if (!fwd_done) {
+        for (int it = 0; it < K; it++) {
+            jac_forward<L, BA>(rhs, h, lr, y);
+            if (it + 1 < K) { jac_forward_out<L, BA>(y, h, ho); send_up(ho, h); }
         }
     }
     // ---- z = D^{-1} y, backward: L^T x = z -----------------------------------------------------------------------------
-    double2 z[L], x[L], pin[BA];                                     // pin[m] = pending update of my row L-1-m from the rows behind my chunk
+    double2 z[L], x[L], pin[BA], po[BA];
 #pragma unroll
     for (int j = 0; j < L; j++) z[j] = mk2(y[j].x * dinv[j].x - y[j].y * dinv[j].y, y[j].x * dinv[j].y + y[j].y * dinv[j].x);
 #pragma unroll
     for (int k = 0; k < BA; k++) pin[k] = mk2(0.0, 0.0);
-    const bool last_lane = (g == G - 1);
-    for (int it = 0; it < K; it++) {
-        double2 acc[L], po[BA];                                      // po[m] = pending update of the row (m+1) positions before my first row
+    bool bwd_done = false;
+    if constexpr (XF_OK) { if (iface) {
+        bwd_done = true;
+        double2 S[BA][BA], po0[BA];
 #pragma unroll
-        for (int j = 0; j < L; j++) acc[j] = z[j];
+        for (int m = 0; m < BA; m++)
 #pragma unroll
-        for (int m = 0; m < BA; m++) {
-            if (m < L) { acc[(m < L) ? L - 1 - m : 0].x += pin[m].x; acc[(m < L) ? L - 1 - m : 0].y += pin[m].y; }
-            po[m] = (m + L < BA) ? pin[(m + L < BA) ? m + L : 0] : mk2(0.0, 0.0);      // (L < BA) updates that only pass through my chunk
-        }
+            for (int k = 0; k < BA; k++) S[m][k] = xf[((1 * BA + m) * BA + k) * G + g];
+        jac_backward<L, BA>(z, pin, lr, x, po0);
 #pragma unroll
-        for (int j = L - 1; j >= 0; j--) {
-            x[j] = acc[j];
+        for (int m = 0; m < BA; m++) po[m] = po0[m];
+        for (int it = 0; it < K - 2; it++) {
+            send_down(po, pin);
 #pragma unroll
-            for (int k = 0; k < BA; k++) {
-                const int t = j - 1 - k;
-                if (t >= 0) {
-                    acc[t].x = fma(-x[j].x, lr[j][k].x, fma(x[j].y, lr[j][k].y, acc[t].x));
-                    acc[t].y = fma(-x[j].x, lr[j][k].y, fma(-x[j].y, lr[j][k].x, acc[t].y));
-                } else {
-                    po[-t - 1].x = fma(-x[j].x, lr[j][k].x, fma(x[j].y, lr[j][k].y, po[-t - 1].x));
-                    po[-t - 1].y = fma(-x[j].x, lr[j][k].y, fma(-x[j].y, lr[j][k].x, po[-t - 1].y));
-                }
-            }
-        }
-        if (it + 1 < K) {
-            if constexpr (MULTI) {
-                double2* mb = mbox + (it & 1) * (nwarps * BA);
-                if (lane == 0) {
-#pragma unroll
-                    for (int k = 0; k < BA; k++) mb[wq * BA + k] = po[k];
-                }
-                traj_sync<true>(bar_id, G);
+            for (int m = 0; m < BA; m++) {
+                double re = po0[m].x, im = po0[m].y;
 #pragma unroll
                 for (int k = 0; k < BA; k++) {
-                    const double2 dn = (wq + 1 < nwarps) ? mb[(wq + 1) * BA + k] : mk2(0.0, 0.0);
-                    const double sx_ = __shfl_down_sync(0xffffffffu, po[k].x, 1), sy_ = __shfl_down_sync(0xffffffffu, po[k].y, 1);
-                    pin[k] = (lane == 31) ? dn : mk2(sx_, sy_);
+                    re = fma(S[m][k].x, pin[k].x, re); re = fma(-S[m][k].y, pin[k].y, re);
+                    im = fma(S[m][k].x, pin[k].y, im); im = fma(S[m][k].y, pin[k].x, im);
                 }
-            } else {
-#pragma unroll
-                for (int k = 0; k < BA; k++) {
-                    const double sx_ = __shfl_down_sync(0xffffffffu, po[k].x, 1), sy_ = __shfl_down_sync(0xffffffffu, po[k].y, 1);
-                    pin[k] = last_lane ? mk2(0.0, 0.0) : mk2(sx_, sy_);
-                }
+                po[m] = mk2(re, im);
             }
+        }
+        send_down(po, pin);
+        jac_backward<L, BA>(z, pin, lr, x, po);
+    } }
+    if (!bwd_done) {
+        for (int it = 0; it < K; it++) {
+            jac_backward<L, BA>(z, pin, lr, x, po);
+            if (it + 1 < K) send_down(po, pin);
         }
     }
     // ---- result -> shared line (halos of the next substep), norm, <x>, escape probability, Fail -----------------------------
@@ -646,6 +757,15 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
         }
     }
     traj_sync<MULTI>(bar_id, G);
+    // chunk-Jacobi interface iteration: boundary transfer matrices of this lane, once per launch (each lane writes and reads only its own entries)
+    const double2* xf = nullptr;
+    if constexpr (TABS && SolveTraits<VAR>::BA <= 2) {
+        if (p.xfer && p.jacobi) {
+            double2* xfw = reinterpret_cast<double2*>(nz + 2 * p.n_sub);
+            jac_transfer_setup<VAR, L>(tab, xfw, g, G);
+            xf = xfw;
+        }
+    }
 
     double sc = 1.0, xbar;
     {
@@ -892,7 +1012,7 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
                 for (int j = 0; j < L; j++) rhs[j] = valid[j] ? mk2(acc[j].x + hw[j].x, acc[j].y + hw[j].y) : mk2(0.0, 0.0);
                 // Fock: the last sweep published w0 in U and its halo readers must be done before the solver overwrites U
                 if constexpr (VAR != QC_QUARTIC) traj_sync<MULTI>(bar_id, G);
-                if (!(p.debug & 1)) solve_traj_jacobi<VAR, L, MULTI>(p, rhs, U, tab, mbox, red, red_phase, iflag, g, G, Gp, bar_id, sc, xbar);
+                if (!(p.debug & 1)) solve_traj_jacobi<VAR, L, MULTI>(p, rhs, U, tab, mbox, red, red_phase, iflag, g, G, Gp, bar_id, sc, xbar, xf);
             } else {
                 // For the grid b0 == V so U's last readers (sweep 4) are behind a barrier; for Fock b0 == U: its halo readers must finish first.
                 if constexpr (VAR != QC_QUARTIC) traj_sync<MULTI>(bar_id, G);

@@ -109,7 +109,12 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             const bool binned = tabs && (want_bin == 1 || (want_bin < 0 && B >= 8 * n_sm && B >= 64 * m.cfg.n_levels));
             const bool herm_smem = binned && var == QC_INV_HARMONIC && m.cfg.herm_mode != 2;     // 17 KB band table: only worth it when shared by a CTA
             const int tab_bytes = CS * L * G * 16 + (herm_smem ? 11 * L * G * 8 : 0);
-            int tstride = nbuf * L * Gp * 16 + (tabs ? tab_bytes : 0) + n_sub * 16 + 2 * QC_MAXRED * (G / 32) * 8 + 2 * (G / 32) * 4 * 16 + 128;
+            // interface iteration of the chunk-Jacobi solve: 2 BA^2 complex per lane after the noise block.  Default for the Fock systems
+            // (BA <= 2: 1-4 KB per trajectory; QCART_XFER=0 switches it off); on the grid (BA = 4) the 4x4 matrices would cost 64 registers.
+            const int BAv = (var == QC_QUARTIC) ? 4 : (var == QC_HARMONIC ? 1 : 2);
+            const bool want_xfer = tabs && G == 32 && BAv <= 2 && env_int("QCART_XFER", 1);      // (the kernel compiles the path for BA <= 2 only)
+            const int xfer_bytes = want_xfer ? 2 * BAv * BAv * 16 * G : 0;
+            int tstride = nbuf * L * Gp * 16 + (tabs ? tab_bytes : 0) + n_sub * 16 + xfer_bytes + 2 * QC_MAXRED * (G / 32) * 8 + 2 * (G / 32) * 4 * 16 + 128;
             tstride = (tstride + 15) / 16 * 16;
             bool vglobal = false;
             if (!tabs && tstride > smem_max - 1024) {        // largest grids: keep only the first line in shared memory
@@ -138,7 +143,7 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             P = (cols + mult - 1) / mult;
             if (P == 1) { W = 0; mult = cols; }
             if (jac) { P = cols; mult = 1; }
-            plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = mult * L; plan.W = W; plan.jacobi = jac ? 1 : 0;
+            plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = mult * L; plan.W = W; plan.jacobi = jac ? 1 : 0; plan.xfer = (jac && want_xfer) ? 1 : 0;
             plan.vglobal = vglobal ? 1 : 0; plan.vglobal_elems_per_traj = (long long)(nbuf - 1) * L * Gp;
             plan.binned = binned ? 1 : 0; plan.herm_smem = herm_smem ? 1 : 0; plan.smem_cta_extra = binned ? tab_bytes : 0;
             plan.NP = NP; plan.threads = T * G; plan.tstride = tstride; plan.smem_bytes = T * tstride + plan.smem_cta_extra; plan.gc = ke->gc; plan.maxt = ke->maxt; plan.tabs = tabs != 0;
