@@ -456,8 +456,8 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
     // K - 2 middle passes of the block-Jacobi iteration only have to update the BA boundary values (a BA x BA complex mat-vec per lane) instead
     // of the whole chunk; the first pass (zero history) gives ho0 / po0 and the last pass is a full one with the converged boundary values.
     // In exact arithmetic this IS the K-pass iteration; it saves (K - 2) (L BA - BA^2) complex multiply-adds per sweep.
-    // Compiled for the Fock systems only (BA <= 2: the BA x BA matrices cost 4-16 registers); on the grid (BA = 4) they would take 64 registers
-    // from a kernel that is already register bound.
+    // Compiled for the Fock systems only (BA <= 2).  On the grid (BA = 4) it was measured and does not pay: the 16 + 16 matrix entries per
+    // iteration come from shared memory and the mat-vec has little ILP (config 2: 0.567 vs 0.564 ms, 8192 trajectories: 3.94 vs 3.87 ms).
     constexpr bool XF_OK = (BA <= 2);
     const bool iface = XF_OK && (xf != nullptr) && K > 2;
     // ---- forward: L y = rhs --------------------------------------------------------------------------------------
@@ -467,11 +467,7 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
     bool fwd_done = false;
     if constexpr (XF_OK) { if (iface) {
         fwd_done = true;
-        double2 T[BA][BA], ho0[BA];
-#pragma unroll
-        for (int m = 0; m < BA; m++)
-#pragma unroll
-            for (int k = 0; k < BA; k++) T[m][k] = xf[((0 * BA + m) * BA + k) * G + g];
+        double2 ho0[BA];
         jac_forward<L, BA>(rhs, h, lr, y);
         jac_forward_out<L, BA>(y, h, ho0);
 #pragma unroll
@@ -483,8 +479,9 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
                 double re = ho0[m].x, im = ho0[m].y;
 #pragma unroll
                 for (int k = 0; k < BA; k++) {
-                    re = fma(T[m][k].x, h[k].x, re); re = fma(-T[m][k].y, h[k].y, re);
-                    im = fma(T[m][k].x, h[k].y, im); im = fma(T[m][k].y, h[k].x, im);
+                    const double2 tv = xf[((0 * BA + m) * BA + k) * G + g];
+                    re = fma(tv.x, h[k].x, re); re = fma(-tv.y, h[k].y, re);
+                    im = fma(tv.x, h[k].y, im); im = fma(tv.y, h[k].x, im);
                 }
                 ho[m] = mk2(re, im);
             }
@@ -507,11 +504,7 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
     bool bwd_done = false;
     if constexpr (XF_OK) { if (iface) {
         bwd_done = true;
-        double2 S[BA][BA], po0[BA];
-#pragma unroll
-        for (int m = 0; m < BA; m++)
-#pragma unroll
-            for (int k = 0; k < BA; k++) S[m][k] = xf[((1 * BA + m) * BA + k) * G + g];
+        double2 po0[BA];
         jac_backward<L, BA>(z, pin, lr, x, po0);
 #pragma unroll
         for (int m = 0; m < BA; m++) po[m] = po0[m];
@@ -522,8 +515,9 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
                 double re = po0[m].x, im = po0[m].y;
 #pragma unroll
                 for (int k = 0; k < BA; k++) {
-                    re = fma(S[m][k].x, pin[k].x, re); re = fma(-S[m][k].y, pin[k].y, re);
-                    im = fma(S[m][k].x, pin[k].y, im); im = fma(S[m][k].y, pin[k].x, im);
+                    const double2 sv = xf[((1 * BA + m) * BA + k) * G + g];
+                    re = fma(sv.x, pin[k].x, re); re = fma(-sv.y, pin[k].y, re);
+                    im = fma(sv.x, pin[k].y, im); im = fma(sv.y, pin[k].x, im);
                 }
                 po[m] = mk2(re, im);
             }
@@ -638,7 +632,8 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     // factor table [L][CS][G] complex (+ inverted harmonic: band of Im C, [L][11][G] real, for the HERMITIAN-descriptor term)
     constexpr int HT = (VAR == QC_INV_HARMONIC) ? 11 : 0;
     const size_t tab_bytes = (size_t)CS_ * L * G * sizeof(double2) + (p.herm_smem ? (size_t)HT * L * G * sizeof(double) : 0);
-    unsigned char* base = smem + (p.shared_tab ? tab_bytes : 0) + (size_t)t * p.tstride;
+    const size_t xf_cta_bytes = (p.shared_tab && p.xfer) ? (size_t)2 * SolveTraits<VAR>::BA * SolveTraits<VAR>::BA * G * sizeof(double2) : 0;
+    unsigned char* base = smem + (p.shared_tab ? tab_bytes + xf_cta_bytes : 0) + (size_t)t * p.tstride;
     double2* U = reinterpret_cast<double2*>(base);
     // Largest grids (two lines no longer fit 227 KB): the second line lives in global memory (p.vglobal, L2 resident); bar.sync orders it.
     // Compile-time gated (generic-width, table-less instances only) so that every other instance keeps pure shared-memory addressing.
@@ -757,13 +752,22 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
         }
     }
     traj_sync<MULTI>(bar_id, G);
-    // chunk-Jacobi interface iteration: boundary transfer matrices of this lane, once per launch (each lane writes and reads only its own entries)
+    // chunk-Jacobi interface iteration: boundary transfer matrices of this lane, once per launch.  Per trajectory after the noise block
+    // (each lane writes and reads only its own entries), or -- binned launches, where the whole CTA shares one force slot -- once per CTA
+    // behind the shared factor table.
     const double2* xf = nullptr;
     if constexpr (TABS && SolveTraits<VAR>::BA <= 2) {
         if (p.xfer && p.jacobi) {
-            double2* xfw = reinterpret_cast<double2*>(nz + 2 * p.n_sub);
-            jac_transfer_setup<VAR, L>(tab, xfw, g, G);
-            xf = xfw;
+            if (p.shared_tab) {
+                double2* xfw = reinterpret_cast<double2*>(smem + tab_bytes);
+                if (t == 0) jac_transfer_setup<VAR, L>(tab, xfw, g, G);
+                __syncthreads();
+                xf = xfw;
+            } else {
+                double2* xfw = reinterpret_cast<double2*>(nz + 2 * p.n_sub);
+                jac_transfer_setup<VAR, L>(tab, xfw, g, G);
+                xf = xfw;
+            }
         }
     }
 

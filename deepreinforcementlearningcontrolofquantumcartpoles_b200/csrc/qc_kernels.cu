@@ -106,14 +106,19 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             const int NP = G * L;
             // binned mode (large batches): trajectories are grouped by force level, the factor table is staged once per CTA
             const int want_bin = env_int("QCART_BIN", -1);
-            const bool binned = tabs && (want_bin == 1 || (want_bin < 0 && B >= 8 * n_sm && B >= 64 * m.cfg.n_levels));
+            const bool binned_large = tabs && (want_bin == 1 || (want_bin < 0 && B >= 8 * n_sm && B >= 64 * m.cfg.n_levels));
+            const bool small_bin = false;     // (binning one-warp grid batches of a few trajectories per SM with T = 8 fits one wave and is free, but buys nothing: measured)
+            const bool binned = binned_large || small_bin;
             const bool herm_smem = binned && var == QC_INV_HARMONIC && m.cfg.herm_mode != 2;     // 17 KB band table: only worth it when shared by a CTA
-            const int tab_bytes = CS * L * G * 16 + (herm_smem ? 11 * L * G * 8 : 0);
-            // interface iteration of the chunk-Jacobi solve: 2 BA^2 complex per lane after the noise block.  Default for the Fock systems
-            // (BA <= 2: 1-4 KB per trajectory; QCART_XFER=0 switches it off); on the grid (BA = 4) the 4x4 matrices would cost 64 registers.
+            const int tab_only = CS * L * G * 16 + (herm_smem ? 11 * L * G * 8 : 0);
+            // interface iteration of the chunk-Jacobi solve: 2 BA^2 complex per lane.  Per trajectory (after the noise block) for the Fock
+            // systems (BA <= 2: 1-4 KB); per CTA, behind the shared factor table, in binned launches.  QCART_XFER=0: off.  Not for the grid
+            // (BA = 4): measured, no gain (see solve_traj_jacobi).
             const int BAv = (var == QC_QUARTIC) ? 4 : (var == QC_HARMONIC ? 1 : 2);
-            const bool want_xfer = tabs && G == 32 && BAv <= 2 && env_int("QCART_XFER", 1);      // (the kernel compiles the path for BA <= 2 only)
-            const int xfer_bytes = want_xfer ? 2 * BAv * BAv * 16 * G : 0;
+            const bool want_xfer = tabs && G == 32 && BAv <= 2 && env_int("QCART_XFER", 1);
+            const int xfer_all = want_xfer ? 2 * BAv * BAv * 16 * G : 0;
+            const int xfer_bytes = binned ? 0 : xfer_all;                     // per-trajectory part
+            const int tab_bytes = tab_only + (binned ? xfer_all : 0);         // CTA-level prefix when binned (factor table + transfer tables)
             int tstride = nbuf * L * Gp * 16 + (tabs ? tab_bytes : 0) + n_sub * 16 + xfer_bytes + 2 * QC_MAXRED * (G / 32) * 8 + 2 * (G / 32) * 4 * 16 + 128;
             tstride = (tstride + 15) / 16 * 16;
             bool vglobal = false;
@@ -128,7 +133,7 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             Tmax = std::min(Tmax, 15);
             if (Tmax < 1) continue;
             int T = forceT;
-            if (T <= 0) { const int per_sm = (B + n_sm - 1) / n_sm; T = std::max(1, std::min(per_sm, 8)); if (binned && G > 32) T = std::min(Tmax, 4); }   // small batch: one even wave
+            if (T <= 0) { const int per_sm = (B + n_sm - 1) / n_sm; T = std::max(1, std::min(per_sm, 8)); if (binned && G > 32) T = std::min(Tmax, 4); if (small_bin) T = 8; }   // small batch: one even wave
             if (tabs && !binned && Tmax < std::min(T, 2) && forceTabs < 0) continue;     // tables would squeeze the CTA too much: use the global-table variant
             T = std::min(T, Tmax);
             if (binned) { tstride = tstride_b; }
