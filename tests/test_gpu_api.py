@@ -208,3 +208,33 @@ def test_fused_result_exchange_single_process_ranks(task):
         fg.close()
     out = sims[0].step(act)                                     # exchange switched off again: plain step works
     assert torch.isfinite(out["moments"]).all()
+
+
+@pytest.mark.gpu
+def test_edge_cases_empty_ragged_and_oversized():
+    """Empty batch is an argument error; a batch that does not fill its last CTA gives the same per-trajectory results as any other
+    batch size (bitwise, with supplied noise); a grid beyond the resident-kernel limit is reported, not mis-computed."""
+    import torch
+    params = configs.quartic(n_sub=6)
+    empty = BatchedSim(params)
+    with pytest.raises(L.QcartError) as e:
+        empty.set_batch(0)
+    assert e.value.code == L.QC_ERR_ARG
+    rng = np.random.default_rng(2)
+    Bbig = 1031                                                   # prime: ragged against every CTA packing
+    psi0 = initial_states(params, 16, seed=4)
+    psi = np.tile(psi0, (Bbig // 16 + 1, 1))[:Bbig]
+    act = rng.integers(0, params["n_levels"], Bbig).astype(np.int32)
+    noise = rng.standard_normal((Bbig, 6, 2))
+    got = {}
+    for B in (Bbig, 37):
+        sim = BatchedSim(params, batch=B)
+        sim.set_state(psi[:B])
+        sim.step(torch.as_tensor(act[:B], device="cuda"), noise=torch.as_tensor(noise[:B], device="cuda"))
+        got[B] = sim.get_state()
+    assert np.array_equal(got[Bbig][:37], got[37])
+    big = configs.quartic_sweep(9473)                              # 9473 > 9216 points
+    with pytest.raises(L.QcartError) as e:
+        sim = BatchedSim(big, batch=2)
+        sim.step(torch.zeros(2, dtype=torch.int32, device="cuda"))
+    assert e.value.code == L.QC_ERR_UNSUPPORTED
