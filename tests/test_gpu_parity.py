@@ -342,3 +342,27 @@ def test_bad_solve_tol_is_rejected():
     from deepreinforcementlearningcontrolofquantumcartpoles_b200 import QcartError
     with pytest.raises(QcartError):
         BatchedSim(dict(configs.quartic(), solve_tol=1e-3), batch=4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M", [2, 3, 4])
+def test_moment_orders_below_five(M):
+    """MOMENT macro of the reference (Q:325): K = (M+3)M/2 moments in the reference's order; M = 2 is the north-star's 5-moment observation."""
+    params, sim, out, psi_gpu, orc, psi_ref, fails, _ = run_case("quartic", 6, seed=3, n_sub=8, overrides={"moment_order": M})
+    K = (M + 3) * M // 2
+    assert sim.K == K and out["moments"].shape[1] == K
+    assert rel_err(psi_gpu, psi_ref) < TOL_STEP
+    mom = out["moments"].cpu().numpy()
+    for b in range(6):
+        ref = orc.get_moments(psi_ref[b])
+        assert ref.shape == (K,)
+        assert np.max(np.abs(mom[b] - ref) / np.maximum(np.abs(ref), 1e-3)) < TOL_STEP, (b, mom[b], ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [1, 2])
+def test_inverted_harmonic_descriptor_modes(mode):
+    """herm_mode 1 (HERMITIAN descriptor with a real diagonal) and 2 (SYMMETRIC, as harmonic/simulation.cpp:532 does) against the oracle run
+    in the same mode; mode 0 (the literal reading, default) is covered by test_control_step_matches_oracle."""
+    params, sim, out, psi_gpu, orc, psi_ref, fails, _ = run_case("inverted_harmonic", 8, seed=5, n_sub=20, overrides={"herm_mode": mode})
+    assert rel_err(psi_gpu, psi_ref) < TOL_STEP
