@@ -366,3 +366,17 @@ def test_inverted_harmonic_descriptor_modes(mode):
     in the same mode; mode 0 (the literal reading, default) is covered by test_control_step_matches_oracle."""
     params, sim, out, psi_gpu, orc, psi_ref, fails, _ = run_case("inverted_harmonic", 8, seed=5, n_sub=20, overrides={"herm_mode": mode})
     assert rel_err(psi_gpu, psi_ref) < TOL_STEP
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task,overrides", [
+    ("quartic", {"n_levels": 11, "f_max": 3.0, "dt": 1.0 / 720, "gamma": 0.05 * np.pi, "x_max": 6.0, "grid_size": 0.08, "lambda_": 0.1 * np.pi, "mass": 0.7 / np.pi}),
+    ("harmonic", {"n_levels": 5, "f_max": 2.0, "dt": 1.0 / 960, "gamma": 0.3 * np.pi, "n_max": 40, "omega": 0.8 * np.pi}),
+    ("inverted_harmonic", {"n_levels": 9, "f_max": 6.0, "dt": 1.0 / 2000, "gamma": 1.5 * np.pi, "n_max": 100}),
+])
+def test_non_default_physics_and_force_grids(task, overrides):
+    """The library takes at run time what the reference bakes in with -D macros / arguments.py: other grids, masses, couplings, level counts."""
+    params, sim, out, psi_gpu, orc, psi_ref, fails, _ = run_case(task, 7, seed=11, n_sub=12, overrides=overrides)
+    assert rel_err(psi_gpu, psi_ref) < TOL_STEP
+    flags = out["flags"].cpu().numpy()
+    assert np.array_equal((flags & L.QC_FLAG_FAIL) != 0, fails != 0)
