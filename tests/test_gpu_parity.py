@@ -380,3 +380,41 @@ def test_non_default_physics_and_force_grids(task, overrides):
     assert rel_err(psi_gpu, psi_ref) < TOL_STEP
     flags = out["flags"].cpu().numpy()
     assert np.array_equal((flags & L.QC_FLAG_FAIL) != 0, fails != 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task,B", [("inverted_harmonic", 8192), ("inverted_quartic", 8192)])
+def test_full_size_properties_configs_3_and_4(task, B):
+    """BASELINE configs[2] (inverted harmonic, 8192 trajectories) and configs[3] per GPU (inverted quartic, 8192 of 65 536) at full size:
+    bitwise run-to-run determinism, unit norm, finite moments, shard independence of the in-kernel noise, and three trajectories against
+    the oracle driven by the host restatement of the Philox stream."""
+    torch = _torch()
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200 import philox_normals
+    params = configs.PRESETS[task]()
+    psi0 = np.tile(initial_states(params, 64, 9), (B // 64, 1))
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    act = torch.randint(0, 21, (B,), device="cuda", dtype=torch.int32, generator=g)
+    runs = []
+    for rep in range(2):
+        sim = BatchedSim(params, batch=B, seed=123)
+        sim.set_state(psi0)
+        out = sim.step(act)
+        torch.cuda.synchronize()
+        runs.append((sim.get_state(), out["moments"].cpu().numpy(), out["aux"].cpu().numpy()))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    psi, mom, aux = runs[0]
+    w = params["grid_size"] if "quartic" in task else 1.0
+    assert np.max(np.abs(np.sum(np.abs(psi) ** 2, axis=1) * w - 1)) < 1e-12
+    assert np.all(np.isfinite(mom)) and np.allclose(aux[:, L.QC_AUX_NORM], 1.0, atol=1e-12)
+    # the second half of the batch as its own shard (different launch geometry): same results
+    half = BatchedSim(params, batch=B // 2, seed=123, traj_offset=B // 2)
+    half.set_state(psi0[B // 2:])
+    half.step(act[B // 2:].contiguous())
+    assert np.array_equal(half.get_state(), psi[B // 2:])
+    orc = oracle_for(params)
+    a = act.cpu().numpy()
+    for b in (0, B // 2 + 17, B - 1):
+        noise = np.array([philox_normals(123, b, s) for s in range(params["n_sub"])])
+        st = psi0[b].copy()
+        orc.run(st, params["dt"], level_force(params, int(a[b])), params["gamma"], noise)
+        assert np.linalg.norm(psi[b] - st) / np.linalg.norm(st) < TOL_STEP
