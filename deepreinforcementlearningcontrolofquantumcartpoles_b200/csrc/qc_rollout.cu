@@ -629,19 +629,23 @@ static int launch_gemm(const GemmArgs& g, int nz, cudaStream_t st, bool use_umma
         attr_set[dev] = true;
     }
     if (use_umma && g.K % UK == 0 && g.N % 64 == 0) {
-        constexpr size_t smem64 = sizeof(float) * 2 * 2 * 8 * (size_t)((UM + 1) * 4 + (64 + 1) * 4), smem32 = sizeof(float) * 2 * 2 * 8 * (size_t)((UM + 1) * 4 + (32 + 1) * 4);
+        auto smem_for = [](int nt) { return sizeof(float) * 2 * 2 * 8 * (size_t)((UM + 1) * 4 + (nt + 1) * 4); };
         static thread_local bool umma_attr[64] = {};
         if (dev < 64 && !umma_attr[dev]) {
-            RO_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
-            RO_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+            RO_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(128)));
+            RO_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(64)));
+            RO_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(32)));
             umma_attr[dev] = true;
         }
         const int mt = (g.M + UM - 1) / UM;
-        if ((size_t)(g.N / 64) * mt * nz < 2 * 148) {     // small batches: narrower tiles so that the grid covers the SMs
-            gemm_umma_kernel<32><<<dim3(g.N / 32, mt, nz), 128, smem32, st>>>(g);
-        } else {
-            gemm_umma_kernel<64><<<dim3(g.N / 64, mt, nz), 128, smem64, st>>>(g);
-        }
+        static const int force_nt = getenv("QCART_UMMA_NT") ? atoi(getenv("QCART_UMMA_NT")) : 0;
+        // tile width by grid size: wide tiles keep the tensor pipe efficient (one instruction per 128 x NT x 8 block) and re-read A less
+        // often, narrow ones let small batches cover the SMs
+        int nt = ((size_t)(g.N / 64) * mt * nz < 2 * 148) ? 32 : (((size_t)(g.N / 128) * mt * nz >= 4 * 148 && g.N % 128 == 0) ? 128 : 64);
+        if (force_nt == 32 || force_nt == 64 || (force_nt == 128 && g.N % 128 == 0)) nt = force_nt;
+        if (nt == 32) gemm_umma_kernel<32><<<dim3(g.N / 32, mt, nz), 128, smem_for(32), st>>>(g);
+        else if (nt == 64) gemm_umma_kernel<64><<<dim3(g.N / 64, mt, nz), 128, smem_for(64), st>>>(g);
+        else gemm_umma_kernel<128><<<dim3(g.N / 128, mt, nz), 128, smem_for(128), st>>>(g);
         return QC_OK;
     }
     const dim3 grid(g.N / BN, (g.M + BM - 1) / BM, nz);
