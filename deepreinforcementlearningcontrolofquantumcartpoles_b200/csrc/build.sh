@@ -4,9 +4,11 @@ set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="$HERE/../libqcart.so"
 OBJ="$HERE/build"
+# QC_DEBUG_HOOKS=1: development build with the QCART_DEBUG timing hooks (wrong results by design) -> libqcart_dbg.so, never loaded by the package
+if [ -n "$QC_DEBUG_HOOKS" ]; then OUT="$HERE/../libqcart_dbg.so"; OBJ="$HERE/build_dbg"; fi
 mkdir -p "$OBJ"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC ${QC_DEBUG_HOOKS:+-DQC_DEBUG_HOOKS}"
 pids=()
 SRCS="qc_kernels.cu qc_api.cu qc_rollout.cu qc_model.cpp $(cd "$HERE" && ls qc_inst_*.cu)"
 for f in $SRCS; do

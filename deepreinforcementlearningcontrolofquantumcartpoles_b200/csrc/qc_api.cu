@@ -282,7 +282,7 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
     if (pl.binned) {
         const int64_t need = b.B + (int64_t)s->cap_slots * pl.T + 16;
         if (s->order_cap < need) {
-            cudaFree(s->d_vglobal); cudaFree(s->d_order); cudaFree(s->d_order_count); s->d_order = nullptr; s->d_order_count = nullptr; s->order_cap = 0;
+            cudaFree(s->d_order); cudaFree(s->d_order_count); s->d_order = nullptr; s->d_order_count = nullptr; s->order_cap = 0;
             QC_CUDA(cudaMalloc(&s->d_order, sizeof(int32_t) * need)); QC_CUDA(cudaMalloc(&s->d_order_count, sizeof(int32_t)));
             s->order_cap = need;
         }
@@ -299,14 +299,16 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
     p.fac = s->d_fac; p.slot_force = s->d_slot_force; p.slot = slot_dev; p.n_slots = s->n_slots; p.herm_tab = s->d_herm;
     p.psi = b.psi; p.noise = noise; p.seed = s->seed; p.traj_offset = s->traj_offset; p.step_count = b.step; p.nsub_traj = nsub_traj;
     p.moments = moments; p.aux = aux; p.flags_out = flags; p.flags_latch = b.flags; p.q_out = q_out; p.xmean_out = xmean_out;
-    p.moments_only = moments_only; p.jacobi = pl.jacobi; p.xfer = pl.xfer; p.herm_smem = pl.herm_smem;
+    p.moments_only = moments_only; p.stagger = pl.stagger; p.jacobi = pl.jacobi; p.xfer = pl.xfer; p.herm_smem = pl.herm_smem;
     if (s->g_world > 0 && &b == &s->batch && !moments_only) {          // fused result exchange: rows + sequence flag to every rank
         if (!moments || !aux || !flags) return fail(QC_ERR_ARG, "qc_set_gather is active: qc_step needs moments, aux and flags buffers");
         if (nsub_traj) return fail(QC_ERR_ARG, "qc_set_gather is active: per-trajectory substep budgets are not exchanged");
         p.g_world = s->g_world; p.g_rank = s->g_rank; p.g_seq = ++s->g_seq; p.g_done = s->d_gdone;
         for (int r = 0; r < s->g_world; r++) { p.g_peer[r] = s->g_peer[r]; p.g_flag[r] = s->g_flag[r]; }
     }
-    { const char* d = getenv("QCART_DEBUG"); p.debug = d ? atoi(d) : 0; }
+#ifdef QC_DEBUG_HOOKS
+    { const char* d = getenv("QCART_DEBUG"); p.debug = d ? atoi(d) : 0; }      // development builds only (libqcart_dbg.so)
+#endif
     std::string err;
     int rc = launch_step(pl, p, stream, err);
     if (rc) return fail(rc, err);

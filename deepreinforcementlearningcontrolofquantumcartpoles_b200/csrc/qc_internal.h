@@ -82,7 +82,8 @@ struct StepParams {
     double* moments; double* aux; unsigned char* flags_out; unsigned char* flags_latch; double* q_out; double* xmean_out;
     int jacobi;              // 1: register-resident chunk-Jacobi solve (one-warp trajectories, chunk == L)
     int xfer;                // 1: chunk-Jacobi with interface iteration (boundary transfer matrices in shared memory after the noise block)
-    int debug;               // development only (QCART_DEBUG): 1 = skip the implicit solve, 2 = skip the explicit part; results are then wrong
+    int debug;               // development builds only (-DQC_DEBUG_HOOKS, QCART_DEBUG): 1 = skip the implicit solve, 2 = skip the explicit part; results are then wrong
+    int stagger;             // multi-warp trajectories: trajectory t of a CTA starts its substep loop t*stagger clock cycles late (0 = off)
     int moments_only;        // 1: skip the substep loop, only compute moments/aux of the resident state
     // fused result exchange (qc_set_gather): every trajectory's row [moments K | aux 4 | flags 1] goes to row g_rank*B + traj of buffer
     // (g_seq & 1) of EVERY rank's gather area (peer memory over NVLink), then the last CTA publishes g_seq in every rank's flag array
@@ -95,7 +96,7 @@ struct StepParams {
 
 struct LaunchPlan {
     int L, T, G, P, chunk, W, NP, threads, smem_bytes, tstride, maxt, gc;
-    bool tabs; int jacobi; int xfer; int binned; int smem_cta_extra; int vglobal; long long vglobal_elems_per_traj; int herm_smem;
+    bool tabs; int jacobi; int xfer; int binned; int smem_cta_extra; int vglobal; long long vglobal_elems_per_traj; int herm_smem; int stagger;
     char info[240];
 };
 

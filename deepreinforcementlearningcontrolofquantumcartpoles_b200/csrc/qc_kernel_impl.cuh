@@ -37,6 +37,14 @@ namespace qc {
 
 #define QC_MAXRED 24
 
+// Development hooks (timing experiments that skip or shorten phases and therefore give WRONG results) exist only in builds made with
+// -DQC_DEBUG_HOOKS (QC_DEBUG_HOOKS=1 csrc/build.sh -> libqcart_dbg.so, used by tests/tools/); the product library compiles them out.
+#ifdef QC_DEBUG_HOOKS
+#define QC_DBG(p, bit) (((p).debug & (bit)) != 0)
+#else
+#define QC_DBG(p, bit) false
+#endif
+
 // ------------------------------------------------------------------------------------------------------
 // small device helpers
 
@@ -396,7 +404,7 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
                                                   double2* __restrict__ mbox, double* red, int& red_phase, int* iflag, int g, int G, int Gp, int bar_id,
                                                   double& sc_out, double& xbar_out, const double2* __restrict__ xf) {
     constexpr int BA = SolveTraits<VAR>::BA, CS = SolveTraits<VAR>::CS, GUARD = Guard<L>::v;
-    const int n = p.n, K = (p.debug & 4) ? 1 : ((p.debug & 8) ? 3 : p.W / L + 1);      // debug bits 4/8: timing experiments only (wrong results)
+    const int n = p.n, K = QC_DBG(p, 4) ? 1 : (QC_DBG(p, 8) ? 3 : p.W / L + 1);      // debug bits 4/8: timing experiments only (wrong results)
     const int lane = g & 31, wq = g >> 5, nwarps = G >> 5;
     double2 lr[L][BA], dinv[L];
 #pragma unroll
@@ -616,7 +624,7 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     // warp runs the serial solve the other two only wait, and that scheduler idles while the others are oversubscribed.  Rotating the
     // trajectory index by the warp row spreads each trajectory over the sub-partitions (QCART_DEBUG bit 32 restores the plain layout).
     const int wq = (tid >> 5) / p.T;
-    const bool rotate = MULTI && (p.T % 4 == 0) && !(p.debug & 32);
+    const bool rotate = MULTI && (p.T % 4 == 0) && !QC_DBG(p, 32);
     const int t = rotate ? ((tid >> 5) % p.T + 32 * p.T - wq) % p.T : (tid >> 5) % p.T, g = wq * 32 + lane;
     const int bar_id = 1 + t;
     // Work list: without binning position == trajectory.  With binning (p.order) trajectories are grouped by factor slot (= force level),
@@ -799,10 +807,16 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     const double e5 = dt * dt * dt * dt * dt * dt / 360.0, e4 = dt * dt * dt * dt * dt / 80.0, e3 = dt * dt * dt * dt / 24.0, e2 = dt * dt * dt / 12.0;
     const double q_scale = 1.0 / sqrt(2.0 * p.gamma) / dt;
 
+    // Multi-warp trajectories alternate between a phase that keeps all their warps busy (explicit part) and one that keeps a single warp
+    // busy (implicit solve).  Trajectories of a CTA that start together stay in lockstep and collide in both phases; a start offset per
+    // trajectory index lets the solve of one overlap the explicit part of another.  Results do not depend on it.
+    if constexpr (MULTI) {
+        if (p.stagger > 0 && t > 0) { const long long c0 = clock64(), wait = (long long)t * p.stagger; while (clock64() - c0 < wait) __nanosleep(64); }
+    }
     // ---- substep loop ---------------------------------------------------------------------------------------
     for (int s = 0; s < p.n_sub; s++) {
         const bool active = s < my_nsub;
-        if (active && !(p.debug & 2)) {
+        if (active && !QC_DBG(p, 2)) {
             const double r0 = nz[2 * s], r1 = nz[2 * s + 1];
             const double dW = r0 * sdt, dZ = sdt * dt * 0.5 * (r0 + r1 / sqrt(3.0));       // Q:573
             const double k1 = 0.5 / sdt * dZ, k2 = 0.25 * dt, k3 = 0.25 / sdt * (dW * dW - dt), k4 = 0.5 / dt * (dW * dt - dZ),
@@ -1016,14 +1030,14 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
                 for (int j = 0; j < L; j++) rhs[j] = valid[j] ? mk2(acc[j].x + hw[j].x, acc[j].y + hw[j].y) : mk2(0.0, 0.0);
                 // Fock: the last sweep published w0 in U and its halo readers must be done before the solver overwrites U
                 if constexpr (VAR != QC_QUARTIC) traj_sync<MULTI>(bar_id, G);
-                if (!(p.debug & 1)) solve_traj_jacobi<VAR, L, MULTI>(p, rhs, U, tab, mbox, red, red_phase, iflag, g, G, Gp, bar_id, sc, xbar, xf);
+                if (!QC_DBG(p, 1)) solve_traj_jacobi<VAR, L, MULTI>(p, rhs, U, tab, mbox, red, red_phase, iflag, g, G, Gp, bar_id, sc, xbar, xf);
             } else {
                 // For the grid b0 == V so U's last readers (sweep 4) are behind a barrier; for Fock b0 == U: its halo readers must finish first.
                 if constexpr (VAR != QC_QUARTIC) traj_sync<MULTI>(bar_id, G);
 #pragma unroll
                 for (int j = 0; j < L; j++) U[j * Gp + GUARD + g] = valid[j] ? mk2(acc[j].x + hw[j].x, acc[j].y + hw[j].y) : mk2(0.0, 0.0);
                 traj_sync<MULTI>(bar_id, G);                       // psi~ complete in U
-                if (g < 32 && !(p.debug & 1)) solve_traj<VAR, L, TABS>(p, U, V, tab, fac, scal, iflag, g, G, Gp);
+                if (g < 32 && !QC_DBG(p, 1)) solve_traj<VAR, L, TABS>(p, U, V, tab, fac, scal, iflag, g, G, Gp);
                 traj_sync<MULTI>(bar_id, G);
                 sc = scal[0]; xbar = scal[1];
             }

@@ -149,6 +149,7 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             if (P == 1) { W = 0; mult = cols; }
             if (jac) { P = cols; mult = 1; }
             plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = mult * L; plan.W = W; plan.jacobi = jac ? 1 : 0; plan.xfer = (jac && want_xfer) ? 1 : 0;
+            plan.stagger = env_int("QCART_STAGGER", 0);
             plan.vglobal = vglobal ? 1 : 0; plan.vglobal_elems_per_traj = (long long)(nbuf - 1) * L * Gp;
             plan.binned = binned ? 1 : 0; plan.herm_smem = herm_smem ? 1 : 0; plan.smem_cta_extra = binned ? tab_bytes : 0;
             plan.NP = NP; plan.threads = T * G; plan.tstride = tstride; plan.smem_bytes = T * tstride + plan.smem_cta_extra; plan.gc = ke->gc; plan.maxt = ke->maxt; plan.tabs = tabs != 0;
