@@ -19,6 +19,9 @@ const KernEntry* qc_entries_fock_h(int* count);
 const KernEntry* qc_entries_fock_ih(int* count);
 const KernEntry* qc_entries_fock_ih2(int* count);
 
+struct PipeEntry { int L, gc, ne, threads; kern_t fn; size_t (*smem)(int n_sub); };
+const PipeEntry* qc_find_pipe(int L, int G);
+
 static std::vector<KernEntry> all_kernels() {
     std::vector<KernEntry> v;
     typedef const KernEntry* (*getter)(int*);
@@ -80,6 +83,25 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
     const int forceL = env_int("QCART_L", 0), forceT = env_int("QCART_T", 0), forceP = env_int("QCART_P", 0);
     const int forceTabs = env_int("QCART_TABS", -1), forceGC = env_int("QCART_GC", -1);
     const int CS = (var == QC_QUARTIC) ? m.ba + 1 : m.ba + 2;
+    // Multi-warp grid trajectories in force-binned launches: the warp-specialised pipeline (qc_pipe_impl.cuh).  QCART_PIPE=0: off.
+    if (var == QC_QUARTIC && n_sub > 0 && env_int("QCART_PIPE", 1) && !forceL && B >= 8 * n_sm && B >= 64 * m.cfg.n_levels && env_int("QCART_BIN", -1) != 0) {
+        const int L = 6, cols = (n + L - 1) / L, G = (cols + 31) / 32 * 32, W = (W_needed + L - 1) / L * L;
+        const PipeEntry* pe = (G > 32) ? qc_find_pipe(L, G) : nullptr;
+        if (pe && W <= 4 * L && (int)pe->smem(n_sub) <= smem_max) {
+            const int cpt = 32 / pe->ne;
+            int mult = (cols + cpt - 1) / cpt; mult |= 1;
+            if (cpt * mult + W / L <= G + 5) {
+                cudaFuncAttributes fa;
+                if (cudaFuncGetAttributes(&fa, (const void*)pe->fn) != cudaSuccess) { err = std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(cudaGetLastError()); return QC_ERR_CUDA; }
+                memset(&plan, 0, sizeof(plan));
+                plan.L = L; plan.T = 2 * pe->ne; plan.G = G; plan.P = cpt; plan.chunk = mult * L; plan.W = W; plan.NP = G * L; plan.threads = pe->threads;
+                plan.smem_bytes = (int)pe->smem(n_sub); plan.tstride = 0; plan.maxt = pe->threads; plan.gc = G; plan.tabs = true; plan.binned = 1; plan.pipe = 1;
+                snprintf(plan.info, sizeof(plan.info), "sse_pipe_kernel<L=%d,G=%d,NE=%d> traj/CTA=%d chunks/traj=%d chunk=%d W=%d bin=1 threads=%d smem=%d regs=%d lmem=%d",
+                         L, G, pe->ne, plan.T, cpt, plan.chunk, W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
+                return QC_OK;
+            }
+        }
+    }
     // candidate points-per-lane, preferred first (few lanes -> fewer barriers and halos; more lanes when the registers do not suffice)
     int cand[6]; int ncand = 0;
     if (var == QC_QUARTIC) { const int c[] = {6, 9, 3, 5}; for (int v : c) cand[ncand++] = v; }
@@ -149,7 +171,7 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             if (P == 1) { W = 0; mult = cols; }
             if (jac) { P = cols; mult = 1; }
             plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = mult * L; plan.W = W; plan.jacobi = jac ? 1 : 0; plan.xfer = (jac && want_xfer) ? 1 : 0;
-            plan.stagger = env_int("QCART_STAGGER", 0);
+            plan.pipe = 0; plan.stagger = env_int("QCART_STAGGER", 0);
             plan.vglobal = vglobal ? 1 : 0; plan.vglobal_elems_per_traj = (long long)(nbuf - 1) * L * Gp;
             plan.binned = binned ? 1 : 0; plan.herm_smem = herm_smem ? 1 : 0; plan.smem_cta_extra = binned ? tab_bytes : 0;
             plan.NP = NP; plan.threads = T * G; plan.tstride = tstride; plan.smem_bytes = T * tstride + plan.smem_cta_extra; plan.gc = ke->gc; plan.maxt = ke->maxt; plan.tabs = tabs != 0;
@@ -163,6 +185,18 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
 }
 
 int launch_step(const LaunchPlan& plan, const StepParams& p, void* stream, std::string& err) {
+    if (plan.pipe) {
+        const PipeEntry* pe = qc_find_pipe(plan.L, plan.G);
+        if (!pe) { err = "pipeline kernel not found"; return QC_ERR_UNSUPPORTED; }
+        if (cudaFuncSetAttribute((const void*)pe->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess) {
+            err = std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(cudaGetLastError()); return QC_ERR_CUDA;
+        }
+        const int grid = (p.B + plan.T - 1) / plan.T + p.n_slots;
+        pe->fn<<<grid, plan.threads, plan.smem_bytes, (cudaStream_t)stream>>>(p);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { err = std::string("kernel launch: ") + cudaGetErrorString(e) + " [" + plan.info + "]"; return QC_ERR_CUDA; }
+        return QC_OK;
+    }
     const KernEntry* ke = find_kernel(p.variant, plan.L, plan.G, plan.maxt, plan.tabs, plan.gc, plan.maxt);
     if (!ke) { err = "kernel not found"; return QC_ERR_UNSUPPORTED; }
     kern_t fn = ke->fn;

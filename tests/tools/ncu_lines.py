@@ -27,7 +27,7 @@ def load(rep):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("rep"); ap.add_argument("--top", type=int, default=30); ap.add_argument("--ranges", default="")
-    ap.add_argument("--file", default="qc_kernel_impl.cuh")
+    ap.add_argument("--file", default="qc_kernel_impl.cuh"); ap.add_argument("--sort", default="samples")
     a = ap.parse_args()
     files = load(a.rep)
     tot = collections.Counter()
@@ -64,10 +64,10 @@ def main():
     print("total samples %d inst %.4g fp64 %.4g smem_wf %.4g spill_inst %.4g" % (tot["samples"], tot["inst"], tot["fp64"], tot["wf"], tot["spill"]))
     print("stalls: " + ", ".join("%s %.1f%%" % (s[6:], 100 * tot[s] / max(tot["samples"], 1)) for s in sorted(stall_names, key=lambda s: -tot[s])[:8]))
     print("\n top lines by samples")
-    for k, c in sorted(per.items(), key=lambda kv: -kv[1]["samples"])[: a.top]:
+    for k, c in sorted(per.items(), key=lambda kv: -kv[1][a.sort])[: a.top]:
         top = sorted(stall_names, key=lambda s: -c[s])[:3]
-        print("%-22s:%5d  samples %5.1f%%  inst %5.1f%%  fp64 %5.1f%%  wf %5.1f%%   %s" % (k[0][:22], k[1], 100 * c["samples"] / tot["samples"], 100 * c["inst"] / tot["inst"],
-              100 * c["fp64"] / max(tot["fp64"], 1), 100 * c["wf"] / max(tot["wf"], 1), " ".join("%s %.0f%%" % (s[6:], 100 * c[s] / max(c["samples"], 1)) for s in top)))
+        print("%-22s:%5d  samples %5.1f%%  inst %5.1f%%  fp64 %5.1f%%  wf %5.1f%%  spill %5.1f%%   %s" % (k[0][:22], k[1], 100 * c["samples"] / tot["samples"], 100 * c["inst"] / tot["inst"],
+              100 * c["fp64"] / max(tot["fp64"], 1), 100 * c["wf"] / max(tot["wf"], 1), 100 * c["spill"] / max(tot["spill"], 1), " ".join("%s %.0f%%" % (s[6:], 100 * c[s] / max(c["samples"], 1)) for s in top)))
     if a.ranges:
         print("\n ranges (%s)" % a.file)
         for spec in a.ranges.split(","):
