@@ -309,10 +309,32 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
 #ifdef QC_DEBUG_HOOKS
     { const char* d = getenv("QCART_DEBUG"); p.debug = d ? atoi(d) : 0; }      // development builds only (libqcart_dbg.so)
 #endif
+#ifdef QC_DEBUG_HOOKS
+    static unsigned long long* dbg_t = nullptr; static int dbg_n = 0;
+    const bool timers = getenv("QCART_TIMERS") && pl.pipe;
+    const int dbg_grid = (int)((b.B + pl.T - 1) / pl.T) + s->n_slots;
+    if (timers) {
+        if (dbg_n < dbg_grid) { cudaFree(dbg_t); cudaMallocManaged(&dbg_t, sizeof(unsigned long long) * 16 * dbg_grid); dbg_n = dbg_grid; }
+        memset(dbg_t, 0, sizeof(unsigned long long) * 16 * dbg_grid);
+        p.dbg_timers = dbg_t;
+    }
+#endif
     std::string err;
     int rc = launch_step(pl, p, stream, err);
     if (rc) return fail(rc, err);
     s->launches++;
+#ifdef QC_DEBUG_HOOKS
+    if (timers) {
+        cudaStreamSynchronize((cudaStream_t)stream);
+        double acc[16] = {0}; int used = 0;
+        for (int c = 0; c < dbg_grid; c++) { if (dbg_t[16 * c + 15] == 0) continue; used++; for (int k = 0; k < 16; k++) acc[k] += (double)dbg_t[16 * c + k]; }
+        if (used) {
+            const double per = 1.0 / used / std::max(1, n_sub);
+            fprintf(stderr, "[timers] CTAs %d  cycles per substep-round: explicit(grp0 warp0): wait %.0f pass1 %.0f horner %.0f tail %.0f | solver A: wait %.0f fwd %.0f bwd %.0f fin %.0f | total %.0f\n",
+                    used, acc[0] * per, acc[1] * per, acc[2] * per, acc[3] * per, acc[4] * per, acc[5] * per, acc[6] * per, acc[7] * per, acc[15] * per);
+        }
+    }
+#endif
     return QC_OK;
 }
 

@@ -21,6 +21,14 @@
 
 namespace qc {
 
+// cycle counters of the pipeline phases (development builds only; see qc_api.cu, QCART_TIMERS=1)
+#ifdef QC_DEBUG_HOOKS
+struct PipeTimers { long long last, begin; unsigned long long acc[4]; __device__ void start() { last = begin = clock64(); acc[0] = acc[1] = acc[2] = acc[3] = 0; }
+                    __device__ __forceinline__ void tick(int k) { const long long now = clock64(); acc[k] += (unsigned long long)(now - last); last = now; } };
+#else
+struct PipeTimers { __device__ void start() {} __device__ __forceinline__ void tick(int) {} };
+#endif
+
 #define QC_PIPE_GU 5          // zero guard columns of a state line (solver warm-up W <= 4 columns + one prefetched column)
 #ifndef QC_PIPE_PF
 #define QC_PIPE_PF 1          // rows the solver's loads run ahead of its arithmetic
@@ -76,7 +84,7 @@ template <int L, int GC, int NE> struct PipeGeo {
 // (which belongs to the neighbour chunk) before any lane writes, the warp runs converged and __syncwarp separates the two parts.
 template <int L, int GC, int NE>
 __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restrict__ Uset, const double2* __restrict__ tab, double* scal_set, int mult, int wb,
-                                           int lane, int s) {
+                                           int lane, int s, PipeTimers& tm) {
     typedef PipeGeo<L, GC, NE> Geo;
     constexpr int BA = 4, CS = Geo::CS, G = Geo::G, Gp = Geo::GpU, GUARD = QC_PIPE_GU;
     const int tt = lane % NE, cc = lane / NE;
@@ -134,6 +142,7 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
         if (act) { for (int b = 0; b < mult; b++, col++) fwd_col(true); }
     }
     __syncwarp();
+    tm.tick(1);
     // ---- backward: L^T x = z (column oriented) -------------------------------------------------------------
     {
         double2 pend[BA];
@@ -181,6 +190,7 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
         __syncwarp();
         if (act) { for (int b = 0; b < mult; b++, col--) bwd_col(true); }
     }
+    tm.tick(2);
     // ---- norm, <x>, escape probability over the chunks of each trajectory (lanes with equal tt), then Fail on the normalised state ----
 #pragma unroll
     for (int o = NE; o < 32; o <<= 1) {
@@ -295,6 +305,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
     __syncthreads();
     }
 
+    PipeTimers tm; tm.start();
     if (!cta_empty && is_solver) {
         // ================= solver warpgroup: warp X of it serves set X ==================================================================
         const int X = warp >> 2;
@@ -304,8 +315,10 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
             const int wb = p.W / L;
             for (int s = 0; s < n_sub; s++) {
                 mbar_wait(&bars[X], s & 1);
-                pipe_solve<L, GC, NE>(p, Uall + (size_t)X * NE * LBU, tab, scal_all + X * NE * 16, mult, wb, lane, s);
+                tm.tick(0);
+                pipe_solve<L, GC, NE>(p, Uall + (size_t)X * NE * LBU, tab, scal_all + X * NE * 16, mult, wb, lane, s, tm);
                 mbar_arrive(&bars[2 + X]);
+                tm.tick(3);
             }
         }
     } else if (!cta_empty && !is_idle) {
@@ -364,6 +377,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                 double* scal = scal_all + ts * 16;
                 const int* iflag = reinterpret_cast<const int*>(scal + 8);
                 if (s > 0) mbar_wait(&bars[2 + X], (s - 1) & 1);
+                tm.tick(0);
                 if (s < iflag[1]) {
                     const double sc = scal[0], xbar = scal[1];
                     const double* nz = nz_all + ((size_t)ts * n_sub + s) * 2;
@@ -398,6 +412,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                             m[0] += xp2; m[1] = fma(x, xp2, m[1]); m[2] = fma(x2, xp2, m[2]); m[3] = fma(x, m2, m[3]);
                         }
                         traj_reduce<4, true>(m, red, red_phase, wq, NWG, lane, bar_id, G);
+                        tm.tick(1);
                         // un-normalised <x> of Y+- and Phi+- (Q:457-460, 605-615, 479-482); coefficient polynomials as in sse_step_kernel
                         const double xbp = p.w * m[0], xbm = p.w * m[3];
                         const double t1 = m[1] - xbp * m[0], t2 = m[2] - 2.0 * xbp * m[1] + xbp * xbp * m[0];
@@ -429,6 +444,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
 #pragma unroll
                     for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(e2, a[j].x, hw[j].x), fma(e2, a[j].y, hw[j].y)) : mk2(0.0, 0.0);        // c2 = dt^3/12
                     pipe_sweep<L>(ops, S1, w, hw, g, G, GpS, bar_id);
+                    tm.tick(2);
                     // psi (own points) again from the state line, v1 = -i cv psi
                     double2 psi[L];
                     {
@@ -459,6 +475,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                     }
                 }
                 mbar_arrive(&bars[X]);
+                tm.tick(3);
             }
         }
 
@@ -584,6 +601,13 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
             if (p.g_world > 0 && have && g < 32) publish_row(p, traj, lane);
         }
     }
+#ifdef QC_DEBUG_HOOKS
+    if (p.dbg_timers && !cta_empty && lane == 0) {
+        unsigned long long* o = p.dbg_timers + 16 * (size_t)blockIdx.x;
+        if (warp == 0) { for (int k = 0; k < 4; k++) o[k] = tm.acc[k]; o[15] = (unsigned long long)(clock64() - tm.begin); }
+        if (warp == 3) { for (int k = 0; k < 4; k++) o[4 + k] = tm.acc[k]; }
+    }
+#endif
     if (p.g_world > 0) publish_done(p);
 }
 

@@ -418,3 +418,76 @@ def test_full_size_properties_configs_3_and_4(task, B):
         st = psi0[b].copy()
         orc.run(st, params["dt"], level_force(params, int(a[b])), params["gamma"], noise)
         assert np.linalg.norm(psi[b] - st) / np.linalg.norm(st) < TOL_STEP
+
+
+# ---- the warp-specialised pipeline kernel (csrc/qc_pipe_impl.cuh): multi-warp grid trajectories in force-binned launches ----------------
+
+def _pipe_case(B, n_sub, seed, ragged_budget=False, one_bin=False, want_q=False):
+    torch = _torch()
+    params = configs.inverted_quartic(n_sub=n_sub)
+    rng = np.random.default_rng(seed)
+    psi0 = initial_states(params, B, seed)
+    actions = rng.integers(0, params["n_levels"], B).astype(np.int32)
+    if one_bin:
+        actions[:] = 13
+    noise = rng.standard_normal((B, n_sub, 2))
+    budget = rng.integers(0, n_sub + 1, B).astype(np.int32) if ragged_budget else None
+    sim = BatchedSim(params, batch=B)
+    sim.set_state(psi0)
+    out = sim.step(torch.as_tensor(actions, device="cuda"), noise=torch.as_tensor(noise, device="cuda"), want_q=want_q,
+                   nsub_traj=None if budget is None else torch.as_tensor(budget, device="cuda"))
+    torch.cuda.synchronize()
+    return params, sim, out, psi0, actions, noise, budget
+
+
+@pytest.mark.parametrize("B,one_bin", [(1400, False), (1351, False), (1400, True)])
+def test_pipeline_kernel_matches_oracle(B, one_bin):
+    """Inverted quartic (N = 521, three warps per trajectory) at a batch that selects sse_pipe_kernel: state, moments, flags, q stream of a
+    random subset against the CPU oracle (same psi0, force, noise).  B = 1351 leaves ragged bins and a partly filled last CTA; one_bin puts
+    every trajectory into one force level."""
+    n_sub = 8
+    params, sim, out, psi0, actions, noise, _ = _pipe_case(B, n_sub, 11, one_bin=one_bin, want_q=True)
+    assert "sse_pipe_kernel" in sim.kernel_info(), sim.kernel_info()
+    pick = np.random.default_rng(5).choice(B, 24, replace=False)
+    pick[:3] = [0, B - 1, B // 2]
+    orc = oracle_for(params)
+    ref, fails, qs = oracle_control_step(orc, params, psi0[pick], actions[pick], noise[pick], want_q=True)
+    got = sim.get_state()
+    assert rel_err(got[pick], ref) < TOL_STEP
+    assert np.allclose(out["aux"].cpu().numpy()[:, L.QC_AUX_NORM], 1.0, atol=1e-12)
+    mom = out["moments"].cpu().numpy(); flags = out["flags"].cpu().numpy()
+    q = out["q"].cpu().numpy(); xm = out["x_mean"].cpu().numpy()
+    for k, b in enumerate(pick):
+        m_ref = orc.get_moments(ref[k])
+        assert np.max(np.abs(mom[b] - m_ref) / np.maximum(np.abs(m_ref), 1e-3)) < TOL_STEP
+        assert bool(flags[b] & L.QC_FLAG_FAIL) == bool(fails[k])
+        assert np.max(np.abs(xm[b] - qs[k][1])) < 1e-10
+        assert np.max(np.abs(q[b] - qs[k][0]) / np.maximum(1.0, np.abs(qs[k][0]))) < 1e-10
+
+
+def test_pipeline_kernel_agrees_with_the_per_trajectory_kernel(monkeypatch):
+    """Same launch with QCART_PIPE=0 (sse_step_kernel, per-trajectory solver): every output agrees to rounding level (the chunking of the
+    substitution differs, so not bitwise), flags identical; per-trajectory substep budgets honoured; both kernels deterministic run to run."""
+    B, n_sub = 1400, 10
+    res = {}
+    for mode in ("0", "1", "1"):
+        monkeypatch.setenv("QCART_PIPE", mode)
+        params, sim, out, psi0, actions, noise, budget = _pipe_case(B, n_sub, 21, ragged_budget=True)
+        assert ("sse_pipe_kernel" in sim.kernel_info()) == (mode == "1")
+        cur = (sim.get_state(), out["moments"].cpu().numpy(), out["aux"].cpu().numpy(), out["flags"].cpu().numpy())
+        if mode in res:
+            for a, b in zip(res[mode], cur):
+                assert np.array_equal(a, b)                     # deterministic
+        res[mode] = cur
+    a, b = res["0"], res["1"]
+    assert rel_err(b[0], a[0]) < 1e-12
+    assert np.max(np.abs(b[1] - a[1]) / np.maximum(np.abs(a[1]), 1e-3)) < TOL_STEP        # 5th-order centred moments amplify rounding
+    assert np.array_equal(a[3], b[3])
+    idle = np.where(budget == 0)[0]
+    assert len(idle) > 0 and rel_err(b[0][idle], psi0[idle]) < 1e-14        # budget 0: state untouched (up to the renormalising store)
+    orc = oracle_for(params)
+    pick = np.argsort(budget)[-6:]
+    for bidx in pick:
+        st = psi0[bidx].copy()
+        orc.run(st, params["dt"], level_force(params, int(actions[bidx])), params["gamma"], noise[bidx][: budget[bidx]])
+        assert rel_err(b[0][bidx][None], st[None]) < TOL_STEP
