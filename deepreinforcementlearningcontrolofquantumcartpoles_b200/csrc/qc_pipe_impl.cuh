@@ -29,7 +29,6 @@ struct PipeTimers { long long last, begin; unsigned long long acc[4]; __device__
 struct PipeTimers { __device__ void start() {} __device__ __forceinline__ void tick(int) {} };
 #endif
 
-#define QC_PIPE_GU 5          // zero guard columns of a state line (solver warm-up W <= 4 columns + one prefetched column)
 #ifndef QC_PIPE_PF
 #define QC_PIPE_PF 1          // rows the solver's loads run ahead of its arithmetic
 #endif
@@ -57,7 +56,10 @@ template <int L, int GD> __device__ __forceinline__ double2 ld_rel_g(const doubl
 // geometry shared by host (plan) and device
 template <int L, int GC, int NE> struct PipeGeo {
     static constexpr int G = GC, NWG = GC / 32, TT = 2 * NE, CPT = 32 / NE;
-    static constexpr int GpU = G + 2 * QC_PIPE_GU, GpS = G + 2 * QC_PIPE_GS;
+    // zero guard columns of a state line: solver warm-up (W <= 4 columns) + one prefetched column; one-warp groups have few, wide chunks whose
+    // last one may reach further past the line
+    static constexpr int GU = (GC == 32) ? 8 : 5;
+    static constexpr int GpU = G + 2 * GU, GpS = G + 2 * QC_PIPE_GS;
     static constexpr int LBU0 = L * GpU;
     // stride between the state lines of a set: = 8/NE (mod 8) in 16-byte units, so that the NE x 2 lanes of a quarter warp of the solver hit
     // distinct bank groups (chunk stride `mult` is odd)
@@ -86,7 +88,7 @@ template <int L, int GC, int NE>
 __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restrict__ Uset, const double2* __restrict__ tab, double* scal_set, int mult, int wb,
                                            int lane, int s, PipeTimers& tm) {
     typedef PipeGeo<L, GC, NE> Geo;
-    constexpr int BA = 4, CS = Geo::CS, G = Geo::G, Gp = Geo::GpU, GUARD = QC_PIPE_GU;
+    constexpr int BA = 4, CS = Geo::CS, G = Geo::G, Gp = Geo::GpU, GUARD = Geo::GU;
     const int tt = lane % NE, cc = lane / NE;
     double2* __restrict__ U = Uset + (size_t)tt * Geo::LBU;
     double* scal = scal_set + tt * 16;
@@ -217,12 +219,12 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
 
 // ------------------------------------------------------------------------------------------------------
 // One Horner sweep of an explicit group: publish w into the sweep line, group barrier, gather the halo, return H0 w.
-template <int L>
+template <int L, bool MULTI>
 __device__ __forceinline__ void pipe_sweep(const LaneOps<QC_QUARTIC, L>& ops, double2* __restrict__ buf, const double2 (&w)[L], double2 (&hw)[L], int g, int G, int Gp, int bar_id) {
     constexpr int GS = QC_PIPE_GS;
 #pragma unroll
     for (int j = 0; j < L; j++) buf[j * Gp + GS + g] = w[j];
-    traj_sync<true>(bar_id, G);
+    traj_sync<MULTI>(bar_id, G);
     double2 ext[L + 8];
 #pragma unroll
     for (int r = -4; r < L + 4; r++) ext[r + 4] = (r >= 0 && r < L) ? w[r] : ld_rel_g<L, GS>(buf, g, Gp, r);
@@ -235,7 +237,8 @@ template <int L, int GC, int NE>
 __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kernel(const StepParams p) {
     typedef PipeGeo<L, GC, NE> Geo;
     constexpr int G = Geo::G, NWG = Geo::NWG, TT = Geo::TT, GpU = Geo::GpU, GpS = Geo::GpS, LBU = Geo::LBU, LBS = Geo::LBS, CS = Geo::CS;
-    constexpr int GU = QC_PIPE_GU, GS = QC_PIPE_GS;
+    constexpr int GU = Geo::GU, GS = QC_PIPE_GS;
+    constexpr bool MULTI = NWG > 1;                                  // one-warp groups synchronise with __syncwarp
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, n = p.n, n_sub = p.n_sub;
     const int warp = tid >> 5, lane = tid & 31;
@@ -358,13 +361,13 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                 const int i = g * L + j;
                 if (i >= p.cen_lo && i < p.cen_hi) v[1] += a2;
             }
-            traj_reduce<2, true>(v, red, red_phase, wq, NWG, lane, bar_id, G);
+            traj_reduce<2, MULTI>(v, red, red_phase, wq, NWG, lane, bar_id, G);
             if (g == 0) {
                 scal[1] = p.w * v[0];
                 if (p.cen_hi > p.cen_lo && iflag[1] > 0) { if (1.0 - p.w * v[1] > 0.5) iflag[0] |= QC_FLAG_ESCAPED; }
             }
         }
-        traj_sync<true>(bar_id, G);
+        traj_sync<MULTI>(bar_id, G);
 
         const double dt = p.dt, sdt = sqrt(dt), g4 = p.gamma / 4.0, gs = sqrt(p.gamma / 2.0), sig = sdt * gs;
         const double e5 = dt * dt * dt * dt * dt * dt / 360.0, e4 = dt * dt * dt * dt * dt / 80.0, e3 = dt * dt * dt * dt / 24.0, e2 = dt * dt * dt / 12.0;
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                             const double xp2 = x * p2;
                             m[0] += xp2; m[1] = fma(x, xp2, m[1]); m[2] = fma(x2, xp2, m[2]); m[3] = fma(x, m2, m[3]);
                         }
-                        traj_reduce<4, true>(m, red, red_phase, wq, NWG, lane, bar_id, G);
+                        traj_reduce<4, MULTI>(m, red, red_phase, wq, NWG, lane, bar_id, G);
                         tm.tick(1);
                         // un-normalised <x> of Y+- and Phi+- (Q:457-460, 605-615, 479-482); coefficient polynomials as in sse_step_kernel
                         const double xbp = p.w * m[0], xbm = p.w * m[3];
@@ -434,16 +437,16 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                     // ===== merged Horner chain in H0 =====
 #pragma unroll
                     for (int j = 0; j < L; j++) w[j] = mk2(-e5 * a[j].y, e5 * a[j].x);                    // c5 a,  c5 = +i dt^6/360
-                    pipe_sweep<L>(ops, S0, w, hw, g, G, GpS, bar_id);
+                    pipe_sweep<L, MULTI>(ops, S0, w, hw, g, G, GpS, bar_id);
 #pragma unroll
                     for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(-e4, a[j].x, hw[j].x), fma(-e4, a[j].y, hw[j].y)) : mk2(0.0, 0.0);      // c4 = -dt^5/80
-                    pipe_sweep<L>(ops, S1, w, hw, g, G, GpS, bar_id);
+                    pipe_sweep<L, MULTI>(ops, S1, w, hw, g, G, GpS, bar_id);
 #pragma unroll
                     for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(e3, a[j].y, hw[j].x), fma(-e3, a[j].x, hw[j].y)) : mk2(0.0, 0.0);       // c3 = -i dt^4/24
-                    pipe_sweep<L>(ops, S0, w, hw, g, G, GpS, bar_id);
+                    pipe_sweep<L, MULTI>(ops, S0, w, hw, g, G, GpS, bar_id);
 #pragma unroll
                     for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(e2, a[j].x, hw[j].x), fma(e2, a[j].y, hw[j].y)) : mk2(0.0, 0.0);        // c2 = dt^3/12
-                    pipe_sweep<L>(ops, S1, w, hw, g, G, GpS, bar_id);
+                    pipe_sweep<L, MULTI>(ops, S1, w, hw, g, G, GpS, bar_id);
                     tm.tick(2);
                     // psi (own points) again from the state line, v1 = -i cv psi
                     double2 psi[L];
@@ -457,7 +460,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                             w[j] = valid[j] ? mk2(fma(cv, psi[j].y, hw[j].x), fma(-cv, psi[j].x, hw[j].y)) : mk2(0.0, 0.0);
                         }
                     }
-                    pipe_sweep<L>(ops, S0, w, hw, g, G, GpS, bar_id);
+                    pipe_sweep<L, MULTI>(ops, S0, w, hw, g, G, GpS, bar_id);
                     {
                         const double A2 = stash[0], A1 = stash[1], A0 = stash[2], P2 = stash[3], P1 = stash[4], P0 = stash[5], M2 = stash[6], M1 = stash[7], M0 = stash[8], G0 = stash[11];
 #pragma unroll
@@ -527,7 +530,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                 tcur[j] = mk2(pr, pim);
                 v0[3] += psi[j].x * pr + psi[j].y * pim;
             }
-            traj_reduce<5, true>(v0, red, red_phase, wq, NWG, lane, bar_id, G);
+            traj_reduce<5, MULTI>(v0, red, red_phase, wq, NWG, lane, bar_id, G);
             const double xm = p.w * v0[1], pm = p.w * v0[3];
             double S[20];
 #pragma unroll
@@ -552,7 +555,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                         double2* buf = (ip & 1) ? S0 : S1;
 #pragma unroll
                         for (int j = 0; j < L; j++) buf[j * GpS + GS + g] = tcur[j];
-                        traj_sync<true>(bar_id, G);
+                        traj_sync<MULTI>(bar_id, G);
                         double2 te[L + 8];
 #pragma unroll
                         for (int r = -4; r < L + 4; r++) te[r + 4] = (r >= 0 && r < L) ? tcur[r] : ld_rel_g<L, GS>(buf, g, GpS, r);
@@ -583,7 +586,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                     }
                 }
             }
-            traj_reduce<20, true>(S, red, red_phase, wq, NWG, lane, bar_id, G);
+            traj_reduce<20, MULTI>(S, red, red_phase, wq, NWG, lane, bar_id, G);
             if (have && g == 0) {
                 if (p.moments) {
                     double* out = p.moments + (size_t)traj * p.K;
