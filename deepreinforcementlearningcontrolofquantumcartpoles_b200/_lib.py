@@ -16,7 +16,7 @@ POLICY_PARAMS = ["FC1_W", "FC1_B", "FC2_W", "FC2_B", "FC31_UW", "FC31_SW", "FC31
 
 
 class QcConfig(C.Structure):
-    _fields_ = [("variant", C.c_int32), ("n", C.c_int32), ("x_max", C.c_double), ("grid_size", C.c_double),
+    _fields_ = [("struct_size", C.c_uint32), ("variant", C.c_int32), ("n", C.c_int32), ("x_max", C.c_double), ("grid_size", C.c_double),
                 ("lambda_", C.c_double), ("mass", C.c_double), ("omega", C.c_double), ("dt", C.c_double),
                 ("gamma", C.c_double), ("n_sub", C.c_int32), ("f_max", C.c_double), ("n_levels", C.c_int32),
                 ("moment_order", C.c_int32), ("x_threshold", C.c_double), ("herm_mode", C.c_int32),
@@ -34,6 +34,7 @@ _vp, _dp, _ip, _i64 = C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64
 SYMBOLS = [
     ("qc_last_error", C.c_char_p, []),
     ("qc_version", C.c_char_p, []),
+    ("qc_config_size", C.c_uint32, []),
     ("qc_create", C.c_int, [C.POINTER(QcConfig), C.POINTER(_vp)]),
     ("qc_destroy", C.c_int, [_vp]),
     ("qc_get_config", C.c_int, [_vp, C.POINTER(QcConfig)]),
@@ -70,6 +71,7 @@ SYMBOLS = [
     ("qc_set_gather", C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(_vp), C.POINTER(_vp)]),
     ("qc_gather_seq", C.c_uint64, [_vp]),
     ("qc_gather_wait", C.c_int, [_vp, C.c_uint64, _vp]),
+    ("qc_gather_error", C.c_int, [_vp, C.POINTER(C.c_uint32)]),
     # ---- include/qcart_rollout.h ----
     ("qc_obs_f32", C.c_int, [_dp, _i64, C.c_double, _vp, _vp]),
     ("qc_policy_create", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),
@@ -112,6 +114,8 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        if lib.qc_config_size() != C.sizeof(QcConfig):
+            raise ImportError("libqcart.so was built from a different include/qcart.h: qc_config has %d bytes there, %d here" % (lib.qc_config_size(), C.sizeof(QcConfig)))
         _lib = lib
     return _lib
 

@@ -29,6 +29,10 @@ struct qc_sim {
     Model model;
     int device = 0;
     cudaStream_t stream = nullptr;          // private stream of the host-buffer entry points
+    // Ordering between the private stream and the caller's streams: every stream-ordered entry point that touches the resident batch records
+    // ev_user on its stream and first waits for ev_host; every host-buffer entry point makes the private stream wait for ev_user and records
+    // ev_host when its device work is enqueued (it also synchronises before returning).
+    cudaEvent_t ev_user = nullptr, ev_host = nullptr;
     // operator tables (device, zero padded by 8 doubles on both sides)
     double *raw_x = nullptr, *raw_hd = nullptr, *raw_h2 = nullptr;
     // factor tables
@@ -52,17 +56,34 @@ struct qc_sim {
     // fused result exchange (qc_set_gather)
     int g_world = 0, g_rank = 0; uint64_t g_seq = 0;
     double* g_peer[QC_MAX_PEERS] = {}; unsigned long long* g_flag[QC_MAX_PEERS] = {};
-    unsigned int* d_gdone = nullptr;
+    unsigned int* d_gdone = nullptr; unsigned int* d_gerr = nullptr;
+    std::vector<uint64_t> slot_stamp; uint64_t call_id = 0;      // LRU of the on-demand factor slots (qc_step_forces / qc_step1)
 };
 
 extern "C" const char* qc_last_error(void) { return g_err.c_str(); }
-extern "C" const char* qc_version(void) { return "qcart 0.1 sm_100a"; }
+extern "C" const char* qc_version(void) { return "qcart 0.2 sm_100a"; }
+extern "C" uint32_t qc_config_size(void) { return (uint32_t)sizeof(qc_config); }
 
 static int use_device(const qc_sim* s) {
     if (!s) return fail(QC_ERR_ARG, "null handle");
     QC_CUDA(cudaSetDevice(s->device));
     return QC_OK;
 }
+
+// the caller's stream is about to touch the resident batch: order it after pending host-buffer work, and remember it
+static int enter_user(qc_sim* s, void* stream) {
+    if ((cudaStream_t)stream == s->stream) return QC_OK;
+    QC_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_host, 0));
+    return QC_OK;
+}
+static int leave_user(qc_sim* s, void* stream) {
+    if ((cudaStream_t)stream == s->stream) return QC_OK;
+    QC_CUDA(cudaEventRecord(s->ev_user, (cudaStream_t)stream));
+    return QC_OK;
+}
+// the private stream is about to touch the resident batch: order it after everything the caller enqueued through this handle
+static int enter_host(qc_sim* s) { QC_CUDA(cudaStreamWaitEvent(s->stream, s->ev_user, 0)); return QC_OK; }
+static int leave_host(qc_sim* s) { QC_CUDA(cudaEventRecord(s->ev_host, s->stream)); return QC_OK; }
 
 static int upload_padded(const std::vector<double>& v, int n, double** raw) {
     std::vector<double> tmp(n + 16, 0.0);
@@ -75,7 +96,15 @@ static int upload_padded(const std::vector<double>& v, int n, double** raw) {
 // add one force to the factor tables (device + host mirror)
 static int add_slot(qc_sim* s, double F, int* slot_out) {
     const Model& m = s->model;
-    if (s->n_slots >= s->cap_slots) return fail(QC_ERR_UNSUPPORTED, "too many distinct force values (factor-table capacity)");
+    int idx = s->n_slots;
+    if (s->n_slots >= s->cap_slots) {
+        // table full: evict the least recently used ON-DEMAND slot (never one of the n_levels controller forces, never one that the current
+        // call has already handed out).  Stream order keeps this safe: the overwrite is enqueued behind every launch that used the old row.
+        idx = -1;
+        for (int k = m.cfg.n_levels; k < s->n_slots; k++)
+            if (s->slot_stamp[k] != s->call_id && (idx < 0 || s->slot_stamp[k] < s->slot_stamp[idx])) idx = k;
+        if (idx < 0) return fail(QC_ERR_UNSUPPORTED, "more distinct force values in one call than on-demand factor slots (" + std::to_string(s->cap_slots - m.cfg.n_levels) + ")");
+    }
     std::vector<zc> tab;
     int rc = m.factor(F, tab);
     if (rc == QC_ERR_PIVOT) return fail(rc, "implicit matrix would need row pivoting for this force (outside the reference's stable parameter range)");
@@ -86,17 +115,22 @@ static int add_slot(qc_sim* s, double F, int* slot_out) {
     const int W = m.decay_width(tab, solve_tol);
     if (W > s->W_needed) { s->W_needed = W; s->batch.plan_nsub = -1; s->one.plan_nsub = -1; }
     const size_t row = (size_t)m.n * (m.ba + 1);
-    QC_CUDA(cudaMemcpy(s->d_fac + row * s->n_slots, tab.data(), sizeof(zc) * row, cudaMemcpyHostToDevice));
-    QC_CUDA(cudaMemcpy(s->d_slot_force + s->n_slots, &F, sizeof(double), cudaMemcpyHostToDevice));
-    if (s->d_herm) { std::vector<double> ht; m.herm_table(F, ht); QC_CUDA(cudaMemcpy(s->d_herm + (size_t)m.n * 11 * s->n_slots, ht.data(), sizeof(double) * ht.size(), cudaMemcpyHostToDevice)); }
-    s->slot_force.push_back(F);
-    *slot_out = s->n_slots++;
+    if (idx < s->n_slots) QC_CUDA(cudaDeviceSynchronize());      // eviction: no launch may still read the row that is replaced
+    QC_CUDA(cudaMemcpy(s->d_fac + row * idx, tab.data(), sizeof(zc) * row, cudaMemcpyHostToDevice));
+    QC_CUDA(cudaMemcpy(s->d_slot_force + idx, &F, sizeof(double), cudaMemcpyHostToDevice));
+    if (s->d_herm) { std::vector<double> ht; m.herm_table(F, ht); QC_CUDA(cudaMemcpy(s->d_herm + (size_t)m.n * 11 * idx, ht.data(), sizeof(double) * ht.size(), cudaMemcpyHostToDevice)); }
+    if (idx == s->n_slots) { s->slot_force.push_back(F); s->slot_stamp.push_back(s->call_id); s->n_slots++; }
+    else { s->slot_force[idx] = F; s->slot_stamp[idx] = s->call_id; }
+    *slot_out = idx;
     return QC_OK;
 }
 
 extern "C" int qc_create(const qc_config* cfg, qc_sim** out) {
     if (!cfg || !out) return fail(QC_ERR_ARG, "null argument");
     *out = nullptr;
+    if (cfg->struct_size != sizeof(qc_config))
+        return fail(QC_ERR_ARG, "qc_config.struct_size is " + std::to_string(cfg->struct_size) + " but this library's qc_config has " + std::to_string(sizeof(qc_config)) +
+                    " bytes: the caller's struct definition is out of date (see include/qcart.h)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0) { cudaGetLastError(); return fail(QC_ERR_CUDA, "no usable CUDA device: libqcart has no CPU fallback"); }
@@ -110,7 +144,8 @@ extern "C" int qc_create(const qc_config* cfg, qc_sim** out) {
     s->model.cfg.n = s->model.n;
     const Model& m = s->model;
     rc = use_device(s); if (rc) { delete s; return rc; }
-    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return fail(QC_ERR_CUDA, "cudaStreamCreate failed"); }
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_user, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_host, cudaEventDisableTiming) != cudaSuccess) { qc_destroy(s); return fail(QC_ERR_CUDA, "cudaStreamCreate / cudaEventCreate failed"); }
     if ((rc = upload_padded(m.x, m.n, &s->raw_x)) || (rc = upload_padded(m.hdiag, m.n, &s->raw_hd))) { qc_destroy(s); return rc; }
     if (m.cfg.variant == QC_INV_HARMONIC && (rc = upload_padded(m.hoff, m.n, &s->raw_h2))) { qc_destroy(s); return rc; }
     s->cap_slots = cfg->n_levels + 256;
@@ -143,6 +178,9 @@ extern "C" int qc_destroy(qc_sim* s) {
     cudaFree(s->batch.psi); cudaFree(s->batch.step); cudaFree(s->batch.flags);
     cudaFree(s->d_gdone); cudaFree(s->d_vglobal); cudaFree(s->d_order); cudaFree(s->d_order_count); cudaFree(s->d_action); cudaFree(s->d_noise); cudaFree(s->d_mom); cudaFree(s->d_aux); cudaFree(s->d_flagout);
     cudaFree(s->one.psi); cudaFree(s->one.step); cudaFree(s->one.flags); cudaFree(s->d_slot1); cudaFree(s->d_noise1); cudaFree(s->d_out1); cudaFree(s->d_flag1);
+    if (s->ev_user) cudaEventDestroy(s->ev_user);
+    if (s->ev_host) cudaEventDestroy(s->ev_host);
+    cudaFree(s->d_gerr);
     if (s->stream) cudaStreamDestroy(s->stream);
     cudaGetLastError();
     delete s;
@@ -170,6 +208,7 @@ extern "C" int qc_set_batch(qc_sim* s, int64_t B) {
     if (B <= 0 || B > (int64_t)1 << 30) return fail(QC_ERR_ARG, "batch size out of range");
     BatchView& b = s->batch;
     if (b.B != B) {
+        s->g_world = 0;                                   // the gather areas were sized for the old batch (qc_set_gather again)
         cudaFree(b.psi); cudaFree(b.step); cudaFree(b.flags); b = BatchView();
         QC_CUDA(cudaMalloc(&b.psi, sizeof(double2) * (size_t)B * s->model.n));
         QC_CUDA(cudaMalloc(&b.step, sizeof(long long) * B));
@@ -187,8 +226,10 @@ extern "C" int qc_set_state(qc_sim* s, const double* psi, int on_device, void* s
     if (!s->batch.psi) return fail(QC_ERR_STATE, "qc_set_batch first");
     if (!psi) return fail(QC_ERR_ARG, "null state");
     const size_t bytes = sizeof(double2) * (size_t)s->batch.B * s->model.n;
+    rc = enter_user(s, stream); if (rc) return rc;
     QC_CUDA(cudaMemcpyAsync(s->batch.psi, psi, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, (cudaStream_t)stream));
     QC_CUDA(cudaMemsetAsync(s->batch.flags, 0, (size_t)s->batch.B, (cudaStream_t)stream));
+    rc = leave_user(s, stream); if (rc) return rc;
     if (!on_device) QC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return QC_OK;
 }
@@ -197,22 +238,28 @@ extern "C" int qc_get_state(const qc_sim* s, double* psi, int on_device, void* s
     if (!s->batch.psi) return fail(QC_ERR_STATE, "qc_set_batch first");
     if (!psi) return fail(QC_ERR_ARG, "null state");
     const size_t bytes = sizeof(double2) * (size_t)s->batch.B * s->model.n;
+    rc = enter_user(const_cast<qc_sim*>(s), stream); if (rc) return rc;
     QC_CUDA(cudaMemcpyAsync(psi, s->batch.psi, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    rc = leave_user(const_cast<qc_sim*>(s), stream); if (rc) return rc;
     if (!on_device) QC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return QC_OK;
 }
 extern "C" int qc_set_seed(qc_sim* s, uint64_t seed, int64_t traj_offset) {
     int rc = use_device(s); if (rc) return rc;
     s->seed = seed; s->traj_offset = traj_offset;
-    if (s->batch.step) QC_CUDA(cudaMemset(s->batch.step, 0, sizeof(long long) * s->batch.B));
-    QC_CUDA(cudaMemset(s->one.step, 0, sizeof(long long)));
+    rc = enter_host(s); if (rc) return rc;               // ordered after every step the caller has enqueued through this handle
+    if (s->batch.step) QC_CUDA(cudaMemsetAsync(s->batch.step, 0, sizeof(long long) * s->batch.B, s->stream));
+    QC_CUDA(cudaMemsetAsync(s->one.step, 0, sizeof(long long), s->stream));
+    rc = leave_host(s); if (rc) return rc;
+    QC_CUDA(cudaStreamSynchronize(s->stream));
     return QC_OK;
 }
 extern "C" int qc_clear_flags(qc_sim* s, void* stream) {
     int rc = use_device(s); if (rc) return rc;
     if (!s->batch.flags) return fail(QC_ERR_STATE, "qc_set_batch first");
+    rc = enter_user(s, stream); if (rc) return rc;
     QC_CUDA(cudaMemsetAsync(s->batch.flags, 0, (size_t)s->batch.B, (cudaStream_t)stream));
-    return QC_OK;
+    return leave_user(s, stream);
 }
 
 static int stage_in(qc_sim* s, const double* host, size_t count, double** dev_out, cudaStream_t st) {
@@ -238,11 +285,12 @@ extern "C" int qc_init_packets(qc_sim* s, const double* wavenumber, const double
         QC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
         dk = wavenumber ? d : nullptr; dm = mean ? d + B : nullptr;
     }
+    rc = enter_user(s, stream); if (rc) return rc;
     rc = launch_init_packets(s->batch.psi, (int)B, s->model.n, s->model.cfg.grid_size, s->model.half, dk, dm, stdv, stream);
     if (rc) return fail(rc, "init kernel launch failed");
     s->launches++;
     QC_CUDA(cudaMemsetAsync(s->batch.flags, 0, (size_t)B, (cudaStream_t)stream));
-    return QC_OK;
+    return leave_user(s, stream);
 }
 extern "C" int qc_init_fock(qc_sim* s, const double* alpha, int on_device, void* stream) {
     int rc = use_device(s); if (rc) return rc;
@@ -250,11 +298,12 @@ extern "C" int qc_init_fock(qc_sim* s, const double* alpha, int on_device, void*
     if (!s->batch.psi) return fail(QC_ERR_STATE, "qc_set_batch first");
     const double* da = alpha;
     if (alpha && !on_device) { double* d = nullptr; rc = stage_in(s, alpha, 2 * (size_t)s->batch.B, &d, (cudaStream_t)stream); if (rc) return rc; da = d; }
+    rc = enter_user(s, stream); if (rc) return rc;
     rc = launch_init_fock(s->batch.psi, (int)s->batch.B, s->model.n, da, stream);
     if (rc) return fail(rc, "init kernel launch failed");
     s->launches++;
     QC_CUDA(cudaMemsetAsync(s->batch.flags, 0, (size_t)s->batch.B, (cudaStream_t)stream));
-    return QC_OK;
+    return leave_user(s, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -272,6 +321,8 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
         if (&b == &s->batch) s->info = b.plan.info;
     }
     const LaunchPlan& pl = b.plan;
+    const bool resident = (b.psi == s->batch.psi);
+    if (resident) { int rc = enter_user(s, stream); if (rc) return rc; }
     StepParams p; memset(&p, 0, sizeof(p));
     if (pl.vglobal) {
         const size_t ntraj = (size_t)((b.B + pl.T - 1) / pl.T + s->cap_slots) * pl.T;
@@ -303,7 +354,7 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
     if (s->g_world > 0 && &b == &s->batch && !moments_only) {          // fused result exchange: rows + sequence flag to every rank
         if (!moments || !aux || !flags) return fail(QC_ERR_ARG, "qc_set_gather is active: qc_step needs moments, aux and flags buffers");
         if (nsub_traj) return fail(QC_ERR_ARG, "qc_set_gather is active: per-trajectory substep budgets are not exchanged");
-        p.g_world = s->g_world; p.g_rank = s->g_rank; p.g_seq = ++s->g_seq; p.g_done = s->d_gdone;
+        p.g_world = s->g_world; p.g_rank = s->g_rank; p.g_seq = s->g_seq + 1; p.g_done = s->d_gdone;
         for (int r = 0; r < s->g_world; r++) { p.g_peer[r] = s->g_peer[r]; p.g_flag[r] = s->g_flag[r]; }
     }
 #ifdef QC_DEBUG_HOOKS
@@ -323,6 +374,8 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
     int rc = launch_step(pl, p, stream, err);
     if (rc) return fail(rc, err);
     s->launches++;
+    if (p.g_world > 0) s->g_seq = p.g_seq;               // only a launch that really happened advances the sequence (peers wait for it)
+    if (resident) { rc = leave_user(s, stream); if (rc) return rc; }
 #ifdef QC_DEBUG_HOOKS
     if (timers) {
         cudaStreamSynchronize((cudaStream_t)stream);
@@ -398,6 +451,7 @@ extern "C" int qc_set_gather(qc_sim* s, int32_t rank, int32_t world, void* const
     if (world < 1 || world > QC_MAX_PEERS || rank < 0 || rank >= world || !gather_ptrs || !flag_ptrs) return fail(QC_ERR_ARG, "qc_set_gather: need 1 <= world <= 8, 0 <= rank < world and the pointer arrays");
     for (int r = 0; r < world; r++) if (!gather_ptrs[r] || !flag_ptrs[r]) return fail(QC_ERR_ARG, "qc_set_gather: NULL peer pointer");
     if (!s->d_gdone) { QC_CUDA(cudaMalloc(&s->d_gdone, sizeof(unsigned int))); QC_CUDA(cudaMemset(s->d_gdone, 0, sizeof(unsigned int))); }
+    if (!s->d_gerr) { QC_CUDA(cudaMalloc(&s->d_gerr, sizeof(unsigned int))); QC_CUDA(cudaMemset(s->d_gerr, 0, sizeof(unsigned int))); }
     for (int r = 0; r < world; r++) { s->g_peer[r] = (double*)gather_ptrs[r]; s->g_flag[r] = (unsigned long long*)flag_ptrs[r]; }
     s->g_world = world; s->g_rank = rank;
     return QC_OK;
@@ -408,8 +462,16 @@ extern "C" uint64_t qc_gather_seq(const qc_sim* s) { return s ? s->g_seq : 0; }
 extern "C" int qc_gather_wait(qc_sim* s, uint64_t seq, void* stream) {
     int rc = use_device(s); if (rc) return rc;
     if (s->g_world <= 0) return fail(QC_ERR_STATE, "qc_gather_wait: qc_set_gather first");
-    if (launch_gather_wait(s->g_flag[s->g_rank], s->g_world, seq, stream)) return fail(QC_ERR_CUDA, "wait kernel launch failed");
+    if (launch_gather_wait(s->g_flag[s->g_rank], s->g_world, seq, s->d_gerr, stream)) return fail(QC_ERR_CUDA, "wait kernel launch failed");
     s->launches++;
+    return QC_OK;
+}
+
+extern "C" int qc_gather_error(qc_sim* s, uint32_t* rank_mask) {
+    int rc = use_device(s); if (rc) return rc;
+    if (!rank_mask) return fail(QC_ERR_ARG, "null output");
+    *rank_mask = 0;
+    if (s->d_gerr) QC_CUDA(cudaMemcpy(rank_mask, s->d_gerr, sizeof(unsigned int), cudaMemcpyDeviceToHost));
     return QC_OK;
 }
 
@@ -435,11 +497,13 @@ extern "C" int qc_step_forces(qc_sim* s, const double* force_host, const double*
     rc = ensure_out(s); if (rc) return rc;
     const int64_t B = s->batch.B;
     std::vector<int32_t> slots(B);
+    s->call_id++;
     for (int64_t i = 0; i < B; i++) {
         const double F = force_host[i];
         int slot = -1;
         for (int k = 0; k < s->n_slots; k++) if (s->slot_force[k] == F) { slot = k; break; }
         if (slot < 0) { rc = add_slot(s, F, &slot); if (rc) return rc; }
+        s->slot_stamp[slot] = s->call_id;
         slots[i] = slot;
     }
     QC_CUDA(cudaMemcpyAsync(s->d_action, slots.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, (cudaStream_t)stream));
@@ -455,6 +519,7 @@ extern "C" int qc_step_host(qc_sim* s, const int32_t* action, const double* nois
     const int64_t B = s->batch.B; const int K = s->model.K;
     if (n_sub <= 0) n_sub = s->model.cfg.n_sub;
     cudaStream_t st = s->stream;
+    rc = enter_host(s); if (rc) return rc;               // behind whatever the caller enqueued on its own streams through this handle
     QC_CUDA(cudaMemcpyAsync(s->d_action, action, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
     double* dn = nullptr;
     rc = stage_in(s, noise, (size_t)B * n_sub * 2, &dn, st); if (rc) return rc;
@@ -463,6 +528,7 @@ extern "C" int qc_step_host(qc_sim* s, const int32_t* action, const double* nois
     if (moments) QC_CUDA(cudaMemcpyAsync(moments, s->d_mom, sizeof(double) * B * K, cudaMemcpyDeviceToHost, st));
     if (aux) QC_CUDA(cudaMemcpyAsync(aux, s->d_aux, sizeof(double) * B * QC_AUX_COUNT, cudaMemcpyDeviceToHost, st));
     if (flags) QC_CUDA(cudaMemcpyAsync(flags, s->d_flagout, (size_t)B, cudaMemcpyDeviceToHost, st));
+    rc = leave_host(s); if (rc) return rc;
     QC_CUDA(cudaStreamSynchronize(st));
     return QC_OK;
 }
@@ -480,7 +546,8 @@ extern "C" int qc_get_moments(qc_sim* s, double* moments, double* aux, void* str
 // single-trajectory shims
 
 static int find_or_add_slot(qc_sim* s, double F, int* slot) {
-    for (int k = 0; k < s->n_slots; k++) if (s->slot_force[k] == F) { *slot = k; return QC_OK; }
+    s->call_id++;
+    for (int k = 0; k < s->n_slots; k++) if (s->slot_force[k] == F) { *slot = k; s->slot_stamp[k] = s->call_id; return QC_OK; }
     return add_slot(s, F, slot);
 }
 

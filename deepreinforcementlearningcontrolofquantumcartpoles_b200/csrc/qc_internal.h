@@ -48,6 +48,7 @@ int build_model(const qc_config& cfg, Model& m, std::string& err);
 // ------------------------------------------------------------------------------------------------------
 // Kernel parameters (passed by value).
 #define QC_MAX_PEERS 8      // ranks of one NVSwitch node
+#define QC_GATHER_BUFS 4    // result-exchange buffers (sequence number mod 4): lets a rank consume step k-1 while step k runs (see qcart.h)
 
 struct StepParams {
     // geometry
@@ -106,7 +107,7 @@ int launch_step(const LaunchPlan& plan, const StepParams& p, void* stream, std::
 int launch_bin(const int32_t* slot, int B, int n_slots, int T, int32_t* order, int32_t* order_count, void* stream);
 int launch_init_packets(double2* psi, int B, int n, double h, int half, const double* k, const double* mean, double stdv, void* stream);
 int launch_init_fock(double2* psi, int B, int n, const double* alpha, void* stream);
-int launch_gather_wait(const unsigned long long* flags, int world, unsigned long long seq, void* stream);
+int launch_gather_wait(const unsigned long long* flags, int world, unsigned long long seq, unsigned int* err_flag, void* stream);
 int measure_fp64_peak(int device, double* flops);
 int measure_smem_peak(int device, double* bps);
 

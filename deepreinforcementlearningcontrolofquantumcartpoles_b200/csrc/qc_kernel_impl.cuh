@@ -588,9 +588,9 @@ __device__ __forceinline__ void publish_row(const StepParams& p, int traj, int l
         if (lane < p.K) v = p.moments[(size_t)traj * p.K + lane];
         else if (lane < p.K + QC_AUX_COUNT) v = p.aux[(size_t)traj * QC_AUX_COUNT + (lane - p.K)];
         else v = (double)p.flags_out[traj];
-        const size_t row = (size_t)(p.g_seq & 1ull) * (size_t)p.g_world * p.B + (size_t)p.g_rank * p.B + traj;
+        const size_t row = (size_t)(p.g_seq & (QC_GATHER_BUFS - 1)) * (size_t)p.g_world * p.B + (size_t)p.g_rank * p.B + traj;
         for (int r = 0; r < p.g_world; r++) p.g_peer[r][row * cols + lane] = v;
-        __threadfence_system();                       // the rows must be visible system-wide before the flag below
+        // no fence here: publish_done's CTA barrier + system-scope fence + release store order every row of the CTA before the flag
     }
 }
 // Last CTA of the launch: publish the sequence number in slot `rank` of every rank's flag array (release at system scope).

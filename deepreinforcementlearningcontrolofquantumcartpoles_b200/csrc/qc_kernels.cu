@@ -272,14 +272,22 @@ __global__ void fp64_peak_kernel(double* out, int iters, double seed) {
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 // Consumer side of the fused result exchange: thread r spins (acquire, system scope) until rank r has published sequence number `seq`.
-__global__ void gather_wait_kernel(const unsigned long long* __restrict__ flags, int world, unsigned long long seq) {
+// The spin is bounded (~2 s): a peer that died must not hang this GPU; on time-out bit r of *err_flag is set (qc_gather_error reports it).
+__global__ void gather_wait_kernel(const unsigned long long* __restrict__ flags, int world, unsigned long long seq, unsigned int* err_flag) {
     if ((int)threadIdx.x < world) {
         unsigned long long v;
-        do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory"); if (v < seq) __nanosleep(200); } while (v < seq);
+        long long spins = 0;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+            if (v >= seq) break;
+            __nanosleep(200);
+            if ((++spins & 1023) == 0 && clock64() - t0 > 4000000000ll) { atomicOr(err_flag, 1u << threadIdx.x); break; }
+        }
     }
 }
-int launch_gather_wait(const unsigned long long* flags, int world, unsigned long long seq, void* stream) {
-    gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, world, seq);
+int launch_gather_wait(const unsigned long long* flags, int world, unsigned long long seq, unsigned int* err_flag, void* stream) {
+    gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, world, seq, err_flag);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

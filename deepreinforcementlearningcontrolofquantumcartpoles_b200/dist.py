@@ -79,6 +79,8 @@ class FusedGather:
     Single-process use (tests; several sims acting as ranks on one device): fgs = FusedGather.local_group(sims)
     """
 
+    NBUF = 4        # QC_GATHER_BUFS: buffer = sequence number mod 4 (allows "enqueue step k, then consume step k-1", see include/qcart.h)
+
     def __init__(self, sim, rank, world, _wire=True):
         import ctypes as C
         from . import _lib as L
@@ -89,7 +91,7 @@ class FusedGather:
         self.gather_ptr = self.flag_ptr = None
         err = None
         try:
-            self.gather_ptr, self.gather_handle = self._alloc(2 * self.rows * self.cols * 8)
+            self.gather_ptr, self.gather_handle = self._alloc(self.NBUF * self.rows * self.cols * 8)
             self.flag_ptr, self.flag_handle = self._alloc(max(self.world, 1) * 8)
             self.peer_g[self.rank], self.peer_f[self.rank] = self.gather_ptr, self.flag_ptr
         except Exception as e:                      # noqa: BLE001  (still take part in the handle exchange below: it is a collective)
@@ -98,12 +100,15 @@ class FusedGather:
             if self.world > 1:
                 import torch.distributed as dist
                 handles = [None] * self.world
-                dist.all_gather_object(handles, None if err is not None else (self.gather_handle, self.flag_handle))
+                dist.all_gather_object(handles, None if err is not None else (self.gather_handle, self.flag_handle, int(sim.B)))
                 if err is None and any(h is None for h in handles):
                     err = RuntimeError("a peer rank could not allocate its gather area")
+                if err is None and any(h[2] != int(sim.B) for h in handles):
+                    # the kernel addresses row rank * B + b in EVERY rank's area: unequal shards would store out of bounds in peer memory
+                    err = ValueError("FusedGather needs the same batch size on every rank, got %s (pad the shards, e.g. dist.shard_range on a multiple of world)" % [h[2] for h in handles])
                 if err is None:
                     try:
-                        for r, (hg, hf) in enumerate(handles):
+                        for r, (hg, hf, _b) in enumerate(handles):
                             if r != self.rank:
                                 self.peer_g[r], self.peer_f[r] = self._open(hg), self._open(hf)
                     except Exception as e:          # noqa: BLE001
@@ -138,6 +143,8 @@ class FusedGather:
     @classmethod
     def local_group(cls, sims):
         """Several sims on the devices of ONE process play the ranks (no IPC: the pointers are passed directly)."""
+        if len({int(s.B) for s in sims}) != 1:
+            raise ValueError("FusedGather needs the same batch size on every rank")
         fgs = [cls(s, r, len(sims), _wire=False) for r, s in enumerate(sims)]
         for a in fgs:
             for r, b in enumerate(fgs):
@@ -152,11 +159,17 @@ class FusedGather:
         """Enqueue (on the current stream) the wait for every rank's rows of control step `seq` (default: the last qc_step of this rank)."""
         self._L.check(self.lib.qc_gather_wait(self.sim.h, self.seq() if seq is None else int(seq), self.sim._stream()))
 
+    def failed_ranks(self):
+        """Ranks a wait() gave up on (bounded spin of the consumer kernel); synchronises the device.  Empty list = healthy."""
+        mask = self._C.c_uint32(0)
+        self._L.check(self.lib.qc_gather_error(self.sim.h, self._C.byref(mask)))
+        return [r for r in range(self.world) if mask.value >> r & 1]
+
     def block(self, seq=None):
         """[world * B, K + 5] float64 view of the buffer holding control step `seq`; valid after wait(seq) in stream order."""
         import torch
         seq = self.seq() if seq is None else int(seq)
-        off = (seq & 1) * self.rows * self.cols * 8
+        off = (seq % self.NBUF) * self.rows * self.cols * 8
         return torch.as_tensor(_DeviceArray(self.gather_ptr + off, (self.rows, self.cols), "<f8"), device="cuda:%d" % self.sim.device)
 
     def close(self, collective=True):

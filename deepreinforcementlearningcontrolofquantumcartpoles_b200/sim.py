@@ -14,6 +14,7 @@ def make_config(params, device=0):
     """dict (see configs.py) -> QcConfig.  Mirrors what the reference fixes through setupC.py -D macros and arguments.py."""
     v = params["variant"]
     c = L.QcConfig()
+    c.struct_size = C.sizeof(L.QcConfig)
     c.variant = _VARIANT[v]
     if c.variant == L.QC_QUARTIC:
         c.n = 0

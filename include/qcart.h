@@ -42,6 +42,9 @@ enum {
 /* What the reference bakes in at compile time with -D macros (Q/setupC.py:55, H/setupC.py:49) plus what it
  * passes per call (dt, gamma; Q:493-497) and the controller's force grid (Q/RL.py:82-84,108-112). */
 typedef struct qc_config {
+    uint32_t struct_size;   /* MUST be sizeof(qc_config) of the header the caller was built against (qc_config_size() returns the library's):
+                               qc_create rejects any other value with QC_ERR_ARG, so a binding whose struct is out of date fails loudly
+                               instead of passing a short struct (fields were appended between versions) */
     int32_t variant;        /* QC_HARMONIC / QC_INV_HARMONIC (Fock basis) or QC_QUARTIC (position grid; inverted quartic = lambda<0) */
     int32_t n;              /* Fock: n_max+1.  Grid: 0 = derive x_n = 2*int(x_max/grid_size+0.5)+1 like Q:21 */
     double x_max;           /* grid: X_MAX */
@@ -66,6 +69,9 @@ typedef struct qc_config {
 } qc_config;
 
 typedef struct qc_sim qc_sim;   /* opaque; handles are independent (no globals) and thread-safe per handle */
+
+/* sizeof(qc_config) as compiled into the library (bindings assert it against their own struct before qc_create). */
+uint32_t qc_config_size(void);
 
 /* Thread-local message of the last failing call. */
 const char *qc_last_error(void);
@@ -125,12 +131,15 @@ int qc_init_fock(qc_sim *sim, const double *alpha_re_im, int on_device, void *st
  *   nsub_traj [B] per-trajectory substep budget (<= n_sub), or NULL                (device)
  *   moments  [B][K] or NULL,  aux [B][QC_AUX_COUNT] or NULL,  flags [B] uint8 or NULL (device, outputs)
  *   q_out    [B][n_sub] measurement outcomes q (Q:577) or NULL;  xmean_out likewise (<x> before each substep)
- * All device work is ordered on `stream` (a cudaStream_t; NULL = legacy default stream). */
+ * All device work is ordered on `stream` (a cudaStream_t; NULL = legacy default stream).  The host-buffer entry points (qc_step_host,
+ * qc_set_seed, the *1 shims) run on a private stream of the handle; the library orders them against the caller's streams with events (a
+ * stream-ordered call waits for the last host-buffer call and vice versa), so mixing both kinds on one handle needs no extra synchronisation. */
 int qc_step(qc_sim *sim, const int32_t *action, const double *noise, int n_sub, const int32_t *nsub_traj,
             double *moments, double *aux, uint8_t *flags, double *q_out, double *xmean_out, void *stream);
 
 /* Same, with arbitrary per-trajectory forces instead of level indices (HOST array; the reference accepts any double F,
- * Q:493-497).  Distinct values are factorised on demand and cached. */
+ * Q:493-497).  Distinct values are factorised on demand and cached in 256 on-demand slots next to the n_levels controller forces; when they are
+ * full the least recently used one is replaced (that costs a device synchronisation).  More than 256 new values in ONE call: QC_ERR_UNSUPPORTED. */
 int qc_step_forces(qc_sim *sim, const double *force_host, const double *noise, int n_sub, const int32_t *nsub_traj,
                    double *moments, double *aux, uint8_t *flags, double *q_out, double *xmean_out, void *stream);
 
@@ -170,8 +179,11 @@ void qc_philox_normals(uint64_t seed, uint64_t traj, uint64_t step, double *out2
  * rank*B + b of the current buffer of EVERY rank's gather area -- ordinary stores to CUDA-IPC mapped peer memory over NVLink /
  * NVSwitch, issued from the kernel's epilogue -- and its last CTA publishes a sequence number in every rank's flag array
  * (st.release.sys).  qc_gather_wait enqueues the consumer side: a one-warp kernel that spins (ld.acquire.sys) until all ranks have
- * published that sequence number.  Gather area per rank: double[2][world * B][K + 5] (buffers alternate with the parity of the sequence
- * number), flag array: uint64[world], both zero-initialised by qc_peer_alloc.
+ * published that sequence number (bounded: after ~2 s without the flag it gives up and records the missing ranks, see qc_gather_error).
+ * Gather area per rank: double[4][world * B][K + 5] (buffer = sequence number mod 4), flag array: uint64[world], both zero-initialised by
+ * qc_peer_alloc.  Four buffers allow the overlapped schedule: enqueue step k, THEN wait for / consume step k-1 -- a rank that runs ahead
+ * writes buffer (k+1) mod 4 or (k+2) mod 4 while the slowest rank may still read (k-1) mod 4; it cannot reach step k+3 (the next user of that
+ * buffer) before every rank has published step k+1, i.e. has consumed step k-1 in stream order.  Every rank must use the same B.
  *
  * qc_peer_alloc / qc_peer_open wrap cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle; the 64-byte handles travel between the
  * rank processes by any host channel (the Python mirror uses torch.distributed.all_gather_object). */
@@ -182,8 +194,10 @@ int qc_peer_close(int32_t device, void *ptr);
 /* gather_ptrs[r] / flag_ptrs[r]: rank r's gather area / flag array as seen from THIS process (own allocation for r == rank).
  * world = 0 switches the exchange off.  While it is on, qc_step requires moments, aux and flags output buffers. */
 int qc_set_gather(qc_sim *sim, int32_t rank, int32_t world, void *const *gather_ptrs, void *const *flag_ptrs);
-uint64_t qc_gather_seq(const qc_sim *sim);        /* sequence number of the last qc_step (1, 2, ...); its rows are in buffer seq & 1 */
+uint64_t qc_gather_seq(const qc_sim *sim);        /* sequence number of the last qc_step (1, 2, ...); its rows are in buffer seq & 3 */
 int qc_gather_wait(qc_sim *sim, uint64_t seq, void *stream);
+/* Bit r set: a qc_gather_wait gave up waiting for rank r (peer died or never stepped).  Synchronises the device. */
+int qc_gather_error(qc_sim *sim, uint32_t *rank_mask);
 
 /* Micro-benchmarks used by bench.py for the roofline denominators (not in MEASURED_PEAKS.json):
  * dependent-free DFMA loop on all SMs -> FLOP/s; conflict-free 128-bit shared-memory load loop -> bytes/s. */

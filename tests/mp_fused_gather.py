@@ -24,14 +24,21 @@ def main():
     g = torch.Generator(device="cuda:%d" % local_rank)
     g.manual_seed(100 + rank)
     ok = True
-    for step in range(1, 5):
+    refs = {}
+    for step in range(1, 9):
         act = torch.randint(0, params["n_levels"], (B,), device="cuda:%d" % local_rank, dtype=torch.int32, generator=g)
         out = sim.step(act)
-        fg.wait()
-        ref = qdist.all_gather_block(qdist.pack_block(out["moments"], out["aux"], out["flags"]), world)
-        torch.cuda.synchronize()
-        ok = ok and fg.seq() == step and bool(torch.equal(fg.block(), ref))
-        ok = ok and bool(torch.equal(fg.block()[rank * B:(rank + 1) * B, :sim.K], out["moments"]))
+        refs[step] = qdist.all_gather_block(qdist.pack_block(out["moments"], out["aux"], out["flags"]), world)
+        if step <= 4:                                      # plain schedule
+            fg.wait()
+            torch.cuda.synchronize()
+            ok = ok and fg.seq() == step and bool(torch.equal(fg.block(), refs[step]))
+            ok = ok and bool(torch.equal(fg.block()[rank * B:(rank + 1) * B, :sim.K], out["moments"]))
+        else:                                              # overlapped schedule: consume step k-1 behind step k, no host sync in between
+            fg.wait(step - 1)
+            ok_dev = torch.equal(fg.block(step - 1), refs[step - 1])
+            ok = ok and bool(ok_dev)
+    ok = ok and fg.failed_ranks() == []
     fg.close()
     flag = torch.tensor([1 if ok else 0], device="cuda:%d" % local_rank)
     torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)

@@ -180,7 +180,8 @@ def test_env_reset_step_protocol(task):
 @pytest.mark.parametrize("task", ["quartic", "harmonic"])
 def test_fused_result_exchange_single_process_ranks(task):
     """qc_set_gather: three sims on one device play three ranks; every rank's gather area ends up with all rows, in rank order, equal to
-    pack_block of each rank's own outputs, for two consecutive control steps (both buffers), and the wait kernel lets the stream pass."""
+    pack_block of each rank's own outputs, for six consecutive control steps (four buffers, plain and overlapped consumer schedule); the
+    bounded wait reports ranks that never publish; unequal batch sizes are refused."""
     import torch
     from deepreinforcementlearningcontrolofquantumcartpoles_b200 import dist as qdist
     params = configs.PRESETS[task](n_sub=8)
@@ -190,18 +191,30 @@ def test_fused_result_exchange_single_process_ranks(task):
         s.set_state(initial_states(params, B, seed=10 + r))
     fgs = qdist.FusedGather.local_group(sims)
     g = torch.Generator(device="cuda"); g.manual_seed(1)
-    for step in range(1, 3):
+    expect = {}
+    for step in range(1, 7):                                   # six steps: every one of the four buffers is reused
         packed = []
         for s in sims:
             act = torch.randint(0, params["n_levels"], (B,), device="cuda", dtype=torch.int32, generator=g)
             out = s.step(act)
             packed.append(qdist.pack_block(out["moments"], out["aux"], out["flags"]))
-        expect = torch.cat(packed, dim=0)
+        expect[step] = torch.cat(packed, dim=0)
         for fg in fgs:
             assert fg.seq() == step
-            fg.wait()
-            torch.cuda.synchronize()
-            assert torch.equal(fg.block(), expect)
+            if step % 2 == 1:                                  # plain schedule: wait for the step just enqueued
+                fg.wait()
+                torch.cuda.synchronize()
+                assert torch.equal(fg.block(), expect[step])
+            else:                                              # overlapped schedule: consume step k-1 behind step k (still intact in its buffer)
+                fg.wait(step - 1)
+                torch.cuda.synchronize()
+                assert torch.equal(fg.block(step - 1), expect[step - 1])
+    assert all(fg.failed_ranks() == [] for fg in fgs)
+    fgs[0].wait(fgs[0].seq() + 1)                              # a step nobody will ever publish: the consumer gives up (bounded spin) and says who
+    torch.cuda.synchronize()
+    assert fgs[0].failed_ranks() == [0, 1, 2]
+    with pytest.raises(ValueError):                            # unequal shards would address peer memory out of bounds
+        qdist.FusedGather.local_group([sims[0], BatchedSim(params, batch=B + 1)])
     with pytest.raises(L.QcartError):                      # the exchange needs all three output buffers
         L.check(sims[0].lib.qc_step(sims[0].h, act.data_ptr(), None, 8, None, None, None, None, None, None, sims[0]._stream()))
     for fg in fgs:
