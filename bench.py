@@ -7,7 +7,11 @@
 A "step" = one control step of every trajectory of the batch: n_sub SSE substeps + moment extraction + flags, ONE kernel
 launch per rank.  Workload at N=1 = BASELINE.json configs[1]: quartic oscillator cooling, 1024 trajectories (N=171 grid
 points, 80 substeps per control step); N>1 = the same per-GPU batch on every rank (weak scaling), trajectories sharded with no
-data-path collective plus the all-gather of the moment/reward block.  Prints ONE JSON line (rank 0).
+data-path collective plus the exchange of the moment/reward block (stored by the SSE kernel into every rank's peer memory).
+Inside the same driver-timed run the line also carries, under "extra", the other BASELINE configurations measured the same way
+(CUDA events, L2 flushed between steps, max over ranks): config3 (inverted harmonic, 8192 trajectories/GPU), config4 (inverted
+quartic, 8192 trajectories/GPU = 65,536 on 8 GPUs, with its own roofline) and, at N=1, three points of the grid-size sweep.
+Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -79,20 +83,23 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_port_rate(task, params, n_traj_per_thread, threads, fast=True):
+def cpu_port_rate(task, params, n_traj_per_thread, threads, fast=True, constant_force=False):
     """The oracle (CPU restatement of the reference algorithm) timed the way the reference runs: one trajectory per
     single-threaded worker, `threads` workers.  Returns (traj-control-steps/s, seconds)."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from common import oracle_for, initial_states, level_force
+    from common import oracle_for, level_force
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200.states import initial_states
     psi0 = initial_states(params, threads * n_traj_per_thread, seed=3)
     rng = np.random.default_rng(7)
     noise = rng.standard_normal((threads * n_traj_per_thread, params["n_sub"], 2))
     acts = rng.integers(0, params["n_levels"], threads * n_traj_per_thread)
+    if constant_force:                       # every worker keeps one force: reset_ab (LU + C = dt^3/12 H0^2 ...) runs once, outside the measurement
+        acts[:] = 13
     oracles = [oracle_for(params, fast=fast) for _ in range(threads)]
     for t, o in enumerate(oracles):      # warm the 21-force cache is NOT done: the reference refactorises on every force change too
         st = psi0[t * n_traj_per_thread].copy()
-        o.run(st, params["dt"], 0.0, params["gamma"], noise[0][:2])
+        o.run(st, params["dt"], level_force(params, 13) if constant_force else 0.0, params["gamma"], noise[0][:2])
 
     def work(t):
         o = oracles[t]
@@ -121,7 +128,8 @@ def reference_build_call_pattern(task, params, n_ctrl=3):
         if not available(task):
             return None
         sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from common import initial_states, level_force
+        from common import level_force
+        from deepreinforcementlearningcontrolofquantumcartpoles_b200.states import initial_states
         ref = RefModule(task)
         psi = initial_states(params, 1, seed=5)[0]
         rng = np.random.default_rng(1)
@@ -160,7 +168,9 @@ def run_reference(args, task, params):
     line = {"impl": "reference", "metric": "trajectory-control-steps/sec", "value": value, "unit": "traj-control-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(task, args.batch, n, params["n_sub"]), "sample": "%d trajectories x 1 control step per timed step" % (cores * per_thread)},
+            "config": {"workload": workload_name(task, args.batch, n, params["n_sub"]), "task": task, "trajectories_per_gpu": args.batch, "global_trajectories": args.gpus * args.batch,
+                       "state_len": n, "n_sub": params["n_sub"]},
+            "measurement": {"sample": "%d trajectories x 1 control step per timed step (bounded sample of the workload above; the rate is per unit of work)" % (cores * per_thread)},
             "cpu_baseline": {"value": value, "unit": "traj-control-steps/s", "cores": cores, "kind": "port",
                              "sample": "%d threads x %d trajectories x 1 control step (%d substeps, N=%d), oracle/sse_oracle.c -Ofast, per-force refactorisation included" % (cores, per_thread, params["n_sub"], n)},
             "e2e": {"value": value, "unit": "traj-control-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -214,6 +224,62 @@ def workload_name(task, B, n, n_sub):
     return "%s SSE control step: %d trajectories/GPU, N=%d complex128, %d substeps/control step, 21 force levels" % (task, B, n, n_sub)
 
 
+def median5(per_step_ms):
+    """Median of the mean step time of 5 equal chunks of the timed region (SURVEY.md 8d asks for a median of 5)."""
+    k = len(per_step_ms)
+    if k < 5:
+        return None
+    c = k // 5
+    means = sorted(sum(per_step_ms[i * c:(i + 1) * c]) / c for i in range(5))
+    return means[2]
+
+
+def measure_extra(task, params, B, steps, warmup, rank, world, local_rank, flush_buf, fp64_peak, tag):
+    """One more workload measured like the headline: device-resident inputs, one launch per control step, per-step CUDA events with the L2
+    flushed in between, max over ranks.  No exchange (the step alone); every rank runs its own shard of B trajectories."""
+    import numpy as np
+    import torch
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200 import BatchedSim, _lib as L
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200.states import initial_states
+    dev = "cuda:%d" % local_rank
+    n = state_len(params)
+    sim = BatchedSim(params, batch=B, device=local_rank, seed=1, traj_offset=rank * B)
+    psi0 = initial_states(params, min(B, 64), seed=100 + rank)
+    sim.set_state(np.tile(psi0, ((B + psi0.shape[0] - 1) // psi0.shape[0], 1))[:B])
+    g = torch.Generator(device=dev); g.manual_seed(1000 + rank)
+    actions = torch.randint(0, params["n_levels"], (warmup + steps, B), device=dev, dtype=torch.int32, generator=g)
+    out = sim.alloc_outputs()
+    for i in range(warmup):
+        sim.step(actions[i], out=out)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    l0 = sim.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        if flush_buf is not None:
+            flush_buf.zero_()
+        evs[i][0].record()
+        sim.step(actions[warmup + i], out=out)
+        evs[i][1].record()
+    torch.cuda.synchronize()
+    per = [a.elapsed_time(b) for a, b in evs]
+    ms = sum(per) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    fpu = flops_per_unit(task, n, params["n_sub"])
+    ach = B / (ms * 1e-3) * fpu / 1e12
+    rec = {"workload": workload_name(task, B, n, params["n_sub"]) + (" [%s]" % tag if tag else ""), "value": world * B / (ms * 1e-3), "unit": "traj-control-steps/s",
+           "n_gpus": world, "global_trajectories": world * B, "steps": steps, "warmup": warmup, "ms_per_step": ms, "gpu_launches": int(sim.launch_count() - l0),
+           "max_norm_deviation": float((out["aux"][:, L.QC_AUX_NORM] - 1).abs().max().item()),
+           "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": ach / (fp64_peak / 1e12), "flops_per_unit": fpu,
+                        "kernel": sim.kernel_info(), "hbm_algorithmic_GBps": B * (32.0 * n + 8.0 * sim.K + 37) / (ms * 1e-3) / 1e9}}
+    del sim
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -228,6 +294,7 @@ def main():
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N>1: how the per-step result block reaches every rank: stored by the SSE kernel into peer memory (fused) or pack + NCCL all-gather")
     ap.add_argument("--no-closed-loop", action="store_true", help="skip the policy + experience-row closed-loop measurement (N=1 only)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra BASELINE configurations (config3, config4, sweep)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -241,8 +308,7 @@ def main():
     import numpy as np
     import torch
     from deepreinforcementlearningcontrolofquantumcartpoles_b200 import BatchedSim, measure_peaks, dist as qdist, _lib as L
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from common import initial_states
+    from deepreinforcementlearningcontrolofquantumcartpoles_b200.states import initial_states
 
     # stdout carries exactly ONE line, the JSON record: libraries that write to file descriptor 1 (NCCL prints its version there) are
     # diverted to stderr for the whole run
@@ -279,24 +345,28 @@ def main():
                 fused.close(collective=False)       # never used: no barriers (the failing ranks have nothing to close)
             fused = None
         gather_mode = "fused" if fused is not None else "nccl (fused unavailable)"
+    consumed = torch.zeros(1, dtype=torch.float64, device=dev)
 
-    def exchange():
-        """Every rank obtains the [world*B, K+5] result block of this control step."""
+    def exchange(first_of_run=False):
+        """Every rank obtains the [world*B, K+5] result block of a control step and reads it (the learner's consumption, here a checksum).
+        Fused: the rows of step k were stored by the kernel itself; the wait for step k-1 is enqueued BEHIND the launch of step k (four
+        buffers make that safe, include/qcart.h), so a rank never idles until the slowest rank has finished the current step."""
         if fused is not None:
-            fused.wait()                                # rows were stored by the kernel itself; this only waits for the other ranks' flags
+            seq = fused.seq()
+            if seq > 1 and not first_of_run:
+                fused.wait(seq - 1)
+                consumed.add_(fused.block(seq - 1)[:, 0].sum())
         elif world > 1:
             qdist.all_gather_block(qdist.pack_block(out["moments"], out["aux"], out["flags"]), world, gathered)
+            consumed.add_(gathered[:, 0].sum())
     flush_buf = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     # roofline denominators measured in-process (MEASURED_PEAKS.json has no FP64 / shared-memory entry)
     fp64_peak, smem_peak = measure_peaks(local_rank)
 
-    def one_step(i):
+    for i in range(W_steps):
         sim.step(actions[i], out=out)
         exchange()
-
-    for i in range(W_steps):
-        one_step(i)
     torch.cuda.synchronize()
     launches0 = sim.launch_count()
     if world > 1:
@@ -318,6 +388,9 @@ def main():
         kev[i][1].record()
         exchange()
         e1.record()
+    if fused is not None:                               # the last step's rows (outside the per-step events: nothing left to overlap them with)
+        fused.wait()
+        consumed.add_(fused.block()[:, 0].sum())
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
@@ -325,34 +398,45 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
     launches = sim.launch_count() - launches0
-    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    per_step = [a.elapsed_time(b) for a, b in evs]
+    ms_total = sum(per_step)
     ms_kernel = sum(a.elapsed_time(b) for a, b in kev) / K_steps
+    ms_med5 = median5(per_step)
     if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_total, ms_med5 or 0.0], dtype=torch.float64, device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms_total = float(t.item())
+        ms_total, ms_med5 = float(t[0].item()), (float(t[1].item()) or None)
     value = world * B * K_steps / (ms_total * 1e-3)
     norm_dev = float((out["aux"][:, L.QC_AUX_NORM] - 1).abs().max().item())
-    gather_ok = None
+    gather_ok, gather_failed = None, None
     if fused is not None:                               # the fused block of the last step must equal a plain NCCL all-gather of the same outputs
         qdist.all_gather_block(qdist.pack_block(out["moments"], out["aux"], out["flags"]), world, gathered)
         gather_ok = bool(torch.equal(fused.block(), gathered))
-        fused.close()
-        sim.step(actions[0], out=out)                   # (the end-to-end leg below runs without the exchange)
+        gather_failed = fused.failed_ranks()
 
-    # ---- end-to-end through the host-buffer C-ABI call (pinned host memory, H2D + kernel + D2H per step) ----
+    # ---- end-to-end through the host-buffer C-ABI call (pinned host memory, H2D + kernel + D2H per step; N>1: plus the exchange) ----
     act_host = actions.cpu().pin_memory()
     mom_h = torch.empty((B, sim.K), dtype=torch.float64).pin_memory()
     aux_h = torch.empty((B, L.QC_AUX_COUNT), dtype=torch.float64).pin_memory()
     flg_h = torch.empty((B,), dtype=torch.uint8).pin_memory()
+
+    def e2e_step(i):
+        sim.step_host(act_host[i], moments=mom_h, aux=aux_h, flags=flg_h)       # synchronous: results are in host memory on return
+        if fused is not None:                           # every rank also needs all other ranks' rows of this step
+            fused.wait()
+            consumed.add_(fused.block()[:, 0].sum())
+            torch.cuda.current_stream().synchronize()
+        elif world > 1:
+            exchange()
+            torch.cuda.current_stream().synchronize()
     for i in range(min(3, W_steps)):
-        sim.step_host(act_host[i], moments=mom_h, aux=aux_h, flags=flg_h)
+        e2e_step(i)
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
     t0 = time.perf_counter()
     for i in range(K_steps):
-        sim.step_host(act_host[W_steps + i], moments=mom_h, aux=aux_h, flags=flg_h)
+        e2e_step(W_steps + i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -360,10 +444,28 @@ def main():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * B * K_steps / e2e_s
+    if fused is not None:
+        fused.close()
+        sim.step(actions[0], out=out)
 
     closed_loop = None
     if world == 1 and not args.no_closed_loop:
         closed_loop = closed_loop_rate(sim, params, B, K_steps, min(W_steps, 10), out)
+    main_kernel_info = sim.kernel_info()
+    K_mom = sim.K
+    del sim
+
+    # ---- the other BASELINE configurations, inside the same driver-timed run ----
+    extra = {}
+    if not args.no_extra:
+        xs, xw = max(5, min(20, K_steps // 10)), 3
+        extra["config3"] = measure_extra("inverted_harmonic", configs.inverted_harmonic(), 8192, xs, xw, rank, world, local_rank, flush_buf, fp64_peak,
+                                         "BASELINE configs[2]; herm_mode 0 = literal HERMITIAN/UPPER application of C (I:23,551); mode 1 differs by < 1e-7 after 5 substeps at F_max, which of the two MKL computes is unpinned")
+        extra["config4"] = measure_extra("inverted_quartic", configs.inverted_quartic(), 8192, xs, xw, rank, world, local_rank, flush_buf, fp64_peak,
+                                         "BASELINE configs[3]: 65,536 trajectories on 8 GPUs = 8192 per GPU")
+        if world == 1:
+            extra["sweep"] = [measure_extra("inverted_quartic", configs.quartic_sweep(npts), Bs, 3, 2, rank, world, local_rank, flush_buf, fp64_peak,
+                                            "BASELINE configs[4], x_max 13, dt ~ h^2") for npts, Bs in ((257, 4096), (1025, 2048), (4097, 296))]
 
     if rank != 0:
         if world > 1:
@@ -379,7 +481,7 @@ def main():
             prof = json.load(open(pj)).get(task, {})
         except Exception:
             prof = {}
-    hbm_bytes = B * (32.0 * n + 8.0 * sim.K + 8.0 * L.QC_AUX_COUNT + 5)
+    hbm_bytes = B * (32.0 * n + 8.0 * K_mom + 8.0 * L.QC_AUX_COUNT + 5)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -387,7 +489,7 @@ def main():
         pass
     roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (fp64_peak / 1e12),
                 "traffic": prof.get("dram_bytes_per_launch"),
-                "kernel": sim.kernel_info(), "kernel_ms": ms_kernel, "flops_per_unit": fpu,
+                "kernel": main_kernel_info, "kernel_ms": ms_kernel, "flops_per_unit": fpu,
                 "peak_source": "measured in-process: dependency-free DFMA loop on all SMs (qc_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                 "smem": {"peak_TBps": smem_peak / 1e12, "bytes_per_launch": prof.get("smem_bytes_per_launch"),
                          "achieved_TBps": (prof.get("smem_bytes_per_launch") / (ms_kernel * 1e-3) / 1e12) if prof.get("smem_bytes_per_launch") else None},
@@ -397,27 +499,39 @@ def main():
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        _, s0 = cpu_port_rate(task, params, 1, cores)
-        per_thread = max(2, int(12.0 / max(s0, 1e-3)))
-        v, secs = cpu_port_rate(task, params, per_thread, cores)
+        cpu_port_rate(task, params, 1, cores)                  # builds / loads the oracle, warms the caches
+        _, s0 = cpu_port_rate(task, params, 16, cores)
+        per_thread = max(2, int(16 * 3.0 / max(s0, 1e-3)))     # five (+ three) samples of ~3 s each
+        runs = sorted(cpu_port_rate(task, params, per_thread, cores) for _ in range(5))
+        v, secs = runs[2]
+        runs_cf = sorted(cpu_port_rate(task, params, per_thread, cores, constant_force=True) for _ in range(3))
+        v_cf = runs_cf[1][0]
         cpu_baseline = {"value": v, "unit": "traj-control-steps/s", "cores": cores, "kind": "port",
-                        "sample": "%d threads x %d trajectories x 1 control step (%d substeps, N=%d) in %.1f s; oracle/sse_oracle.c built -Ofast (the reference's flag), "
-                                  "per-force refactorisation included as in the reference" % (cores, per_thread, params["n_sub"], n, secs),
+                        "value_per_core": v / cores,
+                        "value_per_core_without_reset_ab": v_cf / cores,
+                        "reset_ab_share": max(0.0, 1.0 - v / v_cf),
+                        "sample": "median of 5 runs of %d threads x %d trajectories x 1 control step (%d substeps, N=%d), %.1f s each; oracle/sse_oracle.c built -Ofast (the reference's flag); "
+                                  "force redrawn per control step, so the per-force refactorisation (reset_ab: band LU + H0^2..H0^5) is included as in the reference; "
+                                  "value_per_core_without_reset_ab = same with one force per worker (median of 3)" % (cores, per_thread, params["n_sub"], n, secs),
                         "reference_build_as_shipped": reference_build_call_pattern(task, params)}
 
     line = {"metric": "trajectory-control-steps/sec", "value": value, "unit": "traj-control-steps/s", "n_gpus": world, "steps": K_steps,
-            "warmup": W_steps, "ms_per_step": ms_total / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": W_steps, "ms_per_step": ms_total / K_steps, "ms_per_step_median_of_5": ms_med5, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(task, B, n, params["n_sub"]), "task": task, "trajectories_per_gpu": B, "global_trajectories": world * B,
-                       "state_len": n, "n_sub": params["n_sub"], "noise": "in-kernel Philox4x32-10 + Box-Muller",
+                       "state_len": n, "n_sub": params["n_sub"]},
+            "measurement": {"noise": "in-kernel Philox4x32-10 + Box-Muller",
                        "actions": "uniform over 21 levels, redrawn every control step (torch.Generator seed 0)",
                        "l2": "inputs (2.8 MB/GPU) fit L2; L2 flushed with a 256 MiB write between timed steps, per-step CUDA events summed" if flush_buf is not None else "no flush",
-                       "parallelism": ("%d rank(s), trajectories sharded, [B,%d] f64 result block per step %s" % (world, sim.K + 5,
-                                        "stored by the SSE kernel into every rank's peer memory + flag wait (fused)" if gather_mode == "fused" else "by pack + NCCL all-gather [%s]" % gather_mode)) if world > 1 else "1 rank"},
+                       "parallelism": ("%d rank(s), trajectories sharded, [B,%d] f64 result block per step %s" % (world, K_mom + 5,
+                                        "stored by the SSE kernel into every rank's peer memory; each rank waits for and reads the block of step k-1 behind the launch of step k (fused, 4 buffers)"
+                                        if gather_mode == "fused" else "by pack + NCCL all-gather [%s]" % gather_mode)) if world > 1 else "1 rank"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": "traj-control-steps/s", "h2d_bytes_per_step": B * 4,
-                                      "d2h_bytes_per_step": B * (sim.K * 8 + L.QC_AUX_COUNT * 8 + 1)},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "closed_loop": closed_loop,
-            "check": {"max_norm_deviation": norm_dev, "wall_s_timed_region": t_wall, "fused_gather_equals_nccl": gather_ok}}
+                                      "d2h_bytes_per_step": B * (K_mom * 8 + L.QC_AUX_COUNT * 8 + 1),
+                                      "includes_exchange": world > 1},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "closed_loop": closed_loop, "extra": extra,
+            "check": {"max_norm_deviation": norm_dev, "wall_s_timed_region": t_wall, "fused_gather_equals_nccl": gather_ok, "gather_failed_ranks": gather_failed,
+                      "consumed_checksum": float(consumed.item())}}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
