@@ -346,16 +346,26 @@ def main():
             fused = None
         gather_mode = "fused" if fused is not None else "nccl (fused unavailable)"
     consumed = torch.zeros(1, dtype=torch.float64, device=dev)
+    main_stream = torch.cuda.current_stream()
+    side = torch.cuda.Stream(device=dev) if world > 1 else None          # the learner's side: waits for and reads the gathered blocks
+    side_evs = []
 
-    def exchange(first_of_run=False):
+    def exchange():
         """Every rank obtains the [world*B, K+5] result block of a control step and reads it (the learner's consumption, here a checksum).
-        Fused: the rows of step k were stored by the kernel itself; the wait for step k-1 is enqueued BEHIND the launch of step k (four
-        buffers make that safe, include/qcart.h), so a rank never idles until the slowest rank has finished the current step."""
+        Fused: the rows of step k are stored by the SSE kernel itself.  The consumer (wait for every rank's flag of step k-1, then read the
+        block) runs on a second stream behind the launch of step k -- four buffers make that safe, include/qcart.h -- so the simulation never
+        idles until the slowest rank has finished; the stepping stream only waits for the consumer of step k-2 (throughput-equivalent: the
+        exchange has to keep up with the stepping, it does not add latency to it)."""
         if fused is not None:
             seq = fused.seq()
-            if seq > 1 and not first_of_run:
-                fused.wait(seq - 1)
-                consumed.add_(fused.block(seq - 1)[:, 0].sum())
+            if seq > 1:
+                with torch.cuda.stream(side):
+                    fused.wait(seq - 1)
+                    consumed.add_(fused.block(seq - 1)[:, 0].sum())
+                    ev = torch.cuda.Event(); ev.record(side)
+                side_evs.append(ev)
+                if len(side_evs) > 1:
+                    main_stream.wait_event(side_evs.pop(0))
         elif world > 1:
             qdist.all_gather_block(qdist.pack_block(out["moments"], out["aux"], out["flags"]), world, gathered)
             consumed.add_(gathered[:, 0].sum())
@@ -389,8 +399,9 @@ def main():
         exchange()
         e1.record()
     if fused is not None:                               # the last step's rows (outside the per-step events: nothing left to overlap them with)
-        fused.wait()
-        consumed.add_(fused.block()[:, 0].sum())
+        with torch.cuda.stream(side):
+            fused.wait()
+            consumed.add_(fused.block()[:, 0].sum())
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
@@ -524,7 +535,7 @@ def main():
                        "actions": "uniform over 21 levels, redrawn every control step (torch.Generator seed 0)",
                        "l2": "inputs (2.8 MB/GPU) fit L2; L2 flushed with a 256 MiB write between timed steps, per-step CUDA events summed" if flush_buf is not None else "no flush",
                        "parallelism": ("%d rank(s), trajectories sharded, [B,%d] f64 result block per step %s" % (world, K_mom + 5,
-                                        "stored by the SSE kernel into every rank's peer memory; each rank waits for and reads the block of step k-1 behind the launch of step k (fused, 4 buffers)"
+                                        "stored by the SSE kernel into every rank's peer memory; each rank waits for and reads the block of step k-1 on a second stream behind the launch of step k (fused, 4 buffers)"
                                         if gather_mode == "fused" else "by pack + NCCL all-gather [%s]" % gather_mode)) if world > 1 else "1 rank"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": "traj-control-steps/s", "h2d_bytes_per_step": B * 4,
                                       "d2h_bytes_per_step": B * (K_mom * 8 + L.QC_AUX_COUNT * 8 + 1),
