@@ -50,6 +50,8 @@ SYMBOLS = [
     ("qc_clear_flags", C.c_int, [_vp, _vp]),
     ("qc_init_packets", C.c_int, [_vp, _dp, _dp, C.c_double, C.c_int, _vp]),
     ("qc_init_fock", C.c_int, [_vp, _dp, C.c_int, _vp]),
+    ("qc_reset_accept", C.c_int, [_vp, _dp, C.c_double, _vp, _dp, _vp, _vp]),
+    ("qc_reset_scatter", C.c_int, [_vp, _vp, _vp, _dp, _i64, _vp]),
     ("qc_step", C.c_int, [_vp, _ip, _dp, C.c_int, _ip, _dp, _dp, _vp, _dp, _dp, _vp]),
     ("qc_step_forces", C.c_int, [_vp, _dp, _dp, C.c_int, _ip, _dp, _dp, _vp, _dp, _dp, _vp]),
     ("qc_step_host", C.c_int, [_vp, _ip, _dp, C.c_int, _dp, _dp, _vp]),

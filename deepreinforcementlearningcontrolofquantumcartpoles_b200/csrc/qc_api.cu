@@ -306,6 +306,29 @@ extern "C" int qc_init_fock(qc_sim* s, const double* alpha, int on_device, void*
     return leave_user(s, stream);
 }
 
+// ---- episode reset helpers (include/qcart.h) -----------------------------------------------------------------------------------------
+extern "C" int qc_reset_accept(qc_sim* s, const double* aux, double energy_cutoff, uint8_t* pending, double* store, int32_t* n_pending, void* stream) {
+    int rc = use_device(s); if (rc) return rc;
+    if (!s->batch.psi) return fail(QC_ERR_STATE, "qc_set_batch first");
+    if (!aux || !pending || !store || !n_pending) return fail(QC_ERR_ARG, "qc_reset_accept: null argument");
+    const Model& m = s->model;
+    rc = enter_user(s, stream); if (rc) return rc;
+    if (launch_reset_accept(s->batch.psi, (int)s->batch.B, m.n, m.cfg.variant, m.fail_len, m.fail_thr * m.fail_thr, aux, energy_cutoff, pending,
+                            reinterpret_cast<double2*>(store), n_pending, stream)) return fail(QC_ERR_CUDA, "reset_accept kernel launch failed");
+    s->launches++;
+    return leave_user(s, stream);
+}
+extern "C" int qc_reset_scatter(qc_sim* s, const uint8_t* mask, const int64_t* slot, const double* pool, int64_t pool_size, void* stream) {
+    int rc = use_device(s); if (rc) return rc;
+    if (!s->batch.psi) return fail(QC_ERR_STATE, "qc_set_batch first");
+    if (!mask || !slot || !pool || pool_size <= 0) return fail(QC_ERR_ARG, "qc_reset_scatter: bad argument");
+    rc = enter_user(s, stream); if (rc) return rc;
+    if (launch_reset_scatter(s->batch.psi, (int)s->batch.B, s->model.n, mask, reinterpret_cast<const long long*>(slot), reinterpret_cast<const double2*>(pool),
+                             (long long)pool_size, s->batch.flags, stream)) return fail(QC_ERR_CUDA, "reset_scatter kernel launch failed");
+    s->launches++;
+    return leave_user(s, stream);
+}
+
 // ------------------------------------------------------------------------------------------------------
 static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* noise, int n_sub, const int32_t* nsub_traj,
                double* moments, double* aux, uint8_t* flags, double* q_out, double* xmean_out, int moments_only, void* stream) {

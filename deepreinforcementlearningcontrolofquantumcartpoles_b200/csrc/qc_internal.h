@@ -107,6 +107,9 @@ int launch_step(const LaunchPlan& plan, const StepParams& p, void* stream, std::
 int launch_bin(const int32_t* slot, int B, int n_slots, int T, int32_t* order, int32_t* order_count, void* stream);
 int launch_init_packets(double2* psi, int B, int n, double h, int half, const double* k, const double* mean, double stdv, void* stream);
 int launch_init_fock(double2* psi, int B, int n, const double* alpha, void* stream);
+int launch_reset_accept(const double2* psi, int B, int n, int variant, int fail_len, double fail_thr2, const double* aux, double cutoff, unsigned char* pending,
+                        double2* store, int* n_pending, void* stream);
+int launch_reset_scatter(double2* psi, int B, int n, const unsigned char* mask, const long long* slot, const double2* pool, long long pool_size, unsigned char* flags, void* stream);
 int launch_gather_wait(const unsigned long long* flags, int world, unsigned long long seq, unsigned int* err_flag, void* stream);
 int measure_fp64_peak(int device, double* flops);
 int measure_smem_peak(int device, double* bps);

@@ -249,6 +249,49 @@ __global__ void init_fock_kernel(double2* psi, int B, int n, const double* alpha
     const double s = 1.0 / sqrt(nrm);
     for (int i = 0; i < n; i++) { o[i].x *= s; o[i].y *= s; }
 }
+// Episode-reset helpers (row a15; reference: quartic main_parallel.py:177-198).  One CTA per trajectory.
+// reset_accept: candidate b (still pending) is accepted when its energy is below the cut-off and the boundary test of
+// check_boundary_error holds on its FINAL state -- init_state() returns the Fail of its last step only, not a latched one (:186-187,193-196).
+// Accepted states move to `store`, the rest stay pending and are counted.
+__global__ void reset_accept_kernel(const double2* __restrict__ psi, int n, int variant, int fail_len, double fail_thr2, const double* __restrict__ aux, double energy_cutoff,
+                                    unsigned char* pending, double2* __restrict__ store, int* n_pending) {
+    const int b = blockIdx.x;
+    __shared__ int ok_s;
+    if (threadIdx.x == 0) {
+        int ok = 0;
+        if (pending[b]) {
+            const double2* r = psi + (size_t)b * n;
+            double lo = 0.0, hi = 0.0;
+            for (int k = 0; k < fail_len; k++) {
+                const double2 h = r[n - 1 - k]; hi += h.x * h.x + h.y * h.y;
+                if (variant == QC_QUARTIC) { const double2 l = r[k]; lo += l.x * l.x + l.y * l.y; }
+            }
+            ok = (aux[(size_t)b * QC_AUX_COUNT + QC_AUX_ENERGY] < energy_cutoff) && !(lo > fail_thr2 || hi > fail_thr2);
+            if (ok) pending[b] = 0; else atomicAdd(n_pending, 1);
+        }
+        ok_s = ok;
+    }
+    __syncthreads();
+    if (ok_s) { for (int i = threadIdx.x; i < n; i += blockDim.x) store[(size_t)b * n + i] = psi[(size_t)b * n + i]; }
+}
+// reset_scatter: trajectories with mask[b] != 0 restart from pool state slot[b] mod pool_size; their latched flags are cleared.
+__global__ void reset_scatter_kernel(double2* __restrict__ psi, int n, const unsigned char* __restrict__ mask, const long long* __restrict__ slot,
+                                     const double2* __restrict__ pool, long long pool_size, unsigned char* __restrict__ flags) {
+    const int b = blockIdx.x;
+    if (!mask[b]) return;
+    const long long sl = ((slot[b] % pool_size) + pool_size) % pool_size;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) psi[(size_t)b * n + i] = pool[(size_t)sl * n + i];
+    if (threadIdx.x == 0) flags[b] = 0;
+}
+int launch_reset_accept(const double2* psi, int B, int n, int variant, int fail_len, double fail_thr2, const double* aux, double cutoff, unsigned char* pending,
+                        double2* store, int* n_pending, void* stream) {
+    reset_accept_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(psi, n, variant, fail_len, fail_thr2, aux, cutoff, pending, store, n_pending);
+    return cudaGetLastError() == cudaSuccess ? QC_OK : QC_ERR_CUDA;
+}
+int launch_reset_scatter(double2* psi, int B, int n, const unsigned char* mask, const long long* slot, const double2* pool, long long pool_size, unsigned char* flags, void* stream) {
+    reset_scatter_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(psi, n, mask, slot, pool, pool_size, flags);
+    return cudaGetLastError() == cudaSuccess ? QC_OK : QC_ERR_CUDA;
+}
 int launch_init_packets(double2* psi, int B, int n, double h, int half, const double* k, const double* mean, double stdv, void* stream) {
     const size_t tot = (size_t)B * n;
     init_packets_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(psi, B, n, h, half, k, mean, stdv);

@@ -296,7 +296,20 @@ class DeviceActor:
         obs, reward, done, info = env.step(action)
         obs = obs.contiguous()
         if self.replay is not None and self.train:
-            keep = (alive_before & ~env.last_bad).to(torch.uint8).contiguous()        # a row is stored only if the new state is not terminal (:211-217)
-            self.replay.push(self.obs, obs, action, reward.to(torch.float64), keep=keep)     # float32 -> float64 -> float32 is lossless
+            # Which transitions become experience rows depends on the task:
+            #   quartic / harmonic: only while the new state is alive -- the failing transition and the one that reaches t_max are dropped
+            #     (quartic main_parallel.py:207,211-217; harmonic :237-246);
+            #   inverted harmonic / inverted quartic: the failing transition IS stored, with failing_reward = -1 (inverted harmonic :247-258,
+            #     inverted quartic :203-213) -- the only negative-reward samples the learner ever sees.
+            # A restarted episode's first (uncontrolled) interval is never stored (`i != control_interval`, :204 / :249).
+            if env.task in ("quartic", "harmonic"):
+                keep = alive_before & ~env.last_bad & ~info["timeout"]
+            else:
+                keep = alive_before & ~info["was_fresh"]
+            if env.auto_reset:                                   # the next observation of a finished trajectory already belongs to the new episode
+                nxt = torch.where(info["finished"][:, None], info["terminal_observation"], obs).contiguous()
+            else:
+                nxt = obs
+            self.replay.push(self.obs, nxt, action, reward.to(torch.float64), keep=keep.to(torch.uint8).contiguous())     # float32 -> float64 -> float32 is lossless
         self.obs = obs
         return action, reward, done, info

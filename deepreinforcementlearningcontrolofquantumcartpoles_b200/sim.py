@@ -143,11 +143,32 @@ class BatchedSim:
         L.check(self.lib.qc_clear_flags(self.h, self._stream()))
 
     def init_packets(self, wavenumber=None, mean=None, std=1.0):
-        """Gaussian_packet of quartic main_parallel.py:75-76 for every trajectory (numpy arrays of length B or None)."""
+        """Gaussian_packet of quartic main_parallel.py:75-76 for every trajectory (numpy arrays or CUDA float64 tensors of length B, or None)."""
+        torch = _torch()
+        on_dev = any(isinstance(v, torch.Tensor) for v in (wavenumber, mean))
+        if on_dev:
+            k = None if wavenumber is None else wavenumber.to(torch.float64).contiguous()
+            m = None if mean is None else mean.to(torch.float64).contiguous()
+            assert all(v is None or (v.is_cuda and v.numel() == self.B) for v in (k, m))
+            L.check(self.lib.qc_init_packets(self.h, None if k is None else k.data_ptr(), None if m is None else m.data_ptr(), float(std), 1, self._stream()))
+            return
         k = None if wavenumber is None else np.ascontiguousarray(wavenumber, np.float64)
         m = None if mean is None else np.ascontiguousarray(mean, np.float64)
         L.check(self.lib.qc_init_packets(self.h, None if k is None else k.ctypes.data, None if m is None else m.ctypes.data,
                                          float(std), 0, self._stream()))
+
+    def reset_accept(self, aux, energy_cutoff, pending, store, n_pending):
+        """qc_reset_accept: device-side accept / keep-pending step of the rejection loop of the quartic reset (all CUDA tensors)."""
+        torch = _torch()
+        assert aux.is_cuda and aux.dtype == torch.float64 and pending.dtype == torch.uint8 and store.dtype == torch.complex128 and n_pending.dtype == torch.int32
+        assert tuple(store.shape) == (self.B, self.n) and store.is_contiguous() and pending.numel() == self.B
+        L.check(self.lib.qc_reset_accept(self.h, aux.data_ptr(), float(energy_cutoff), pending.data_ptr(), store.data_ptr(), n_pending.data_ptr(), self._stream()))
+
+    def reset_scatter(self, mask, slot, pool):
+        """qc_reset_scatter: trajectories with mask != 0 restart from pool[slot mod len(pool)] (CUDA tensors: uint8 [B], int64 [B], complex128 [P, N])."""
+        torch = _torch()
+        assert mask.is_cuda and mask.dtype == torch.uint8 and slot.dtype == torch.int64 and pool.dtype == torch.complex128 and pool.is_contiguous() and pool.shape[1] == self.n
+        L.check(self.lib.qc_reset_scatter(self.h, mask.data_ptr(), slot.data_ptr(), pool.data_ptr(), int(pool.shape[0]), self._stream()))
 
     def init_fock(self, alpha=None):
         """Fock vacuum (harmonic main_parallel.py:226-227) or coherent states alpha[B] (complex)."""

@@ -121,6 +121,18 @@ int qc_clear_flags(qc_sim *sim, void *stream);
 int qc_init_packets(qc_sim *sim, const double *wavenumber, const double *mean, double std, int on_device, void *stream);
 int qc_init_fock(qc_sim *sim, const double *alpha_re_im, int on_device, void *stream);
 
+/* ---- episode reset -------------------------------------------------------------------------------------------------
+ * The quartic task draws its initial state by rejection: Gaussian packet, free SSE evolution for U(15,20) time units, retry while <H> >= 7.5
+ * or the boundary test fails on the final state (quartic main_parallel.py:177-198).  The candidates are evolved by qc_step with per-trajectory
+ * substep budgets; these two calls keep the bookkeeping on the device:
+ *   qc_reset_accept   for every b with pending[b] != 0: accept when aux[b][QC_AUX_ENERGY] < energy_cutoff and check_boundary_error (Q:559-565)
+ *                     holds on the resident FINAL state -> copy it to store[b], clear pending[b]; otherwise add 1 to *n_pending.
+ *                     aux [B][QC_AUX_COUNT], pending [B] uint8 (in/out), store [B][N] complex128, n_pending int32 scalar (caller zeroes it): device.
+ *   qc_reset_scatter  for every b with mask[b] != 0: resident state b := pool[slot[b] mod pool_size] and its latched flags are cleared (a new
+ *                     episode; the substep counter, i.e. the Philox stream, runs on).  mask [B] uint8, slot [B] int64, pool [pool_size][N]: device. */
+int qc_reset_accept(qc_sim *sim, const double *aux, double energy_cutoff, uint8_t *pending, double *store, int32_t *n_pending, void *stream);
+int qc_reset_scatter(qc_sim *sim, const uint8_t *mask, const int64_t *slot, const double *pool, int64_t pool_size, void *stream);
+
 /* ---- the hot path ------------------------------------------------------------------------------------------
  * One control step for all B trajectories = n_sub SSE substeps (go_one_step, Q:569-624) at the force chosen by
  * `action` + latched Fail / escape flags (check_boundary_error Q:559-565) + moment extraction (compute_statistics

@@ -290,7 +290,7 @@ def test_device_actor_closed_loop_writes_consistent_rows():
     per_step_rows = []
     for t in range(steps):
         a, r, done, info = actor.step()
-        keep = alive & ~env.last_bad.cpu().numpy()
+        keep = alive.copy()                         # inverted quartic: the failing transition is stored too (inverted quartic main_parallel.py:203-213)
         per_step_rows.append(np.flatnonzero(keep))
         acts.append(a.cpu().numpy()); rewards.append(r.cpu().numpy())
         alive &= ~done.cpu().numpy()
