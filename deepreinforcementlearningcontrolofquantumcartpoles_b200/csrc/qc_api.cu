@@ -60,6 +60,11 @@ struct qc_sim {
     std::vector<uint64_t> slot_stamp; uint64_t call_id = 0;      // LRU of the on-demand factor slots (qc_step_forces / qc_step1)
 };
 
+#ifdef QC_DEBUG_HOOKS
+static unsigned int* g_dbg_guard = nullptr;
+// development build only: non-zero guard cells seen by all launches so far (synchronises the device)
+extern "C" unsigned int qc_debug_guard_errors(void) { cudaDeviceSynchronize(); return g_dbg_guard ? *g_dbg_guard : 0u; }
+#endif
 extern "C" const char* qc_last_error(void) { return g_err.c_str(); }
 extern "C" const char* qc_version(void) { return "qcart 0.2 sm_100a"; }
 extern "C" uint32_t qc_config_size(void) { return (uint32_t)sizeof(qc_config); }
@@ -384,6 +389,9 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
     { const char* d = getenv("QCART_DEBUG"); p.debug = d ? atoi(d) : 0; }      // development builds only (libqcart_dbg.so)
 #endif
 #ifdef QC_DEBUG_HOOKS
+    static unsigned int* dbg_g = nullptr;
+    if (!dbg_g) { cudaMallocManaged(&dbg_g, sizeof(unsigned int)); *dbg_g = 0; g_dbg_guard = dbg_g; }
+    p.dbg_guard = dbg_g;
     static unsigned long long* dbg_t = nullptr; static int dbg_n = 0;
     const bool timers = getenv("QCART_TIMERS") && pl.pipe;
     const int dbg_grid = (int)((b.B + pl.T - 1) / pl.T) + s->n_slots;

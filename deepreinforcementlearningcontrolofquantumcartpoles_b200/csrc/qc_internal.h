@@ -84,6 +84,7 @@ struct StepParams {
     int jacobi;              // 1: register-resident chunk-Jacobi solve (one-warp trajectories, chunk == L)
     int xfer;                // 1: chunk-Jacobi with interface iteration (boundary transfer matrices in shared memory after the noise block)
     int debug;               // development builds only (-DQC_DEBUG_HOOKS, QCART_DEBUG): 1 = skip the implicit solve, 2 = skip the explicit part; results are then wrong
+    unsigned int* dbg_guard;          // development builds only: count of non-zero guard cells found after the last substep (tests/tools/selfcheck.py)
     unsigned long long* dbg_timers;   // development builds only: [grid][8] cycle counters of the pipeline kernel (QCART_TIMERS=1)
     int stagger;             // multi-warp trajectories: trajectory t of a CTA starts its substep loop t*stagger clock cycles late (0 = off)
     int moments_only;        // 1: skip the substep loop, only compute moments/aux of the resident state

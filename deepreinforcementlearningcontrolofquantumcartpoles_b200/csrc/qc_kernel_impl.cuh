@@ -1054,7 +1054,9 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
         if (g == 0) { p.step_count[traj] = step0 + my_nsub; p.flags_latch[traj] = (unsigned char)iflag[0]; }
     }
     if (have && g == 0 && p.flags_out) p.flags_out[traj] = (unsigned char)iflag[0];
+#ifndef QC_DEBUG_HOOKS
     if (p.moments == nullptr && p.aux == nullptr) return;
+#endif
 
     if constexpr (VAR == QC_QUARTIC) {
         // compute_statistics (Q:325-362) + cal_energy (Q/main_parallel.py:63-64) + outside probability (IQ/main_parallel.py:78-81)
@@ -1198,6 +1200,18 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
             }
         }
     }
+#ifdef QC_DEBUG_HOOKS
+    // development build: the zero guard columns of every shared-memory line must still be exactly zero (an out-of-range store of a sweep, of
+    // the solver or of the moment passes lands there first)
+    if (p.dbg_guard) {
+        traj_sync<MULTI>(bar_id, G);
+        for (int e = g; e < nbuf_s * L * 2 * GUARD; e += G) {
+            const int line = e / (L * 2 * GUARD), r = e % (L * 2 * GUARD), j = r / (2 * GUARD), c = r % (2 * GUARD);
+            const double2 v = U[(size_t)line * LB + j * Gp + (c < GUARD ? c : G + c)];
+            if (v.x != 0.0 || v.y != 0.0) atomicAdd(p.dbg_guard, 1u);
+        }
+    }
+#endif
     if (p.g_world > 0) {                              // uniform over the grid
         if (have && g < 32) publish_row(p, traj, lane);
         publish_done(p);

@@ -605,6 +605,18 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
         }
     }
 #ifdef QC_DEBUG_HOOKS
+    if (p.dbg_guard && !cta_empty) {                 // guard columns and line padding of all state / sweep lines must still be zero (see sse_step_kernel)
+        __syncthreads();
+        for (int e = tid; e < TT * LBU; e += blockDim.x) {
+            const int r = e % LBU, col = (r % GpU);
+            const bool guard = r >= Geo::LBU0 || col < GU || col >= GU + G;
+            if (guard && (Uall[e].x != 0.0 || Uall[e].y != 0.0)) atomicAdd(p.dbg_guard, 1u);
+        }
+        for (int e = tid; e < NE * 2 * LBS; e += blockDim.x) {
+            const int col = (e % LBS) % GpS;
+            if ((col < GS || col >= GS + G) && (Sall[e].x != 0.0 || Sall[e].y != 0.0)) atomicAdd(p.dbg_guard, 1u);
+        }
+    }
     if (p.dbg_timers && !cta_empty && lane == 0) {
         unsigned long long* o = p.dbg_timers + 16 * (size_t)blockIdx.x;
         if (warp == 0) { for (int k = 0; k < 4; k++) o[k] = tm.acc[k]; o[15] = (unsigned long long)(clock64() - tm.begin); }
