@@ -69,9 +69,11 @@ template <int L, int GC, int NE> struct PipeGeo {
     // Warp roles follow the SM sub-partition a warp runs on (warp id mod 4): ids with (id & 3) == 3 are the solver warps (3: set A, 7: set B;
     // further ones idle), all other ids are explicit warps, numbered consecutively.  The serial substitution then has one scheduler's FP64 pipe
     // to itself instead of a quarter of it (measured: 155 -> ~45 cycles per recurrence row), and every explicit group spreads over the other three.
+    // One-warp groups (SOLO = false): a scheduler hosts at most two or three warps anyway, so the solver warps simply follow the explicit ones.
+    static constexpr bool SOLO = NWG > 1;
     static constexpr int NXW = NE * NWG;                            // explicit warps
-    static constexpr int LASTW = (NXW - 1) + (NXW - 1) / 3;         // warp id of the last explicit warp
-    static constexpr int WARPS = ((LASTW > 7 ? LASTW : 7) + 4) / 4 * 4;
+    static constexpr int LASTW = SOLO ? (NXW - 1) + (NXW - 1) / 3 : NXW + 1;     // highest warp id in use
+    static constexpr int WARPS = ((LASTW > 7 || !SOLO ? LASTW : 7) + 4) / 4 * 4;
     static constexpr int THREADS = WARPS * 32;
     static constexpr size_t tab_bytes = (size_t)CS * L * G * 16;
     static constexpr size_t fixed_bytes = tab_bytes + (size_t)TT * LBU * 16 + (size_t)NE * 2 * LBS * 16 + (size_t)TT * 128 /* scal */ +
@@ -200,7 +202,7 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
     }
     __syncwarp();
     if (cc == 0 && s < iflag[1]) {
-        const double sc = 1.0 / sqrt(nrm) / sqrt(p.w);         // normalize(): Q:259-263
+        const double sc = rsqrt(nrm * p.w);                    // normalize(): psi / (||psi||_2 sqrt(w))   (Q:259-263)
         const double s2 = sc * sc;
         double bl = 0.0, br = 0.0;                             // check_boundary_error (Q:559-565)
         for (int k = 0; k < p.fail_len; k++) {
@@ -242,8 +244,8 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, n = p.n, n_sub = p.n_sub;
     const int warp = tid >> 5, lane = tid & 31;
-    const bool is_solver = (warp & 3) == 3;
-    const int xw = warp - (warp >> 2);                              // explicit warp number
+    const bool is_solver = Geo::SOLO ? (warp & 3) == 3 : (warp >= Geo::NXW && warp < Geo::NXW + 2);
+    const int xw = Geo::SOLO ? warp - (warp >> 2) : warp;           // explicit warp number
     const bool is_idle = !is_solver && xw >= Geo::NXW;
     const int e = (is_solver || is_idle) ? 0 : xw / NWG;            // explicit group
     const int wq = (is_solver || is_idle) ? 0 : xw % NWG, g = wq * 32 + lane;   // warp / lane inside the group
@@ -311,7 +313,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
     PipeTimers tm; tm.start();
     if (!cta_empty && is_solver) {
         // ================= solver warpgroup: warp X of it serves set X ==================================================================
-        const int X = warp >> 2;
+        const int X = Geo::SOLO ? warp >> 2 : warp - Geo::NXW;
         if (X < 2) {
             const int cols = (n + L - 1) / L;
             int mult = (cols + Geo::CPT - 1) / Geo::CPT; mult |= 1;         // odd chunk stride (bank-conflict-free factor and state loads)
@@ -620,7 +622,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
     if (p.dbg_timers && !cta_empty && lane == 0) {
         unsigned long long* o = p.dbg_timers + 16 * (size_t)blockIdx.x;
         if (warp == 0) { for (int k = 0; k < 4; k++) o[k] = tm.acc[k]; o[15] = (unsigned long long)(clock64() - tm.begin); }
-        if (warp == 3) { for (int k = 0; k < 4; k++) o[4 + k] = tm.acc[k]; }
+        if (warp == (Geo::SOLO ? 3 : Geo::NXW)) { for (int k = 0; k < 4; k++) o[4 + k] = tm.acc[k]; }
     }
 #endif
     if (p.g_world > 0) publish_done(p);
