@@ -19,8 +19,8 @@ const KernEntry* qc_entries_fock_h(int* count);
 const KernEntry* qc_entries_fock_ih(int* count);
 const KernEntry* qc_entries_fock_ih2(int* count);
 
-struct PipeEntry { int L, gc, ne, threads; kern_t fn; size_t (*smem)(int n_sub); };
-const PipeEntry* qc_find_pipe(int L, int G, int ne);
+struct PipeEntry { int var, L, gc, ne, threads; kern_t fn; size_t (*smem)(int n_sub); };
+const PipeEntry* qc_find_pipe(int var, int L, int G, int ne);
 
 static std::vector<KernEntry> all_kernels() {
     std::vector<KernEntry> v;
@@ -83,29 +83,35 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
     const int forceL = env_int("QCART_L", 0), forceT = env_int("QCART_T", 0), forceP = env_int("QCART_P", 0);
     const int forceTabs = env_int("QCART_TABS", -1), forceGC = env_int("QCART_GC", -1);
     const int CS = (var == QC_QUARTIC) ? m.ba + 1 : m.ba + 2;
-    // Grid trajectories in force-binned launches: the warp-specialised pipeline (qc_pipe_impl.cuh).  QCART_PIPE=0: off; QCART_PIPE_NE: groups per CTA.
-    if (var == QC_QUARTIC && n_sub > 0 && env_int("QCART_PIPE", 1) && !forceL && env_int("QCART_BIN", -1) != 0) {
-        const int L = 6, cols = (n + L - 1) / L, G = (cols + 31) / 32 * 32, W = (W_needed + L - 1) / L * L;
-        const PipeEntry* pe = qc_find_pipe(L, G, env_int("QCART_PIPE_NE", 0));
-        if (pe && W <= 4 * L && (int)pe->smem(n_sub) <= smem_max) {
-            const int TT = 2 * pe->ne, cpt = 32 / pe->ne, GU = (G == 32) ? 8 : 5;
+    // Force-binned launches: the warp-specialised pipeline (qc_pipe_impl.cuh).  QCART_PIPE=0: off, 2: whenever an instance exists;
+    // QCART_PIPE_NE / QCART_PIPE_L: groups per CTA / points per lane (experiments).
+    // Geometry per system (measured, 8192 trajectories): grid with several warps per trajectory L = 6 (config 4: 28.6 -> 17.5 ms);
+    // inverted harmonic L = 3 with two-warp groups (5.18 -> 4.19 ms; one-warp groups with L = 6 spill at 168 registers and are latency bound
+    // at 255: 5.07 ms); harmonic L = 3, eight one-warp groups (1.81 -> 1.78 ms).  One-warp GRID trajectories (N <= 192) stay with the
+    // register-resident chunk-Jacobi kernel (0.55 vs 0.73 ms at 1024 and 3.7 vs 3.9 ms at 8192 trajectories of config 2).
+    if (n_sub > 0 && env_int("QCART_PIPE", 1) && !forceL && env_int("QCART_BIN", -1) != 0) {
+        const int L = env_int("QCART_PIPE_L", (var == QC_QUARTIC) ? 6 : 3), cols = (n + L - 1) / L, G = (cols + 31) / 32 * 32, W = (W_needed + L - 1) / L * L;
+        const int want_ne = env_int("QCART_PIPE_NE", (var == QC_HARMONIC) ? 8 : ((var == QC_INV_HARMONIC) ? 4 : 0));
+        const PipeEntry* pe = qc_find_pipe(var, L, G, want_ne);
+        const int GUc = (G == 32) ? 10 : ((var == QC_QUARTIC) ? 5 : 12);
+        if (pe && W <= (GUc - 1) * L && (int)pe->smem(n_sub) <= smem_max) {
+            const int TT = 2 * pe->ne, cpt = 32 / pe->ne, GU = GUc;
             int mult = (cols + cpt - 1) / cpt; mult |= 1;
             const int c_last = (cols - 1) / mult;
             // Binning pads every force level to whole CTAs.  Large batches: the padding is noise.  Small batches: only when even the worst
             // case (every bin one trajectory past a CTA) still fits one wave of CTAs, so that no SM ever runs a second, nearly empty round.
             const long long worst_ctas = ((long long)B + (long long)m.cfg.n_levels * (TT - 1) + TT - 1) / TT;
-            // One-warp trajectories (N <= 192): measured slower than the register-resident chunk-Jacobi kernel (0.74 vs 0.55 ms at 1024 and
-            // 3.9 vs 3.7 ms at 8192 trajectories of config 2) -- only on request (QCART_PIPE=2).
-            const bool big = G > 32 && B >= 8 * n_sm && B >= 64 * m.cfg.n_levels;
-            const bool one_wave = G > 32 && B >= 16 * m.cfg.n_levels && worst_ctas <= n_sm;
+            const bool allowed = var != QC_QUARTIC || G > 32;
+            const bool big = allowed && B >= 8 * n_sm && B >= 64 * m.cfg.n_levels;
+            const bool one_wave = allowed && var == QC_QUARTIC && B >= 16 * m.cfg.n_levels && worst_ctas <= n_sm;
             if ((big || one_wave || env_int("QCART_PIPE", 1) == 2) && c_last < cpt && c_last * mult + mult + W / L <= G + GU) {
                 cudaFuncAttributes fa;
                 if (cudaFuncGetAttributes(&fa, (const void*)pe->fn) != cudaSuccess) { err = std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(cudaGetLastError()); return QC_ERR_CUDA; }
                 memset(&plan, 0, sizeof(plan));
                 plan.L = L; plan.T = TT; plan.G = G; plan.P = cpt; plan.chunk = mult * L; plan.W = W; plan.NP = G * L; plan.threads = pe->threads;
                 plan.smem_bytes = (int)pe->smem(n_sub); plan.tstride = 0; plan.maxt = pe->threads; plan.gc = G; plan.tabs = true; plan.binned = 1; plan.pipe = pe->ne;
-                snprintf(plan.info, sizeof(plan.info), "sse_pipe_kernel<L=%d,G=%d,NE=%d> traj/CTA=%d chunks/traj=%d chunk=%d W=%d bin=1 threads=%d smem=%d regs=%d lmem=%d",
-                         L, G, pe->ne, plan.T, cpt, plan.chunk, W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
+                snprintf(plan.info, sizeof(plan.info), "sse_pipe_kernel<var=%d,L=%d,G=%d,NE=%d> traj/CTA=%d chunks/traj=%d chunk=%d W=%d bin=1 threads=%d smem=%d regs=%d lmem=%d",
+                         var, L, G, pe->ne, plan.T, cpt, plan.chunk, W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
                 return QC_OK;
             }
         }
@@ -194,7 +200,7 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
 
 int launch_step(const LaunchPlan& plan, const StepParams& p, void* stream, std::string& err) {
     if (plan.pipe) {
-        const PipeEntry* pe = qc_find_pipe(plan.L, plan.G, plan.pipe);
+        const PipeEntry* pe = qc_find_pipe(p.variant, plan.L, plan.G, plan.pipe);
         if (!pe) { err = "pipeline kernel not found"; return QC_ERR_UNSUPPORTED; }
         if (cudaFuncSetAttribute((const void*)pe->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess) {
             err = std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(cudaGetLastError()); return QC_ERR_CUDA;

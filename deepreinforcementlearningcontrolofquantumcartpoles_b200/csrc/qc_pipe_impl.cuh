@@ -32,7 +32,6 @@ struct PipeTimers { __device__ void start() {} __device__ __forceinline__ void t
 #ifndef QC_PIPE_PF
 #define QC_PIPE_PF 1          // rows the solver's loads run ahead of its arithmetic
 #endif
-#define QC_PIPE_GS 1          // zero guard columns of a sweep line (halo of the 9-point stencil: 4 points <= one column)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
@@ -54,18 +53,24 @@ template <int L, int GD> __device__ __forceinline__ double2 ld_rel_g(const doubl
 }
 
 // geometry shared by host (plan) and device
-template <int L, int GC, int NE> struct PipeGeo {
+template <int VAR, int L, int GC, int NE> struct PipeGeo {
     static constexpr int G = GC, NWG = GC / 32, TT = 2 * NE, CPT = 32 / NE;
+    static constexpr int BA = VarTraits<VAR>::BA;
+    // sweep lines per explicit group: two alternate in the Horner chain (the Fock systems first use them for Y+ / Y-); the inverted harmonic
+    // oscillator needs a third one for the left halo of a (HERMITIAN-descriptor term).  Their guard: the widest halo in columns.
+    static constexpr int NS = (VAR == QC_INV_HARMONIC) ? 3 : 2;
+    static constexpr int GS = (VAR == QC_INV_HARMONIC) ? (10 + L - 1) / L : 1;     // 9-point stencil / ladder operators: one column; Im C band: 10 points
+    static constexpr int HT = (VAR == QC_INV_HARMONIC) ? 11 : 0;  // Im C band entries per point (HERMITIAN-descriptor term), doubles
     // zero guard columns of a state line: solver warm-up (W <= 4 columns) + one prefetched column; one-warp groups have few, wide chunks whose
     // last one may reach further past the line
-    static constexpr int GU = (GC == 32) ? 8 : 5;
-    static constexpr int GpU = G + 2 * GU, GpS = G + 2 * QC_PIPE_GS;
+    static constexpr int GU = (GC == 32) ? 10 : ((VAR == QC_QUARTIC) ? 5 : 12);
+    static constexpr int GpU = G + 2 * GU, GpS = G + 2 * GS;
     static constexpr int LBU0 = L * GpU;
     // stride between the state lines of a set: = 8/NE (mod 8) in 16-byte units, so that the NE x 2 lanes of a quarter warp of the solver hit
     // distinct bank groups (chunk stride `mult` is odd)
     static constexpr int LBU = LBU0 + ((8 / NE) - (LBU0 % 8) + 8) % 8;
     static constexpr int LBS = L * GpS;
-    static constexpr int CS = 5;                                  // factor row: l_1..l_4, 1/d
+    static constexpr int CS = (VAR == QC_QUARTIC) ? BA + 1 : BA + 2;    // factor row: l_1..l_BA, 1/d, (Fock) xl
     // Warp roles follow the SM sub-partition a warp runs on (warp id mod 4): ids with (id & 3) == 3 are the solver warps (3: set A, 7: set B;
     // further ones idle), all other ids are explicit warps, numbered consecutively.  The serial substitution then has one scheduler's FP64 pipe
     // to itself instead of a quarter of it (measured: 155 -> ~45 cycles per recurrence row), and every explicit group spreads over the other three.
@@ -75,8 +80,8 @@ template <int L, int GC, int NE> struct PipeGeo {
     static constexpr int LASTW = SOLO ? (NXW - 1) + (NXW - 1) / 3 : NXW + 1;     // highest warp id in use
     static constexpr int WARPS = ((LASTW > 7 || !SOLO ? LASTW : 7) + 4) / 4 * 4;
     static constexpr int THREADS = WARPS * 32;
-    static constexpr size_t tab_bytes = (size_t)CS * L * G * 16;
-    static constexpr size_t fixed_bytes = tab_bytes + (size_t)TT * LBU * 16 + (size_t)NE * 2 * LBS * 16 + (size_t)TT * 128 /* scal */ +
+    static constexpr size_t tab_bytes = (size_t)CS * L * G * 16 + (size_t)HT * L * G * 8;
+    static constexpr size_t fixed_bytes = tab_bytes + (size_t)TT * LBU * 16 + (size_t)NE * NS * LBS * 16 + (size_t)TT * 128 /* scal */ +
                                           (size_t)NE * 2 * QC_MAXRED * NWG * 8 /* red */ + (size_t)NE * 128 /* stash */ + 64 /* mbarriers */;
     static size_t smem_bytes(int n_sub) { return fixed_bytes + (size_t)TT * n_sub * 16; }
 };
@@ -86,11 +91,11 @@ template <int L, int GC, int NE> struct PipeGeo {
 // lane = cc*NE + tt: chunk cc (mult columns = mult*L points) of trajectory tt; both substitutions start wb columns outside the chunk with
 // zero history (same truncation as solve_traj).  z overwrites the right-hand side and x overwrites z: every lane reads its warm-up region
 // (which belongs to the neighbour chunk) before any lane writes, the warp runs converged and __syncwarp separates the two parts.
-template <int L, int GC, int NE>
+template <int VAR, int L, int GC, int NE>
 __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restrict__ Uset, const double2* __restrict__ tab, double* scal_set, int mult, int wb,
                                            int lane, int s, PipeTimers& tm) {
-    typedef PipeGeo<L, GC, NE> Geo;
-    constexpr int BA = 4, CS = Geo::CS, G = Geo::G, Gp = Geo::GpU, GUARD = Geo::GU;
+    typedef PipeGeo<VAR, L, GC, NE> Geo;
+    constexpr int BA = Geo::BA, CS = Geo::CS, G = Geo::G, Gp = Geo::GpU, GUARD = Geo::GU;
     const int tt = lane % NE, cc = lane / NE;
     double2* __restrict__ U = Uset + (size_t)tt * Geo::LBU;
     double* scal = scal_set + tt * 16;
@@ -100,7 +105,8 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
     const bool act = (col0 < cols) && (s < iflag[1]);          // iflag[1] = substep budget of the trajectory (0 when the slot is empty)
     double nrm = 0.0, sx = 0.0, cen = 0.0;
     struct Row { double2 v; double2 cf[BA + 1]; };
-    constexpr int PF = QC_PIPE_PF, NR = PF + 1;
+    constexpr int PF = (L % (QC_PIPE_PF + 1) == 0) ? QC_PIPE_PF : 2, NR = PF + 1;      // the row ring restarts with every column: L must be a multiple of NR
+    static_assert(L % NR == 0, "row ring: L must be a multiple of PF + 1");
     // ---- forward: L y = rhs in column (scatter) form, z = D^{-1} y --------------------------------------------------------------
     // As soon as y_i is final its contributions l_{i+k,k} y_i to the next BA rows are subtracted from their pending sums: the loop-carried
     // dependency is one complex multiply-add per row instead of a 2*BA-deep chain.  The factor rows are stored by rows; entry (i+k, k) is
@@ -152,12 +158,14 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
         double2 pend[BA];
 #pragma unroll
         for (int k = 0; k < BA; k++) pend[k] = mk2(0.0, 0.0);
-        const bool do_cen = p.cen_hi > p.cen_lo;
+        const bool do_cen = (VAR == QC_QUARTIC) && p.cen_hi > p.cen_lo;
+        double2 xprev = mk2(0.0, 0.0);                          // Fock: x_{i+1} for <x> = sum 2 xl_i Re(conj(x_i) x_{i+1})
         auto load_row = [&](Row& r, int col, int j, bool) {
             const int tc = min(max(col, 0), G - 1);
             r.v = U[j * Gp + GUARD + col];
 #pragma unroll
             for (int k = 0; k < BA; k++) r.cf[k] = tab[(j * CS + k) * G + tc];
+            if constexpr (VAR != QC_QUARTIC) r.cf[BA] = tab[(j * CS + BA + 1) * G + tc];      // (xl_i, 0)
         };
         Row ring[NR];
         int col = col0 + mult + wb - 1;
@@ -184,10 +192,15 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
                     ub[j * Gp] = mk2(xr, xi);
                     const double a2 = xr * xr + xi * xi;
                     nrm += a2;
-                    const int i = col * L + j;
-                    sx = fma(p.h * (double)(i - p.half), a2, sx);
-                    if (do_cen && i >= p.cen_lo && i < p.cen_hi) cen += a2;
+                    if constexpr (VAR == QC_QUARTIC) {
+                        const int i = col * L + j;
+                        sx = fma(p.h * (double)(i - p.half), a2, sx);
+                        if (do_cen && i >= p.cen_lo && i < p.cen_hi) cen += a2;
+                    } else {
+                        sx = fma(2.0 * r.cf[BA].x, xr * xprev.x + xi * xprev.y, sx);
+                    }
                 }
+                if constexpr (VAR != QC_QUARTIC) xprev = mk2(xr, xi);
             }
         };
         if (act) { for (int b = 0; b < wb; b++, col--) bwd_col(false); }
@@ -208,12 +221,12 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
         for (int k = 0; k < p.fail_len; k++) {
             const int ih = p.n - 1 - k;
             const double2 hi = U[(ih % L) * Gp + GUARD + ih / L]; br += hi.x * hi.x + hi.y * hi.y;
-            const double2 lo = U[(k % L) * Gp + GUARD + k / L]; bl += lo.x * lo.x + lo.y * lo.y;
+            if constexpr (VAR == QC_QUARTIC) { const double2 lo = U[(k % L) * Gp + GUARD + k / L]; bl += lo.x * lo.x + lo.y * lo.y; }
         }
         scal[0] = sc; scal[1] = p.w * sx * s2;
         int f = iflag[0];
         if (bl * s2 > p.fail_thr2 || br * s2 > p.fail_thr2) f |= QC_FLAG_FAIL;
-        if (p.cen_hi > p.cen_lo) { if (1.0 - p.w * cen * s2 > 0.5) f |= QC_FLAG_ESCAPED; }
+        if (VAR == QC_QUARTIC && p.cen_hi > p.cen_lo) { if (1.0 - p.w * cen * s2 > 0.5) f |= QC_FLAG_ESCAPED; }
         iflag[0] = f;
     }
     __syncwarp();
@@ -221,25 +234,25 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
 
 // ------------------------------------------------------------------------------------------------------
 // One Horner sweep of an explicit group: publish w into the sweep line, group barrier, gather the halo, return H0 w.
-template <int L, bool MULTI>
-__device__ __forceinline__ void pipe_sweep(const LaneOps<QC_QUARTIC, L>& ops, double2* __restrict__ buf, const double2 (&w)[L], double2 (&hw)[L], int g, int G, int Gp, int bar_id) {
-    constexpr int GS = QC_PIPE_GS;
+template <int VAR, int L, int GS, bool MULTI>
+__device__ __forceinline__ void pipe_sweep(const LaneOps<VAR, L>& ops, double2* __restrict__ buf, const double2 (&w)[L], double2 (&hw)[L], int g, int G, int Gp, int bar_id) {
+    constexpr int HB = VarTraits<VAR>::HB;
 #pragma unroll
     for (int j = 0; j < L; j++) buf[j * Gp + GS + g] = w[j];
     traj_sync<MULTI>(bar_id, G);
-    double2 ext[L + 8];
+    double2 ext[L + 2 * HB];
 #pragma unroll
-    for (int r = -4; r < L + 4; r++) ext[r + 4] = (r >= 0 && r < L) ? w[r] : ld_rel_g<L, GS>(buf, g, Gp, r);
+    for (int r = -HB; r < L + HB; r++) ext[r + HB] = (r >= 0 && r < L) ? w[r] : ld_rel_g<L, GS>(buf, g, Gp, r);
 #pragma unroll
     for (int j = 0; j < L; j++) hw[j] = ops.h0(ext, j);
 }
 
 // ------------------------------------------------------------------------------------------------------
-template <int L, int GC, int NE>
-__global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kernel(const StepParams p) {
-    typedef PipeGeo<L, GC, NE> Geo;
+template <int VAR, int L, int GC, int NE>
+__global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE>::THREADS, 1) sse_pipe_kernel(const StepParams p) {
+    typedef PipeGeo<VAR, L, GC, NE> Geo;
     constexpr int G = Geo::G, NWG = Geo::NWG, TT = Geo::TT, GpU = Geo::GpU, GpS = Geo::GpS, LBU = Geo::LBU, LBS = Geo::LBS, CS = Geo::CS;
-    constexpr int GU = Geo::GU, GS = QC_PIPE_GS;
+    constexpr int GU = Geo::GU, GS = Geo::GS, NS = Geo::NS, HT = Geo::HT, BA = Geo::BA;
     constexpr bool MULTI = NWG > 1;                                  // one-warp groups synchronise with __syncwarp
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, n = p.n, n_sub = p.n_sub;
@@ -252,9 +265,10 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
     const int bar_id = 1 + e;
 
     double2* tab = reinterpret_cast<double2*>(smem);
-    double2* Uall = tab + (size_t)CS * L * G;                       // [2][NE] state lines, stride LBU
-    double2* Sall = Uall + (size_t)TT * LBU;                        // [NE][2] sweep lines
-    double* scal_all = reinterpret_cast<double*>(Sall + (size_t)NE * 2 * LBS);      // [TT][16]: scale, <x>, ..., (int) flags, budget, trajectory id
+    double* khs = reinterpret_cast<double*>(tab + (size_t)CS * L * G);               // [L][HT][G] band of Im C (inverted harmonic)
+    double2* Uall = reinterpret_cast<double2*>(khs + (size_t)HT * L * G);            // [2][NE] state lines, stride LBU
+    double2* Sall = Uall + (size_t)TT * LBU;                        // [NE][NS] sweep lines
+    double* scal_all = reinterpret_cast<double*>(Sall + (size_t)NE * NS * LBS);     // [TT][16]: scale, <x>, ..., (int) flags, budget, trajectory id
     double* red_all = scal_all + TT * 16;                           // [NE][2 * QC_MAXRED * NWG]
     double* stash_all = red_all + NE * 2 * QC_MAXRED * NWG;         // [NE][16]
     uint64_t* bars = reinterpret_cast<uint64_t*>(stash_all + NE * 16);              // full[2], done[2]
@@ -265,7 +279,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
     const bool cta_empty = blockIdx.x * TT >= npos;
     if (!cta_empty) {
     // ---- CTA prologue: zero lines, barriers, factor table of the CTA's force slot ---------------------------------------------------
-    for (int i = tid; i < TT * LBU + NE * 2 * LBS; i += blockDim.x) Uall[i] = mk2(0.0, 0.0);
+    for (int i = tid; i < TT * LBU + NE * NS * LBS; i += blockDim.x) Uall[i] = mk2(0.0, 0.0);
     if (tid == 0) {
         int sl = 0;
         for (int q = 0; q < TT; q++) { const int ps = blockIdx.x * TT + q; if (ps < npos && p.order[ps] >= 0) { sl = min(max(p.slot[p.order[ps]], 0), p.n_slots - 1); break; } }
@@ -274,11 +288,21 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
     }
     __syncthreads();
     {
-        const double2* __restrict__ fs = p.fac + (size_t)cta_slot * n * 5;
+        const double2* __restrict__ fs = p.fac + (size_t)cta_slot * n * (BA + 1);
         for (int i = tid; i < G * L; i += blockDim.x) {
             const int jj = i % L, cc = i / L;
 #pragma unroll
-            for (int k = 0; k < CS; k++) tab[(jj * CS + k) * G + cc] = (i < n) ? __ldg(&fs[(size_t)i * 5 + k]) : mk2(0.0, 0.0);
+            for (int k = 0; k < CS; k++) {
+                double2 v = mk2(0.0, 0.0);
+                if (i < n) { if (k <= BA) v = __ldg(&fs[(size_t)i * (BA + 1) + k]); else v = mk2(__ldg(&p.x[i]), 0.0); }
+                tab[(jj * CS + k) * G + cc] = v;
+            }
+            if constexpr (HT > 0) {
+                if (p.herm_mode != 2) {
+#pragma unroll
+                    for (int k = 0; k < HT; k++) khs[(jj * HT + k) * G + cc] = (i < n) ? __ldg(&p.herm_tab[((size_t)cta_slot * n + i) * HT + k]) : 0.0;
+                }
+            }
         }
     }
     // ---- per-trajectory prologue (explicit groups): state -> line, noise table, flags, budget ------------------------------------------
@@ -321,7 +345,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
             for (int s = 0; s < n_sub; s++) {
                 mbar_wait(&bars[X], s & 1);
                 tm.tick(0);
-                pipe_solve<L, GC, NE>(p, Uall + (size_t)X * NE * LBU, tab, scal_all + X * NE * 16, mult, wb, lane, s, tm);
+                pipe_solve<VAR, L, GC, NE>(p, Uall + (size_t)X * NE * LBU, tab, scal_all + X * NE * 16, mult, wb, lane, s, tm);
                 mbar_arrive(&bars[2 + X]);
                 tm.tick(3);
             }
@@ -330,20 +354,39 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
         // ================= explicit group ========================================================================================
         const int slot = cta_slot;
         const double F = p.slot_force[slot];
-        LaneOps<QC_QUARTIC, L> ops;
-        double xs[L];
+        LaneOps<VAR, L> ops;
+        double xs[(VAR == QC_QUARTIC) ? L : 1];      // grid: x_j
+        double xl[(VAR == QC_QUARTIC) ? 1 : L + 3];  // Fock: xl_r = sqrt((r+1)/2), r in [-2, L]  (index r+2)
         bool valid[L];
 #pragma unroll
         for (int j = 0; j < L; j++) {
             const int i = g * L + j;
             valid[j] = i < n;
-            xs[j] = valid[j] ? __ldg(&p.x[i]) : 0.0;
-            ops.dg[j] = valid[j] ? (__ldg(&p.hdiag[i]) - p.kappa * F * xs[j]) : 0.0;
+            if constexpr (VAR == QC_QUARTIC) {
+                xs[j] = valid[j] ? __ldg(&p.x[i]) : 0.0;
+                ops.dg[j] = valid[j] ? (__ldg(&p.hdiag[i]) - p.kappa * F * xs[j]) : 0.0;
+            } else {
+                ops.dg[j] = valid[j] ? __ldg(&p.hdiag[i]) : 0.0;
+            }
         }
+        if constexpr (VAR == QC_QUARTIC) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) ops.tk[k] = p.tk[k];
-        double2* S0 = Sall + (size_t)e * 2 * LBS;
+            for (int k = 0; k < 4; k++) ops.tk[k] = p.tk[k];
+        } else {
+#pragma unroll
+            for (int r = -2; r <= L; r++) {
+                const int i = g * L + r;                 // tables are zero padded by 8 on both sides
+                const double v = (i < n + 8) ? __ldg(&p.x[i]) : 0.0;
+                xl[r + 2] = v; ops.fxl[r + 2] = -p.kappa * F * v;
+            }
+            if constexpr (VAR == QC_INV_HARMONIC) {
+#pragma unroll
+                for (int r = -2; r < L; r++) { const int i = g * L + r; ops.h2[r + 2] = (i < n + 8) ? __ldg(&p.h2[i]) : 0.0; }
+            }
+        }
+        double2* S0 = Sall + (size_t)e * NS * LBS;
         double2* S1 = S0 + LBS;
+        double2* S2 = S1 + LBS;                       // inverted harmonic only
         double* red = red_all + e * 2 * QC_MAXRED * NWG;
         double* stash = stash_all + e * 16;
         int red_phase = 0;
@@ -358,15 +401,20 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
 #pragma unroll
             for (int j = 0; j < L; j++) {
                 const double2 c = U[j * GpU + GU + g];
-                const double a2 = c.x * c.x + c.y * c.y;
-                v[0] = fma(xs[j], a2, v[0]);
-                const int i = g * L + j;
-                if (i >= p.cen_lo && i < p.cen_hi) v[1] += a2;
+                if constexpr (VAR == QC_QUARTIC) {
+                    const double a2 = c.x * c.x + c.y * c.y;
+                    v[0] = fma(xs[j], a2, v[0]);
+                    const int i = g * L + j;
+                    if (i >= p.cen_lo && i < p.cen_hi) v[1] += a2;
+                } else {
+                    const double2 nx = ld_rel_g<L, GU>(U, g, GpU, j + 1);
+                    v[0] = fma(2.0 * xl[j + 2], c.x * nx.x + c.y * nx.y, v[0]);
+                }
             }
             traj_reduce<2, MULTI>(v, red, red_phase, wq, NWG, lane, bar_id, G);
             if (g == 0) {
                 scal[1] = p.w * v[0];
-                if (p.cen_hi > p.cen_lo && iflag[1] > 0) { if (1.0 - p.w * v[1] > 0.5) iflag[0] |= QC_FLAG_ESCAPED; }
+                if (VAR == QC_QUARTIC && p.cen_hi > p.cen_lo && iflag[1] > 0) { if (1.0 - p.w * v[1] > 0.5) iflag[0] |= QC_FLAG_ESCAPED; }
             }
         }
         traj_sync<MULTI>(bar_id, G);
@@ -395,6 +443,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                         if (p.q_out) p.q_out[(size_t)traj * n_sub + s] = xbar + dW * q_scale;      // Q:577
                         if (p.xmean_out) p.xmean_out[(size_t)traj * n_sub + s] = xbar;
                     }
+                    if constexpr (VAR == QC_QUARTIC) {
                     double2 a[L], w[L], hw[L];
                     {
                         double2 ext[L + 8];
@@ -439,16 +488,16 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                     // ===== merged Horner chain in H0 =====
 #pragma unroll
                     for (int j = 0; j < L; j++) w[j] = mk2(-e5 * a[j].y, e5 * a[j].x);                    // c5 a,  c5 = +i dt^6/360
-                    pipe_sweep<L, MULTI>(ops, S0, w, hw, g, G, GpS, bar_id);
+                    pipe_sweep<VAR, L, GS, MULTI>(ops, S0, w, hw, g, G, GpS, bar_id);
 #pragma unroll
                     for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(-e4, a[j].x, hw[j].x), fma(-e4, a[j].y, hw[j].y)) : mk2(0.0, 0.0);      // c4 = -dt^5/80
-                    pipe_sweep<L, MULTI>(ops, S1, w, hw, g, G, GpS, bar_id);
+                    pipe_sweep<VAR, L, GS, MULTI>(ops, S1, w, hw, g, G, GpS, bar_id);
 #pragma unroll
                     for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(e3, a[j].y, hw[j].x), fma(-e3, a[j].x, hw[j].y)) : mk2(0.0, 0.0);       // c3 = -i dt^4/24
-                    pipe_sweep<L, MULTI>(ops, S0, w, hw, g, G, GpS, bar_id);
+                    pipe_sweep<VAR, L, GS, MULTI>(ops, S0, w, hw, g, G, GpS, bar_id);
 #pragma unroll
                     for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(e2, a[j].x, hw[j].x), fma(e2, a[j].y, hw[j].y)) : mk2(0.0, 0.0);        // c2 = dt^3/12
-                    pipe_sweep<L, MULTI>(ops, S1, w, hw, g, G, GpS, bar_id);
+                    pipe_sweep<VAR, L, GS, MULTI>(ops, S1, w, hw, g, G, GpS, bar_id);
                     tm.tick(2);
                     // psi (own points) again from the state line, v1 = -i cv psi
                     double2 psi[L];
@@ -462,7 +511,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                             w[j] = valid[j] ? mk2(fma(cv, psi[j].y, hw[j].x), fma(-cv, psi[j].x, hw[j].y)) : mk2(0.0, 0.0);
                         }
                     }
-                    pipe_sweep<L, MULTI>(ops, S0, w, hw, g, G, GpS, bar_id);
+                    pipe_sweep<VAR, L, GS, MULTI>(ops, S0, w, hw, g, G, GpS, bar_id);
                     {
                         const double A2 = stash[0], A1 = stash[1], A0 = stash[2], P2 = stash[3], P1 = stash[4], P0 = stash[5], M2 = stash[6], M1 = stash[7], M0 = stash[8], G0 = stash[11];
 #pragma unroll
@@ -477,6 +526,135 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                             // psi~ = acc + H0 w0: right-hand side of the implicit solve, straight into the state line
                             U[j * GpU + GU + g] = valid[j] ? mk2(ar + hw[j].x, ai + hw[j].y) : mk2(0.0, 0.0);
                         }
+                    }
+                    } else {
+                    // ===== Fock basis: x is tridiagonal.  Same algebra as sse_step_kernel: Phi+- = (1 +- sig (x - <x>_Y+)) Y+ are never formed, their
+                    // un-normalised <x> follow from <Y+, x^k Y+> (k = 1..3), one reduction per substep; psi~ minus the Horner terms is a scalar-coefficient
+                    // combination of psi, (x-<x>)psi, (x-<x>)^2 psi, Y+-, xY+-, x^2 Y+- whose known-coefficient part is folded into acc first. =====
+                    constexpr int HB = VarTraits<VAR>::HB;
+                    double2 a[L], acc[L], w[L], hw[L];
+                    double2 pe[L + 4];                       // psi on [-2, L+1]
+#pragma unroll
+                    for (int r = -2; r < L + 2; r++) { const double2 c = ld_rel_g<L, GU>(U, g, GpU, r); pe[r + 2] = mk2(sc * c.x, sc * c.y); }
+                    double2 rel0[L + 2];                     // (x - <x>) psi on [-1, L]
+#pragma unroll
+                    for (int r = -1; r <= L; r++) {
+                        const double xa = xl[r + 2], xb = xl[r + 1];     // xl_r, xl_{r-1}
+                        rel0[r + 1] = mk2(xa * pe[r + 3].x + xb * pe[r + 1].x - xbar * pe[r + 2].x, xa * pe[r + 3].y + xb * pe[r + 1].y - xbar * pe[r + 2].y);
+                    }
+                    const double c_rel0 = gs * (dW - 2.0 * k4), c_sq0 = -2.0 * k2 * g4;
+                    const double c_sqp = 2.0 * k5 * gs * sig - g4 * (k1 + k2), c_sqm = g4 * (k1 - k2), c_relm = gs * (k4 - k3 + k5);
+                    const double cvb = 2.0 * sdt * (k1 - k6) * gs, cvp = 2.0 * k2;
+                    double2 yp[L], ym[L], v1[L];
+#pragma unroll
+                    for (int j = 0; j < L; j++) {
+                        const double2 ps = pe[j + 2];
+                        const double xa = xl[j + 2], xb = xl[j + 1];
+                        const double2 r0_ = rel0[j + 1];
+                        const double2 sq0 = mk2(xa * rel0[j + 2].x + xb * rel0[j].x - xbar * r0_.x, xa * rel0[j + 2].y + xb * rel0[j].y - xbar * r0_.y);
+                        const double2 h = ops.h0(pe + (2 - HB), j);
+                        a[j] = mk2(h.y - g4 * sq0.x, -h.x - g4 * sq0.y);                                   // D1 (H:260-290)
+                        const double ux = fma(dt, a[j].x, ps.x), uy = fma(dt, a[j].y, ps.y);
+                        yp[j] = mk2(fma(sig, r0_.x, ux), fma(sig, r0_.y, uy));                              // Y+- (H:428-437)
+                        ym[j] = mk2(fma(-sig, r0_.x, ux), fma(-sig, r0_.y, uy));
+                        acc[j] = mk2(fma(c_sq0, sq0.x, fma(c_rel0, r0_.x, ps.x)), fma(c_sq0, sq0.y, fma(c_rel0, r0_.y, ps.y)));
+                        const double tvx = fma(cvb, r0_.x, cvp * ps.x), tvy = fma(cvb, r0_.y, cvp * ps.y);
+                        v1[j] = mk2(tvy, -tvx);
+                    }
+#pragma unroll
+                    for (int j = 0; j < L; j++) {
+                        S0[j * GpS + GS + g] = yp[j]; S1[j * GpS + GS + g] = ym[j];
+                        if constexpr (VAR == QC_INV_HARMONIC) S2[j * GpS + GS + g] = a[j];     // left halo of a for the HERMITIAN-descriptor term below
+                    }
+                    traj_sync<MULTI>(bar_id, G);
+                    // psi is dead from here on (every lane has read its halo): the own slots of the state line park v1 until the last Horner sweep
+#pragma unroll
+                    for (int j = 0; j < L; j++) U[j * GpU + GU + g] = v1[j];
+                    double2 u1p[L], u1m[L];                  // x Y+- on the own points
+                    double m[4] = {0.0, 0.0, 0.0, 0.0};      // <Y+,xY+>, <Y+,x^2 Y+>, <Y+,x^3 Y+>, <Y-,xY->
+                    {
+                        double2 ype[L + 4], yme[L + 4];
+#pragma unroll
+                        for (int r = -2; r < L + 2; r++) {
+                            ype[r + 2] = (r >= 0 && r < L) ? yp[r] : ld_rel_g<L, GS>(S0, g, GpS, r);
+                            yme[r + 2] = (r >= 0 && r < L) ? ym[r] : ld_rel_g<L, GS>(S1, g, GpS, r);
+                        }
+                        double2 xyp[L + 2], xym[L + 2];      // x Y+- on [-1, L]
+#pragma unroll
+                        for (int r = -1; r <= L; r++) {
+                            const double xa = xl[r + 2], xb = xl[r + 1];
+                            xyp[r + 1] = mk2(xa * ype[r + 3].x + xb * ype[r + 1].x, xa * ype[r + 3].y + xb * ype[r + 1].y);
+                            xym[r + 1] = mk2(xa * yme[r + 3].x + xb * yme[r + 1].x, xa * yme[r + 3].y + xb * yme[r + 1].y);
+                        }
+#pragma unroll
+                        for (int j = 0; j < L; j++) {
+                            const double xa = xl[j + 2], xb = xl[j + 1];
+                            u1p[j] = xyp[j + 1]; u1m[j] = xym[j + 1];
+                            const double2 u2p = mk2(xa * xyp[j + 2].x + xb * xyp[j].x, xa * xyp[j + 2].y + xb * xyp[j].y);     // x^2 Y+
+                            const double2 u2m = mk2(xa * xym[j + 2].x + xb * xym[j].x, xa * xym[j + 2].y + xb * xym[j].y);     // x^2 Y-
+                            m[0] += yp[j].x * u1p[j].x + yp[j].y * u1p[j].y;
+                            m[1] += u1p[j].x * u1p[j].x + u1p[j].y * u1p[j].y;
+                            m[2] += u1p[j].x * u2p.x + u1p[j].y * u2p.y;
+                            m[3] += ym[j].x * u1m[j].x + ym[j].y * u1m[j].y;
+                            acc[j].x = fma(c_sqm, u2m.x, fma(c_sqp, u2p.x, acc[j].x)); acc[j].y = fma(c_sqm, u2m.y, fma(c_sqp, u2p.y, acc[j].y));
+                        }
+                    }
+                    traj_reduce<4, MULTI>(m, red, red_phase, wq, NWG, lane, bar_id, G);
+                    tm.tick(1);
+                    {
+                        const double xbp = p.w * m[0], xbm = p.w * m[3];                       // un-normalised <x> of Y+-  (D1ImRe, H:292-314)
+                        const double t1 = m[1] - xbp * m[0], t2 = m[2] - 2.0 * xbp * m[1] + xbp * xbp * m[0];
+                        const double xfp = p.w * (m[0] + 2.0 * sig * t1 + sig * sig * t2), xfm = p.w * (m[0] - 2.0 * sig * t1 + sig * sig * t2);
+                        const double c_relp = gs * (k3 + k4 - k5 + k5 * sig * (2.0 * xbp - xfp - xfm)), c_yp = k5 * gs * (xfm - xfp);
+                        const double PY = c_yp - xbp * c_relp + xbp * xbp * c_sqp, PU1 = c_relp - 2.0 * xbp * c_sqp;
+                        const double MY = xbm * xbm * c_sqm - xbm * c_relm, MU1 = c_relm - 2.0 * xbm * c_sqm;
+#pragma unroll
+                        for (int j = 0; j < L; j++) {
+                            acc[j].x = fma(MU1, u1m[j].x, fma(MY, ym[j].x, fma(PU1, u1p[j].x, fma(PY, yp[j].x, acc[j].x))));
+                            acc[j].y = fma(MU1, u1m[j].y, fma(MY, ym[j].y, fma(PU1, u1p[j].y, fma(PY, yp[j].y, acc[j].y))));
+                        }
+                    }
+                    if constexpr (VAR == QC_INV_HARMONIC) {
+                        // The reference applies the complex-symmetric correction matrix C with a HERMITIAN/UPPER descriptor (I:23,551):
+                        // C_herm = C - 2i strict_lower(Im C).  herm_mode 0 reproduces that; 1 additionally drops Im(C_ii); 2 = symmetric (as H:532).
+                        if (p.herm_mode != 2) {
+                            double2 ah[L + 10];
+#pragma unroll
+                            for (int r = -10; r < L; r++) ah[r + 10] = (r >= 0) ? a[r] : ld_rel_g<L, GS>(S2, g, GpS, r);
+#pragma unroll
+                            for (int j = 0; j < L; j++) {
+                                if (valid[j]) {
+                                    double cr = 0.0, ci = 0.0;
+#pragma unroll
+                                    for (int k = 1; k <= 10; k++) {
+                                        const double c = khs[(j * 11 + k) * G + g];
+                                        cr = fma(c, ah[j + 10 - k].x, cr); ci = fma(c, ah[j + 10 - k].y, ci);
+                                    }
+                                    acc[j].x += 2.0 * ci; acc[j].y -= 2.0 * cr;
+                                    if (p.herm_mode == 1) { const double kd = khs[(j * 11) * G + g]; acc[j].x += kd * a[j].y; acc[j].y -= kd * a[j].x; }
+                                }
+                            }
+                        }
+                    }
+                    // ===== merged Horner chain in H0 =====
+#pragma unroll
+                    for (int j = 0; j < L; j++) w[j] = mk2(-e5 * a[j].y, e5 * a[j].x);
+                    pipe_sweep<VAR, L, GS, MULTI>(ops, S0, w, hw, g, G, GpS, bar_id);
+#pragma unroll
+                    for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(-e4, a[j].x, hw[j].x), fma(-e4, a[j].y, hw[j].y)) : mk2(0.0, 0.0);
+                    pipe_sweep<VAR, L, GS, MULTI>(ops, S1, w, hw, g, G, GpS, bar_id);
+#pragma unroll
+                    for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(e3, a[j].y, hw[j].x), fma(-e3, a[j].x, hw[j].y)) : mk2(0.0, 0.0);
+                    pipe_sweep<VAR, L, GS, MULTI>(ops, S0, w, hw, g, G, GpS, bar_id);
+#pragma unroll
+                    for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(e2, a[j].x, hw[j].x), fma(e2, a[j].y, hw[j].y)) : mk2(0.0, 0.0);
+                    pipe_sweep<VAR, L, GS, MULTI>(ops, S1, w, hw, g, G, GpS, bar_id);
+                    tm.tick(2);
+#pragma unroll
+                    for (int j = 0; j < L; j++) { const double2 v = U[j * GpU + GU + g]; w[j] = valid[j] ? mk2(v.x + hw[j].x, v.y + hw[j].y) : mk2(0.0, 0.0); }
+                    pipe_sweep<VAR, L, GS, MULTI>(ops, S0, w, hw, g, G, GpS, bar_id);
+#pragma unroll
+                    for (int j = 0; j < L; j++) U[j * GpU + GU + g] = valid[j] ? mk2(acc[j].x + hw[j].x, acc[j].y + hw[j].y) : mk2(0.0, 0.0);
                     }
                 }
                 mbar_arrive(&bars[X]);
@@ -502,6 +680,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                 if (g == 0) { p.step_count[traj] += iflag[1]; p.flags_latch[traj] = (unsigned char)iflag[0]; if (p.flags_out) p.flags_out[traj] = (unsigned char)iflag[0]; }
             }
             if (p.moments == nullptr && p.aux == nullptr) continue;
+            if constexpr (VAR == QC_QUARTIC) {
             double2 ext[L + 8];
 #pragma unroll
             for (int r = -4; r < L + 4; r++) { const double2 c = ld_rel_g<L, GU>(U, g, GpU, r); ext[r + 4] = (r >= 0 && r < L) ? psi[r] : mk2(sc * c.x, sc * c.y); }
@@ -603,6 +782,41 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
                     ax[QC_AUX_NORM] = p.w * v0[0];
                 }
             }
+            } else {
+                // get_data_xp (H/main_parallel.py:128-130) and phonon_number (H/main_parallel.py:88-89)
+                double v0[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // norm, <x>, <p>, |x psi|^2, |p psi|^2, Re<x psi|p psi>, <n>
+#pragma unroll
+                for (int j = 0; j < L; j++) {
+                    const int i = g * L + j;
+                    const double2 cn = ld_rel_g<L, GU>(U, g, GpU, j + 1), cp_ = ld_rel_g<L, GU>(U, g, GpU, j - 1);
+                    const double2 nx = (j + 1 < L) ? psi[j + 1 < L ? j + 1 : 0] : mk2(sc * cn.x, sc * cn.y);
+                    const double2 pv = (j - 1 >= 0) ? psi[j - 1 >= 0 ? j - 1 : 0] : mk2(sc * cp_.x, sc * cp_.y);
+                    const double xa = xl[j + 2], xb = xl[j + 1];
+                    const double xr_ = xa * nx.x + xb * pv.x, xi_ = xa * nx.y + xb * pv.y;                 // x psi
+                    const double dr = xb * pv.x - xa * nx.x, di = xb * pv.y - xa * nx.y;                   // p = i/sqrt2 (a^dag - a)  (H/main_parallel.py:66-67)
+                    const double pr = -di, pim = dr;
+                    const double a2 = psi[j].x * psi[j].x + psi[j].y * psi[j].y;
+                    v0[0] += a2;
+                    v0[1] += psi[j].x * xr_ + psi[j].y * xi_;
+                    v0[2] += psi[j].x * pr + psi[j].y * pim;
+                    v0[3] += xr_ * xr_ + xi_ * xi_;
+                    v0[4] += pr * pr + pim * pim;
+                    v0[5] += xr_ * pr + xi_ * pim;
+                    v0[6] = fma((double)i, a2, v0[6]);
+                }
+                traj_reduce<7, MULTI>(v0, red, red_phase, wq, NWG, lane, bar_id, G);
+                if (have && g == 0) {
+                    if (p.moments) {
+                        double* out = p.moments + (size_t)traj * p.K;
+                        out[0] = v0[1]; out[1] = v0[2];
+                        out[2] = v0[3] - v0[1] * v0[1]; out[3] = v0[4] - v0[2] * v0[2]; out[4] = v0[5] - v0[1] * v0[2];
+                    }
+                    if (p.aux) {
+                        double* ax = p.aux + (size_t)traj * QC_AUX_COUNT;
+                        ax[QC_AUX_ENERGY] = v0[6]; ax[QC_AUX_XMEAN] = v0[1]; ax[QC_AUX_OUTSIDE] = 0.0; ax[QC_AUX_NORM] = v0[0];
+                    }
+                }
+            }
             if (p.g_world > 0 && have && g < 32) publish_row(p, traj, lane);
         }
     }
@@ -614,7 +828,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
             const bool guard = r >= Geo::LBU0 || col < GU || col >= GU + G;
             if (guard && (Uall[e].x != 0.0 || Uall[e].y != 0.0)) atomicAdd(p.dbg_guard, 1u);
         }
-        for (int e = tid; e < NE * 2 * LBS; e += blockDim.x) {
+        for (int e = tid; e < NE * NS * LBS; e += blockDim.x) {
             const int col = (e % LBS) % GpS;
             if ((col < GS || col >= GS + G) && (Sall[e].x != 0.0 || Sall[e].y != 0.0)) atomicAdd(p.dbg_guard, 1u);
         }
@@ -629,7 +843,7 @@ __global__ void __launch_bounds__(PipeGeo<L, GC, NE>::THREADS, 1) sse_pipe_kerne
 }
 
 
-struct PipeEntry { int L, gc, ne, threads; kern_t fn; size_t (*smem)(int n_sub); };
-#define QC_PE(L, GC, NE) {L, GC, NE, PipeGeo<L, GC, NE>::THREADS, sse_pipe_kernel<L, GC, NE>, PipeGeo<L, GC, NE>::smem_bytes}
+struct PipeEntry { int var, L, gc, ne, threads; kern_t fn; size_t (*smem)(int n_sub); };
+#define QC_PE(VAR, L, GC, NE) {VAR, L, GC, NE, PipeGeo<VAR, L, GC, NE>::THREADS, sse_pipe_kernel<VAR, L, GC, NE>, PipeGeo<VAR, L, GC, NE>::smem_bytes}
 
 }  // namespace qc

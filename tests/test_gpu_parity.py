@@ -448,9 +448,9 @@ def test_full_size_properties_configs_3_and_4(task, B):
 
 # ---- the warp-specialised pipeline kernel (csrc/qc_pipe_impl.cuh): multi-warp grid trajectories in force-binned launches ----------------
 
-def _pipe_case(B, n_sub, seed, ragged_budget=False, one_bin=False, want_q=False):
+def _pipe_case(B, n_sub, seed, ragged_budget=False, one_bin=False, want_q=False, task="inverted_quartic"):
     torch = _torch()
-    params = configs.inverted_quartic(n_sub=n_sub)
+    params = configs.PRESETS[task](n_sub=n_sub)
     rng = np.random.default_rng(seed)
     psi0 = initial_states(params, B, seed)
     actions = rng.integers(0, params["n_levels"], B).astype(np.int32)
@@ -517,3 +517,35 @@ def test_pipeline_kernel_agrees_with_the_per_trajectory_kernel(monkeypatch):
         st = psi0[bidx].copy()
         orc.run(st, params["dt"], level_force(params, int(actions[bidx])), params["gamma"], noise[bidx][: budget[bidx]])
         assert rel_err(b[0][bidx][None], st[None]) < TOL_STEP
+
+
+@pytest.mark.parametrize("task", ["inverted_harmonic", "harmonic"])
+def test_pipeline_kernel_fock_systems_match_oracle(task, monkeypatch):
+    """The Fock instantiations of sse_pipe_kernel (inverted harmonic: two-warp groups with L = 3 incl. the HERMITIAN-descriptor term;
+    harmonic: eight one-warp groups) against the CPU oracle on a random subset, with ragged per-trajectory budgets, and against the
+    chunk-Jacobi kernel (QCART_PIPE=0) on everything."""
+    B, n_sub = 1400, 10
+    params, sim, out, psi0, actions, noise, budget = _pipe_case(B, n_sub, 31, ragged_budget=True, want_q=True, task=task)
+    assert "sse_pipe_kernel" in sim.kernel_info(), sim.kernel_info()
+    got = sim.get_state(); mom = out["moments"].cpu().numpy(); aux = out["aux"].cpu().numpy(); flags = out["flags"].cpu().numpy()
+    q = out["q"].cpu().numpy(); xm = out["x_mean"].cpu().numpy()
+    orc = oracle_for(params)
+    pick = np.random.default_rng(7).choice(B, 24, replace=False)
+    pick[:2] = [0, B - 1]
+    for b in pick:
+        st = psi0[b].copy()
+        nb = int(budget[b])
+        f, qq, xx = orc.run(st, params["dt"], level_force(params, int(actions[b])), params["gamma"], noise[b][:nb], want_q=True)
+        assert rel_err(got[b][None], st[None]) < TOL_STEP
+        obs, nph = fock_observation(st, sim.n)
+        assert np.max(np.abs(mom[b] - obs)) < 1e-9 and abs(aux[b, L.QC_AUX_ENERGY] - nph) < 1e-9
+        assert bool(flags[b] & L.QC_FLAG_FAIL) == bool(f)
+        if nb:
+            assert np.max(np.abs(xm[b][:nb] - xx)) < 1e-10
+            assert np.max(np.abs(q[b][:nb] - qq) / np.maximum(1.0, np.abs(qq))) < 1e-10
+    assert np.allclose(aux[:, L.QC_AUX_NORM], 1.0, atol=1e-12)
+    monkeypatch.setenv("QCART_PIPE", "0")
+    _, sim0, out0, *_ = _pipe_case(B, n_sub, 31, ragged_budget=True, task=task)
+    assert "sse_step_kernel" in sim0.kernel_info()
+    assert rel_err(got, sim0.get_state()) < 1e-12
+    assert np.array_equal(flags, out0["flags"].cpu().numpy())

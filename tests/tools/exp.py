@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
 import gpu_time
 
 TASK = {"iq": "inverted_quartic", "q": "quartic", "ih": "inverted_harmonic", "h": "harmonic"}
-KEYS = ("QCART_PIPE_NE", "QCART_L", "QCART_T", "QCART_P", "QCART_TABS", "QCART_GC", "QCART_JACOBI", "QCART_BIN", "QCART_MAXT", "QCART_STAGGER", "QCART_DEBUG", "QCART_XFER", "QCART_COOP", "QCART_PIPE")
+KEYS = ("QCART_PIPE_NE", "QCART_PIPE_L", "QCART_L", "QCART_T", "QCART_P", "QCART_TABS", "QCART_GC", "QCART_JACOBI", "QCART_BIN", "QCART_MAXT", "QCART_STAGGER", "QCART_DEBUG", "QCART_XFER", "QCART_COOP", "QCART_PIPE")
 
 if __name__ == "__main__":
     spec = sys.argv[1].split(":")
