@@ -53,7 +53,9 @@ template <int L, int GD> __device__ __forceinline__ double2 ld_rel_g(const doubl
 }
 
 // geometry shared by host (plan) and device
-template <int VAR, int L, int GC, int NE> struct PipeGeo {
+// TABG: the factor table of the CTA's force level stays in global memory (L2 / L1 resident) instead of shared memory: grids whose table
+// (80 N bytes) would not leave room for the lines.
+template <int VAR, int L, int GC, int NE, bool TABG = false> struct PipeGeo {
     static constexpr int G = GC, NWG = GC / 32, TT = 2 * NE, CPT = 32 / NE;
     static constexpr int BA = VarTraits<VAR>::BA;
     // sweep lines per explicit group: two alternate in the Horner chain (the Fock systems first use them for Y+ / Y-); the inverted harmonic
@@ -80,7 +82,7 @@ template <int VAR, int L, int GC, int NE> struct PipeGeo {
     static constexpr int LASTW = SOLO ? (NXW - 1) + (NXW - 1) / 3 : NXW + 1;     // highest warp id in use
     static constexpr int WARPS = ((LASTW > 7 || !SOLO ? LASTW : 7) + 4) / 4 * 4;
     static constexpr int THREADS = WARPS * 32;
-    static constexpr size_t tab_bytes = (size_t)CS * L * G * 16 + (size_t)HT * L * G * 8;
+    static constexpr size_t tab_bytes = TABG ? 0 : (size_t)CS * L * G * 16 + (size_t)HT * L * G * 8;
     static constexpr size_t fixed_bytes = tab_bytes + (size_t)TT * LBU * 16 + (size_t)NE * NS * LBS * 16 + (size_t)TT * 128 /* scal */ +
                                           (size_t)NE * 2 * QC_MAXRED * NWG * 8 /* red */ + (size_t)NE * 128 /* stash */ + 64 /* mbarriers */;
     static size_t smem_bytes(int n_sub) { return fixed_bytes + (size_t)TT * n_sub * 16; }
@@ -91,10 +93,10 @@ template <int VAR, int L, int GC, int NE> struct PipeGeo {
 // lane = cc*NE + tt: chunk cc (mult columns = mult*L points) of trajectory tt; both substitutions start wb columns outside the chunk with
 // zero history (same truncation as solve_traj).  z overwrites the right-hand side and x overwrites z: every lane reads its warm-up region
 // (which belongs to the neighbour chunk) before any lane writes, the warp runs converged and __syncwarp separates the two parts.
-template <int VAR, int L, int GC, int NE>
+template <int VAR, int L, int GC, int NE, bool TABG>
 __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restrict__ Uset, const double2* __restrict__ tab, double* scal_set, int mult, int wb,
                                            int lane, int s, PipeTimers& tm) {
-    typedef PipeGeo<VAR, L, GC, NE> Geo;
+    typedef PipeGeo<VAR, L, GC, NE, TABG> Geo;
     constexpr int BA = Geo::BA, CS = Geo::CS, G = Geo::G, Gp = Geo::GpU, GUARD = Geo::GU;
     const int tt = lane % NE, cc = lane / NE;
     double2* __restrict__ U = Uset + (size_t)tt * Geo::LBU;
@@ -105,6 +107,12 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
     const bool act = (col0 < cols) && (s < iflag[1]);          // iflag[1] = substep budget of the trajectory (0 when the slot is empty)
     double nrm = 0.0, sx = 0.0, cen = 0.0;
     struct Row { double2 v; double2 cf[BA + 1]; };
+    // factor entry k of point (col, j): shared-memory copy [j][k][column], or (TABG) the global table [point][k] (zero outside the grid)
+    const int npts = p.n;
+    auto tabv = [&](int j, int k, int col) -> double2 {
+        if constexpr (!TABG) return tab[(j * CS + k) * G + min(max(col, 0), G - 1)];
+        else { const int i = col * L + j; return (i >= 0 && i < npts) ? __ldg(&tab[(size_t)i * (BA + 1) + k]) : mk2(0.0, 0.0); }
+    };
     constexpr int PF = (L % (QC_PIPE_PF + 1) == 0) ? QC_PIPE_PF : 2, NR = PF + 1;      // the row ring restarts with every column: L must be a multiple of NR
     static_assert(L % NR == 0, "row ring: L must be a multiple of PF + 1");
     // ---- forward: L y = rhs in column (scatter) form, z = D^{-1} y --------------------------------------------------------------
@@ -117,9 +125,9 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
 #pragma unroll
             for (int k = 1; k <= BA; k++) {
                 const int jj = (j + k) % L, dc = (j + k) / L;
-                r.cf[k - 1] = tab[(jj * CS + (k - 1)) * G + min(max(col + dc, 0), G - 1)];
+                r.cf[k - 1] = tabv(jj, k - 1, col + dc);
             }
-            r.cf[BA] = tab[(j * CS + BA) * G + min(max(col, 0), G - 1)];
+            r.cf[BA] = tabv(j, BA, col);
         };
         double2 pend[BA];
 #pragma unroll
@@ -161,11 +169,10 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
         const bool do_cen = (VAR == QC_QUARTIC) && p.cen_hi > p.cen_lo;
         double2 xprev = mk2(0.0, 0.0);                          // Fock: x_{i+1} for <x> = sum 2 xl_i Re(conj(x_i) x_{i+1})
         auto load_row = [&](Row& r, int col, int j, bool) {
-            const int tc = min(max(col, 0), G - 1);
             r.v = U[j * Gp + GUARD + col];
 #pragma unroll
-            for (int k = 0; k < BA; k++) r.cf[k] = tab[(j * CS + k) * G + tc];
-            if constexpr (VAR != QC_QUARTIC) r.cf[BA] = tab[(j * CS + BA + 1) * G + tc];      // (xl_i, 0)
+            for (int k = 0; k < BA; k++) r.cf[k] = tabv(j, k, col);
+            if constexpr (VAR != QC_QUARTIC) r.cf[BA] = tabv(j, BA + 1, col);      // (xl_i, 0)
         };
         Row ring[NR];
         int col = col0 + mult + wb - 1;
@@ -248,9 +255,10 @@ __device__ __forceinline__ void pipe_sweep(const LaneOps<VAR, L>& ops, double2* 
 }
 
 // ------------------------------------------------------------------------------------------------------
-template <int VAR, int L, int GC, int NE>
-__global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE>::THREADS, 1) sse_pipe_kernel(const StepParams p) {
-    typedef PipeGeo<VAR, L, GC, NE> Geo;
+template <int VAR, int L, int GC, int NE, bool TABG>
+__global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG>::THREADS, 1) sse_pipe_kernel(const StepParams p) {
+    typedef PipeGeo<VAR, L, GC, NE, TABG> Geo;
+    static_assert(!TABG || VAR == QC_QUARTIC, "global factor table: grid only");
     constexpr int G = Geo::G, NWG = Geo::NWG, TT = Geo::TT, GpU = Geo::GpU, GpS = Geo::GpS, LBU = Geo::LBU, LBS = Geo::LBS, CS = Geo::CS;
     constexpr int GU = Geo::GU, GS = Geo::GS, NS = Geo::NS, HT = Geo::HT, BA = Geo::BA;
     constexpr bool MULTI = NWG > 1;                                  // one-warp groups synchronise with __syncwarp
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE>::THREADS, 1) sse_pipe_
     const int bar_id = 1 + e;
 
     double2* tab = reinterpret_cast<double2*>(smem);
-    double* khs = reinterpret_cast<double*>(tab + (size_t)CS * L * G);               // [L][HT][G] band of Im C (inverted harmonic)
+    double* khs = reinterpret_cast<double*>(tab + (TABG ? 0 : (size_t)CS * L * G));  // [L][HT][G] band of Im C (inverted harmonic)
     double2* Uall = reinterpret_cast<double2*>(khs + (size_t)HT * L * G);            // [2][NE] state lines, stride LBU
     double2* Sall = Uall + (size_t)TT * LBU;                        // [NE][NS] sweep lines
     double* scal_all = reinterpret_cast<double*>(Sall + (size_t)NE * NS * LBS);     // [TT][16]: scale, <x>, ..., (int) flags, budget, trajectory id
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE>::THREADS, 1) sse_pipe_
         mbar_init(&bars[0], NE * G); mbar_init(&bars[1], NE * G); mbar_init(&bars[2], 32); mbar_init(&bars[3], 32);
     }
     __syncthreads();
-    {
+    if constexpr (!TABG) {
         const double2* __restrict__ fs = p.fac + (size_t)cta_slot * n * (BA + 1);
         for (int i = tid; i < G * L; i += blockDim.x) {
             const int jj = i % L, cc = i / L;
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE>::THREADS, 1) sse_pipe_
             for (int s = 0; s < n_sub; s++) {
                 mbar_wait(&bars[X], s & 1);
                 tm.tick(0);
-                pipe_solve<VAR, L, GC, NE>(p, Uall + (size_t)X * NE * LBU, tab, scal_all + X * NE * 16, mult, wb, lane, s, tm);
+                pipe_solve<VAR, L, GC, NE, TABG>(p, Uall + (size_t)X * NE * LBU, TABG ? p.fac + (size_t)cta_slot * n * (BA + 1) : tab, scal_all + X * NE * 16, mult, wb, lane, s, tm);
                 mbar_arrive(&bars[2 + X]);
                 tm.tick(3);
             }
@@ -844,6 +852,7 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE>::THREADS, 1) sse_pipe_
 
 
 struct PipeEntry { int var, L, gc, ne, threads; kern_t fn; size_t (*smem)(int n_sub); };
-#define QC_PE(VAR, L, GC, NE) {VAR, L, GC, NE, PipeGeo<VAR, L, GC, NE>::THREADS, sse_pipe_kernel<VAR, L, GC, NE>, PipeGeo<VAR, L, GC, NE>::smem_bytes}
+#define QC_PE(VAR, L, GC, NE) {VAR, L, GC, NE, PipeGeo<VAR, L, GC, NE>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, false>, PipeGeo<VAR, L, GC, NE>::smem_bytes}
+#define QC_PE_TABG(VAR, L, GC, NE) {VAR, L, GC, NE, PipeGeo<VAR, L, GC, NE, true>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, true>, PipeGeo<VAR, L, GC, NE, true>::smem_bytes}
 
 }  // namespace qc
