@@ -177,18 +177,20 @@ def test_env_reset_step_protocol(task):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("task", ["quartic", "harmonic"])
+@pytest.mark.parametrize("task", ["quartic", "harmonic", "inverted_quartic_pipeline"])
 def test_fused_result_exchange_single_process_ranks(task):
     """qc_set_gather: three sims on one device play three ranks; every rank's gather area ends up with all rows, in rank order, equal to
     pack_block of each rank's own outputs, for six consecutive control steps (four buffers, plain and overlapped consumer schedule); the
     bounded wait reports ranks that never publish; unequal batch sizes are refused."""
     import torch
     from deepreinforcementlearningcontrolofquantumcartpoles_b200 import dist as qdist
-    params = configs.PRESETS[task](n_sub=8)
     B, world = 40, 3
+    if task == "inverted_quartic_pipeline":                    # a batch that selects sse_pipe_kernel: its epilogue publishes the rows too
+        task, B = "inverted_quartic", 1400
+    params = configs.PRESETS[task](n_sub=8)
     sims = [BatchedSim(params, batch=B, seed=3, traj_offset=r * B) for r in range(world)]
     for r, s in enumerate(sims):
-        s.set_state(initial_states(params, B, seed=10 + r))
+        s.set_state(np.tile(initial_states(params, 40, seed=10 + r), ((B + 39) // 40, 1))[:B])
     fgs = qdist.FusedGather.local_group(sims)
     g = torch.Generator(device="cuda"); g.manual_seed(1)
     expect = {}
@@ -199,6 +201,8 @@ def test_fused_result_exchange_single_process_ranks(task):
             out = s.step(act)
             packed.append(qdist.pack_block(out["moments"], out["aux"], out["flags"]))
         expect[step] = torch.cat(packed, dim=0)
+        if B > 1000:
+            assert "sse_pipe_kernel" in sims[0].kernel_info()
         for fg in fgs:
             assert fg.seq() == step
             if step % 2 == 1:                                  # plain schedule: wait for the step just enqueued
