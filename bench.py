@@ -271,11 +271,18 @@ def measure_extra(task, params, B, steps, warmup, rank, world, local_rank, flush
         ms = float(t.item())
     fpu = flops_per_unit(task, n, params["n_sub"])
     ach = B / (ms * 1e-3) * fpu / 1e12
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_static.json"))).get(task, {})
+        if B == 8192 and not tag.startswith("BASELINE configs[4]"):
+            traffic = prof.get("dram_bytes_per_launch")
+    except Exception:
+        pass
     rec = {"workload": workload_name(task, B, n, params["n_sub"]) + (" [%s]" % tag if tag else ""), "value": world * B / (ms * 1e-3), "unit": "traj-control-steps/s",
            "n_gpus": world, "global_trajectories": world * B, "steps": steps, "warmup": warmup, "ms_per_step": ms, "gpu_launches": int(sim.launch_count() - l0),
            "max_norm_deviation": float((out["aux"][:, L.QC_AUX_NORM] - 1).abs().max().item()),
-           "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": ach / (fp64_peak / 1e12), "flops_per_unit": fpu,
-                        "kernel": sim.kernel_info(), "hbm_algorithmic_GBps": B * (32.0 * n + 8.0 * sim.K + 37) / (ms * 1e-3) / 1e9}}
+           "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": ach / (fp64_peak / 1e12), "traffic": traffic, "flops_per_unit": fpu,
+                        "kernel": sim.kernel_info(), "hbm_algorithmic_bytes_per_launch": B * (32.0 * n + 8.0 * sim.K + 37), "hbm_algorithmic_GBps": B * (32.0 * n + 8.0 * sim.K + 37) / (ms * 1e-3) / 1e9}}
     del sim
     return rec
 
