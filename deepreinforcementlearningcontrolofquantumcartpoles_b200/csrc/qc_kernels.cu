@@ -91,7 +91,7 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
     // register-resident chunk-Jacobi kernel (0.55 vs 0.73 ms at 1024 and 3.7 vs 3.9 ms at 8192 trajectories of config 2).
     if (n_sub > 0 && env_int("QCART_PIPE", 1) && !forceL && env_int("QCART_BIN", -1) != 0) {
         const int L = env_int("QCART_PIPE_L", (var == QC_QUARTIC) ? 6 : 3), cols = (n + L - 1) / L, G = (cols + 31) / 32 * 32, W = (W_needed + L - 1) / L * L;
-        const int want_ne = env_int("QCART_PIPE_NE", (var == QC_HARMONIC) ? 8 : ((var == QC_INV_HARMONIC) ? 4 : 0));
+        const int want_ne = env_int("QCART_PIPE_NE", (var == QC_HARMONIC) ? 8 : ((var == QC_INV_HARMONIC) ? 4 : (G >= 128 ? 1 : 0)));
         const PipeEntry* pe = qc_find_pipe(var, L, G, want_ne);
         const int GUc = (G == 32) ? 10 : ((var == QC_QUARTIC) ? 5 : 12);
         if (pe && W <= (GUc - 1) * L && (int)pe->smem(n_sub) <= smem_max) {
@@ -102,7 +102,8 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             // case (every bin one trajectory past a CTA) still fits one wave of CTAs, so that no SM ever runs a second, nearly empty round.
             const long long worst_ctas = ((long long)B + (long long)m.cfg.n_levels * (TT - 1) + TT - 1) / TT;
             const bool allowed = var != QC_QUARTIC || G > 32;
-            const bool big = allowed && B >= 8 * n_sm && B >= 64 * m.cfg.n_levels;
+            // large batch: at least one CTA per SM and bins that are not mostly padding (every force level is padded to whole CTAs)
+            const bool big = allowed && B >= TT * n_sm && B >= 8 * TT * m.cfg.n_levels;
             const bool one_wave = allowed && var == QC_QUARTIC && B >= 16 * m.cfg.n_levels && worst_ctas <= n_sm;
             if ((big || one_wave || env_int("QCART_PIPE", 1) == 2) && c_last < cpt && c_last * mult + mult + W / L <= G + GU) {
                 cudaFuncAttributes fa;

@@ -25,6 +25,10 @@ def run(npts, B, env, steps=3):
     fl = 160 * 568.0 * npts + 250.0 * npts
     print("N=%d B=%d %-16s %8.3f ms  %8.0f traj/s  %.1f%% | %s" % (npts, B, env, ms, B / ms * 1e3, B / ms * 1e3 * fl / 35.86e12 * 100, sim.kernel_info()), flush=True)
     return psi
-for npts, B in ((769, 4096), (1025, 2048)):
-    a = run(npts, B, {"QCART_PIPE": "0"}); b = run(npts, B, {})
-    print("   max rel diff", float(np.max(np.linalg.norm(a - b, axis=1) / np.linalg.norm(a, axis=1))))
+cases = [(int(a.split(":")[0]), int(a.split(":")[1])) for a in sys.argv[1:] if ":" in a and "=" not in a] or [(2049, 1024), (1281, 2048)]
+envs = [dict(kv.split("=") for kv in a.split()) for a in sys.argv[1:] if "=" in a] or [{}]
+for npts, B in cases:
+    a = run(npts, B, {"QCART_PIPE": "0"})
+    for env in envs:
+        b = run(npts, B, env)
+        print("   max rel diff", float(np.max(np.linalg.norm(a - b, axis=1) / np.linalg.norm(a, axis=1))))
