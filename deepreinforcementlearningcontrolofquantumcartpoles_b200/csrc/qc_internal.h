@@ -99,7 +99,7 @@ struct StepParams {
 
 struct LaunchPlan {
     int L, T, G, P, chunk, W, NP, threads, smem_bytes, tstride, maxt, gc;
-    bool tabs; int jacobi; int xfer; int binned; int smem_cta_extra; int vglobal; long long vglobal_elems_per_traj; int herm_smem; int stagger; int pipe;
+    bool tabs; int jacobi; int xfer; int binned; int smem_cta_extra; int vglobal; long long vglobal_elems_per_traj; int herm_smem; int stagger; int pipe; int cluster;
     char info[240];
 };
 

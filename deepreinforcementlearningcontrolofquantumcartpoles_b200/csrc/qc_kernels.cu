@@ -21,6 +21,8 @@ const KernEntry* qc_entries_fock_ih2(int* count);
 
 struct PipeEntry { int var, L, gc, ne, threads; kern_t fn; size_t (*smem)(int n_sub); };
 const PipeEntry* qc_find_pipe(int var, int L, int G, int ne);
+struct ClusterEntry { int L, gsl, c, threads; kern_t fn; size_t (*smem)(int n_sub); };
+const ClusterEntry* qc_find_cluster(int L, int cols);
 
 static std::vector<KernEntry> all_kernels() {
     std::vector<KernEntry> v;
@@ -83,6 +85,22 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
     const int forceL = env_int("QCART_L", 0), forceT = env_int("QCART_T", 0), forceP = env_int("QCART_P", 0);
     const int forceTabs = env_int("QCART_TABS", -1), forceGC = env_int("QCART_GC", -1);
     const int CS = (var == QC_QUARTIC) ? m.ba + 1 : m.ba + 2;
+    // Grids that do not fit one SM (more than 352 columns of 6 points): one trajectory per thread-block cluster (qc_cluster_impl.cuh).
+    // QCART_CLUSTER=0: off (the single-CTA instances with local-memory spills handle N <= 9216).
+    if (var == QC_QUARTIC && env_int("QCART_CLUSTER", 1) && !forceL) {
+        const int L = 6, cols = (n + L - 1) / L, W = (W_needed + L - 1) / L * L;
+        const ClusterEntry* ce = (cols > 352 || env_int("QCART_CLUSTER", 1) == 2) ? qc_find_cluster(L, cols) : nullptr;
+        if (ce && W <= 4 * L && (int)ce->smem(n_sub) <= smem_max) {
+            cudaFuncAttributes fa;
+            if (cudaFuncGetAttributes(&fa, (const void*)ce->fn) != cudaSuccess) { err = std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(cudaGetLastError()); return QC_ERR_CUDA; }
+            memset(&plan, 0, sizeof(plan));
+            plan.L = L; plan.T = 1; plan.G = ce->gsl; plan.P = 32; plan.chunk = ce->gsl / 32 * L; plan.W = W; plan.NP = ce->gsl * ce->c * L; plan.threads = ce->threads;
+            plan.smem_bytes = (int)ce->smem(n_sub); plan.maxt = ce->threads; plan.gc = ce->gsl; plan.tabs = false; plan.cluster = ce->c;
+            snprintf(plan.info, sizeof(plan.info), "sse_cluster_kernel<L=%d,slice=%d lanes,C=%d> 1 trajectory per cluster of %d CTAs, chunk=%d W=%d threads=%d smem=%d regs=%d lmem=%d",
+                     L, ce->gsl, ce->c, ce->c, plan.chunk, W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
+            return QC_OK;
+        }
+    }
     // Force-binned launches: the warp-specialised pipeline (qc_pipe_impl.cuh).  QCART_PIPE=0: off, 2: whenever an instance exists;
     // QCART_PIPE_NE / QCART_PIPE_L: groups per CTA / points per lane (experiments).
     // Geometry per system (measured, 8192 trajectories): grid with several warps per trajectory L = 6 (config 4: 28.6 -> 17.5 ms);
@@ -200,6 +218,21 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
 }
 
 int launch_step(const LaunchPlan& plan, const StepParams& p, void* stream, std::string& err) {
+    if (plan.cluster) {
+        const ClusterEntry* ce = qc_find_cluster(plan.L, (p.n + plan.L - 1) / plan.L);
+        if (!ce || ce->c != plan.cluster) { err = "cluster kernel not found"; return QC_ERR_UNSUPPORTED; }
+        if (cudaFuncSetAttribute((const void*)ce->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes) != cudaSuccess) {
+            err = std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(cudaGetLastError()); return QC_ERR_CUDA;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(p.B * plan.cluster)); cfg.blockDim = dim3((unsigned)plan.threads); cfg.dynamicSmemBytes = (size_t)plan.smem_bytes; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)plan.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, ce->fn, p);
+        if (e != cudaSuccess) { cudaGetLastError(); err = std::string("cluster kernel launch: ") + cudaGetErrorString(e) + " [" + plan.info + "]"; return QC_ERR_CUDA; }
+        return QC_OK;
+    }
     if (plan.pipe) {
         const PipeEntry* pe = qc_find_pipe(p.variant, plan.L, plan.G, plan.pipe);
         if (!pe) { err = "pipeline kernel not found"; return QC_ERR_UNSUPPORTED; }

@@ -250,7 +250,19 @@ def test_edge_cases_empty_ragged_and_oversized():
         sim.step(torch.as_tensor(act[:B], device="cuda"), noise=torch.as_tensor(noise[:B], device="cuda"))
         got[B] = sim.get_state()
     assert np.array_equal(got[Bbig][:37], got[37])
-    big = configs.quartic_sweep(9473)                              # 9473 > 9216 points
+    # 9473 points: beyond what one CTA can hold (9216) -- a cluster of 8 CTAs takes it (up to 10 752); compare with the oracle
+    mid = configs.quartic_sweep(9473, n_sub=3)
+    sim = BatchedSim(mid, batch=2)
+    p0 = initial_states(mid, 2, seed=6)
+    sim.set_state(p0)
+    nz = np.random.default_rng(3).standard_normal((2, 3, 2))
+    sim.step(torch.as_tensor(np.array([4, 17], np.int32), device="cuda"), noise=torch.as_tensor(nz, device="cuda"))
+    assert "sse_cluster_kernel" in sim.kernel_info() and "C=8" in sim.kernel_info()
+    from common import oracle_for, oracle_control_step
+    ref, _, _ = oracle_control_step(oracle_for(mid), mid, p0, np.array([4, 17], np.int32), nz)
+    got = sim.get_state()
+    assert float(np.max(np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1))) < 1e-10
+    big = configs.quartic_sweep(10801)                             # beyond 8 CTAs x 224 lanes x 6 points: reported, not mis-computed
     with pytest.raises(L.QcartError) as e:
         sim = BatchedSim(big, batch=2)
         sim.step(torch.zeros(2, dtype=torch.int32, device="cuda"))

@@ -549,3 +549,68 @@ def test_pipeline_kernel_fock_systems_match_oracle(task, monkeypatch):
     assert "sse_step_kernel" in sim0.kernel_info()
     assert rel_err(got, sim0.get_state()) < 1e-12
     assert np.array_equal(flags, out0["flags"].cpu().numpy())
+
+
+@pytest.mark.parametrize("npts,B", [(1281, 340), (2049, 340)])
+def test_wide_grid_pipeline_matches_oracle(npts, B):
+    """Single-group pipeline instances with the factor table in global memory (N = 577 .. 2112): a subset against the oracle."""
+    torch = _torch()
+    params = configs.quartic_sweep(npts, n_sub=4)
+    rng = np.random.default_rng(9)
+    psi0 = np.tile(initial_states(params, 4, 3), (B // 4, 1))
+    actions = rng.integers(0, 21, B).astype(np.int32)
+    noise = rng.standard_normal((B, 4, 2))
+    sim = BatchedSim(params, batch=B)
+    sim.set_state(psi0)
+    out = sim.step(torch.as_tensor(actions, device="cuda"), noise=torch.as_tensor(noise, device="cuda"))
+    torch.cuda.synchronize()
+    assert "sse_pipe_kernel" in sim.kernel_info() and "NE=1" in sim.kernel_info(), sim.kernel_info()
+    pick = np.array([0, 1, B // 2, B - 1])
+    orc = oracle_for(params)
+    ref, fails, _ = oracle_control_step(orc, params, psi0[pick], actions[pick], noise[pick])
+    assert rel_err(sim.get_state()[pick], ref) < TOL_STEP
+    mom = out["moments"].cpu().numpy()
+    for k, b in enumerate(pick):
+        m_ref = orc.get_moments(ref[k])
+        assert np.max(np.abs(mom[b][:5] - m_ref[:5]) / np.maximum(np.abs(m_ref[:5]), 1e-3)) < 1e-9
+
+
+@pytest.mark.parametrize("npts", [2501, 4097])
+def test_cluster_kernel_matches_oracle(npts):
+    """One trajectory per thread-block cluster (N > 2112): state, all 20 moments, energy, <x>, q / <x> streams and flags against the oracle,
+    with ragged per-trajectory substep budgets; bitwise deterministic run to run; agrees with the single-CTA instance (QCART_CLUSTER=0 in
+    the other tests' history) to rounding level."""
+    torch = _torch()
+    n_sub = 5
+    params = configs.quartic_sweep(npts, n_sub=n_sub)
+    B = 5
+    rng = np.random.default_rng(13)
+    psi0 = initial_states(params, B, 8)
+    actions = np.array([0, 6, 10, 15, 20], np.int32)
+    noise = rng.standard_normal((B, n_sub, 2))
+    budget = np.array([5, 0, 3, 5, 1], np.int32)
+    runs = []
+    for rep in range(2):
+        sim = BatchedSim(params, batch=B)
+        sim.set_state(psi0)
+        out = sim.step(torch.as_tensor(actions, device="cuda"), noise=torch.as_tensor(noise, device="cuda"), want_q=True,
+                       nsub_traj=torch.as_tensor(budget, device="cuda"))
+        torch.cuda.synchronize()
+        assert "sse_cluster_kernel" in sim.kernel_info(), sim.kernel_info()
+        runs.append((sim.get_state(), out["moments"].cpu().numpy(), out["aux"].cpu().numpy(), out["flags"].cpu().numpy(), out["q"].cpu().numpy(), out["x_mean"].cpu().numpy()))
+    for a, b in zip(runs[0][:4], runs[1][:4]):
+        assert np.array_equal(a, b)
+    got, mom, aux, flags, q, xm = runs[0]
+    orc = oracle_for(params)
+    for b in range(B):
+        st = psi0[b].copy()
+        nb = int(budget[b])
+        f, qq, xx = orc.run(st, params["dt"], level_force(params, int(actions[b])), params["gamma"], noise[b][:nb], want_q=True)
+        assert rel_err(got[b][None], st[None]) < TOL_STEP
+        m_ref = orc.get_moments(st)
+        assert np.max(np.abs(mom[b] - m_ref) / np.maximum(np.abs(m_ref), 1e-3)) < TOL_STEP
+        assert abs(aux[b, L.QC_AUX_XMEAN] - orc.x_expectation(st)) < 1e-10 and abs(aux[b, L.QC_AUX_NORM] - 1) < 1e-12
+        assert bool(flags[b] & L.QC_FLAG_FAIL) == bool(f)
+        if nb:
+            assert np.max(np.abs(xm[b][:nb] - xx)) < 1e-10
+            assert np.max(np.abs(q[b][:nb] - qq) / np.maximum(1.0, np.abs(qq))) < 1e-10

@@ -28,7 +28,7 @@ def run(npts, B, env, steps=3):
 cases = [(int(a.split(":")[0]), int(a.split(":")[1])) for a in sys.argv[1:] if ":" in a and "=" not in a] or [(2049, 1024), (1281, 2048)]
 envs = [dict(kv.split("=") for kv in a.split()) for a in sys.argv[1:] if "=" in a] or [{}]
 for npts, B in cases:
-    a = run(npts, B, {"QCART_PIPE": "0"})
+    a = run(npts, B, {"QCART_PIPE": "0", "QCART_CLUSTER": "0"})
     for env in envs:
         b = run(npts, B, env)
         print("   max rel diff", float(np.max(np.linalg.norm(a - b, axis=1) / np.linalg.norm(a, axis=1))))
