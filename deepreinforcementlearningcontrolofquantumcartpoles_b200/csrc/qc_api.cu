@@ -393,8 +393,8 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
     if (!dbg_g) { cudaMallocManaged(&dbg_g, sizeof(unsigned int)); *dbg_g = 0; g_dbg_guard = dbg_g; }
     p.dbg_guard = dbg_g;
     static unsigned long long* dbg_t = nullptr; static int dbg_n = 0;
-    const bool timers = getenv("QCART_TIMERS") && pl.pipe;
-    const int dbg_grid = (int)((b.B + pl.T - 1) / pl.T) + s->n_slots;
+    const bool timers = getenv("QCART_TIMERS") && (pl.pipe || pl.cluster);
+    const int dbg_grid = pl.cluster ? (int)b.B : (int)((b.B + pl.T - 1) / pl.T) + s->n_slots;
     if (timers) {
         if (dbg_n < dbg_grid) { cudaFree(dbg_t); cudaMallocManaged(&dbg_t, sizeof(unsigned long long) * 16 * dbg_grid); dbg_n = dbg_grid; }
         memset(dbg_t, 0, sizeof(unsigned long long) * 16 * dbg_grid);
@@ -412,7 +412,12 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
         cudaStreamSynchronize((cudaStream_t)stream);
         double acc[16] = {0}; int used = 0;
         for (int c = 0; c < dbg_grid; c++) { if (dbg_t[16 * c + 15] == 0) continue; used++; for (int k = 0; k < 16; k++) acc[k] += (double)dbg_t[16 * c + k]; }
-        if (used) {
+        if (used && pl.cluster) {
+            const double per = 1.0 / used / std::max(1, n_sub);
+            fprintf(stderr, "[timers] clusters %d  cycles per substep: explicit thread 0: pass1 %.0f reduce-waits %.0f sweeps %.0f rhs+sync %.0f wait-fwd %.0f sync %.0f wait-bwd %.0f | solver lane 0: wait-explicit %.0f reduces %.0f sweep-syncs %.0f rhs-sync %.0f fwd %.0f sync %.0f bwd %.0f | total %.0f\n",
+                    used, acc[0] * per, acc[1] * per, acc[2] * per, acc[3] * per, acc[4] * per, acc[5] * per, acc[6] * per,
+                    acc[8] * per, acc[9] * per, acc[10] * per, acc[11] * per, acc[12] * per, acc[13] * per, acc[14] * per, acc[15] * per);
+        } else if (used) {
             const double per = 1.0 / used / std::max(1, n_sub);
             fprintf(stderr, "[timers] CTAs %d  cycles per substep-round: explicit(grp0 warp0): wait %.0f pass1 %.0f horner %.0f tail %.0f | solver A: wait %.0f fwd %.0f bwd %.0f fin %.0f | total %.0f\n",
                     used, acc[0] * per, acc[1] * per, acc[2] * per, acc[3] * per, acc[4] * per, acc[5] * per, acc[6] * per, acc[7] * per, acc[15] * per);

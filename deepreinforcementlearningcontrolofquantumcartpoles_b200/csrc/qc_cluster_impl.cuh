@@ -116,6 +116,12 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
     int* iflag = reinterpret_cast<int*>(scal + 8);
     double* nz = scal + 32;                                       // [n_sub][2]
     int phase = 0;
+#ifdef QC_DEBUG_HOOKS
+    long long t_last = clock64(); const long long t_begin = t_last; unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define QC_CT(k) do { const long long t_now = clock64(); t_acc[k] += (unsigned long long)(t_now - t_last); t_last = t_now; } while (0)
+#else
+#define QC_CT(k) do { } while (0)
+#endif
 
     const int slot = min(max(p.slot[traj], 0), p.n_slots - 1);
     const double F = p.slot_force[slot];
@@ -208,6 +214,7 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
         }
     };
 
+    QC_CT(7);
     for (int s = 0; s < my_nsub; s++) {                            // (my_nsub is uniform over the cluster)
         const double r0 = nz[2 * s], r1 = nz[2 * s + 1];
         const double dW = r0 * sdt, dZ = sdt * dt * 0.5 * (r0 + r1 / sqrt(3.0));       // Q:573
@@ -239,7 +246,9 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
                 m[0] += xp2; m[1] = fma(x, xp2, m[1]); m[2] = fma(x2, xp2, m[2]); m[3] = fma(x, m2, m[3]);
             }
         }
+        QC_CT(0);
         cluster_reduce<4, C, NWT>(cluster, m, wred, cred, phase, rank);
+        QC_CT(1);
         if (!is_solver) {
             const double xbp = p.w * m[0], xbm = p.w * m[3];       // un-normalised <x> of Y+-, Phi+- (Q:457-460, 605-615, 479-482)
             const double t1 = m[1] - xbp * m[0], t2 = m[2] - 2.0 * xbp * m[1] + xbp * xbp * m[0];
@@ -287,6 +296,7 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
             for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(v1[j].x + hw[j].x, v1[j].y + hw[j].y) : mk2(0.0, 0.0);
         }
         sweep(S0, w, hw);
+        QC_CT(2);
         // right-hand side of the implicit solve into the state line; 4 edge columns to the neighbours (warm-up of their substitutions)
         if (!is_solver) {
             double2 rhs[L];
@@ -295,6 +305,7 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
             push_halo<L>(cluster, U, GpU, GU, GSL, 4, g, rank, C, rhs);
         }
         cluster_rendezvous(!is_solver && (g < 4 || g >= GSL - 4));
+        QC_CT(3);
         // ---- implicit solve: forward sweep (solver warp), z of the first 4 columns to the left neighbour, backward sweep ----------------
         double part[5] = {0.0, 0.0, 0.0, 0.0, 0.0};               // norm, sum x|psi|^2, centre probability, low / high boundary norms
         const int col0 = lane * mult;
@@ -347,7 +358,9 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
                 for (int e = lane; e < wb * L; e += 32) { const int c = e / L, j = e % L; nb[j * GpU + GU + GSL + c] = U[j * GpU + GU + c]; }
             }
         }
+        QC_CT(4);
         cluster_rendezvous(is_solver);
+        QC_CT(5);
         if (act) {
             double2 pend[BA];
 #pragma unroll
@@ -392,7 +405,9 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
             __syncwarp(__activemask());
             for (int b = 0; b < mult; b++, col--) bwd_col(true);
         }
+        QC_CT(6);
         cluster_reduce<5, C, NWT>(cluster, part, wred, cred, phase, rank);
+        QC_CT(1);
         sc = rsqrt(part[0] * p.w);                                 // normalize(): psi / (||psi||_2 sqrt(w))   (Q:259-263)
         const double s2 = sc * sc;
         xbar = p.w * part[1] * s2;
@@ -404,6 +419,13 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
         }
     }
 
+#ifdef QC_DEBUG_HOOKS
+    if (p.dbg_timers && rank == 0 && (tid == 0 || tid == GSL)) {
+        unsigned long long* o = p.dbg_timers + 16 * (size_t)(blockIdx.x / C) + (tid == 0 ? 0 : 8);
+        for (int k = 0; k < 7; k++) o[k] = t_acc[k];
+        if (tid == 0) o[15 - 8] = 0; else o[7] = (unsigned long long)(clock64() - t_begin);
+    }
+#endif
     // ---- epilogue: normalised state -> HBM, compute_statistics (Q:325-362), cal_energy, outside probability, flags ------------------------
     double2 psi[L];
 #pragma unroll
