@@ -355,14 +355,13 @@ def main():
     consumed = torch.zeros(1, dtype=torch.float64, device=dev)
     main_stream = torch.cuda.current_stream()
     side = torch.cuda.Stream(device=dev) if world > 1 else None          # the learner's side: waits for and reads the gathered blocks
-    side_evs = []
 
     def exchange():
         """Every rank obtains the [world*B, K+5] result block of a control step and reads it (the learner's consumption, here a checksum).
-        Fused: the rows of step k are stored by the SSE kernel itself.  The consumer (wait for every rank's flag of step k-1, then read the
-        block) runs on a second stream behind the launch of step k -- four buffers make that safe, include/qcart.h -- so the simulation never
-        idles until the slowest rank has finished; the stepping stream only waits for the consumer of step k-2 (throughput-equivalent: the
-        exchange has to keep up with the stepping, it does not add latency to it)."""
+        Fused: the rows of step k are stored by the SSE kernel itself into its own rank's area.  The consumer (wait for every rank's flag of
+        step k-1, pull the peers' rows over NVLink, read the block) runs on a second stream behind the launch of step k; step k+1 waits for
+        it (four buffers make that safe, include/qcart.h).  The simulation never idles until the slowest rank has finished the current step:
+        the exchange has to keep up with the stepping, it does not add latency to it."""
         if fused is not None:
             seq = fused.seq()
             if seq > 1:
@@ -370,9 +369,7 @@ def main():
                     fused.wait(seq - 1)
                     consumed.add_(fused.block(seq - 1)[:, 0].sum())
                     ev = torch.cuda.Event(); ev.record(side)
-                side_evs.append(ev)
-                if len(side_evs) > 1:
-                    main_stream.wait_event(side_evs.pop(0))
+                main_stream.wait_event(ev)              # step seq+1 runs behind the consumer of step seq-1 (buffer-reuse rule of include/qcart.h)
         elif world > 1:
             qdist.all_gather_block(qdist.pack_block(out["moments"], out["aux"], out["flags"]), world, gathered)
             consumed.add_(gathered[:, 0].sum())
@@ -542,7 +539,7 @@ def main():
                        "actions": "uniform over 21 levels, redrawn every control step (torch.Generator seed 0)",
                        "l2": "inputs (2.8 MB/GPU) fit L2; L2 flushed with a 256 MiB write between timed steps, per-step CUDA events summed" if flush_buf is not None else "no flush",
                        "parallelism": ("%d rank(s), trajectories sharded, [B,%d] f64 result block per step %s" % (world, K_mom + 5,
-                                        "stored by the SSE kernel into every rank's peer memory; each rank waits for and reads the block of step k-1 on a second stream behind the launch of step k (fused, 4 buffers)"
+                                        "stored by the SSE kernel into its rank's gather area + flags to all ranks; each rank pulls and reads the block of step k-1 over NVLink on a second stream behind the launch of step k (fused, 4 buffers)"
                                         if gather_mode == "fused" else "by pack + NCCL all-gather [%s]" % gather_mode)) if world > 1 else "1 rank"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": "traj-control-steps/s", "h2d_bytes_per_step": B * 4,
                                       "d2h_bytes_per_step": B * (K_mom * 8 + L.QC_AUX_COUNT * 8 + 1),

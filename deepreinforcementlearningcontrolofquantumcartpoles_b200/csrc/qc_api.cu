@@ -498,7 +498,10 @@ extern "C" uint64_t qc_gather_seq(const qc_sim* s) { return s ? s->g_seq : 0; }
 extern "C" int qc_gather_wait(qc_sim* s, uint64_t seq, void* stream) {
     int rc = use_device(s); if (rc) return rc;
     if (s->g_world <= 0) return fail(QC_ERR_STATE, "qc_gather_wait: qc_set_gather first");
-    if (launch_gather_wait(s->g_flag[s->g_rank], s->g_world, seq, s->d_gerr, stream)) return fail(QC_ERR_CUDA, "wait kernel launch failed");
+    const long long cols = s->model.K + QC_AUX_COUNT + 1;
+    const long long block = (long long)s->batch.B * cols;                             // one rank's rows
+    const long long buf_off = (long long)(seq & (QC_GATHER_BUFS - 1)) * s->g_world * block;
+    if (launch_gather_wait(s->g_peer, s->g_rank, s->g_world, buf_off, block, s->g_flag[s->g_rank], seq, s->d_gerr, stream)) return fail(QC_ERR_CUDA, "wait kernel launch failed");
     s->launches++;
     return QC_OK;
 }

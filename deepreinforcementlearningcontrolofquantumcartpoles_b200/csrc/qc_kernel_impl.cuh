@@ -578,8 +578,10 @@ __device__ __forceinline__ void solve_traj_jacobi(const StepParams& p, const dou
 }
 
 // Fused result exchange (include/qcart.h, qc_set_gather): the first warp of the trajectory copies the row it has just written to the
-// local outputs -- [moments K | aux 4 | flags 1] as doubles -- into row (rank * B + traj) of the current buffer of every rank's gather area.
-// Peer buffers are ordinary global pointers (CUDA IPC mappings over NVLink); one coalesced 8 (K + 5)-byte store per rank.
+// local outputs -- [moments K | aux 4 | flags 1] as doubles -- into row (rank * B + traj) of the current buffer of THIS rank's gather area;
+// the last CTA then publishes the sequence number in every rank's flag array, and the consumers PULL the rows over NVLink (qc_gather_wait).
+// (Round 1 pushed every row to all ranks from here: 8 peer stores per row and a system-scope fence behind them in the tail of every CTA
+// made the kernel 4 % slower on 8 GPUs than alone.)
 __device__ __forceinline__ void publish_row(const StepParams& p, int traj, int lane) {
     __syncwarp();                                     // lane 0 wrote moments / aux / flags_out of this trajectory
     const int cols = p.K + QC_AUX_COUNT + 1;
@@ -589,7 +591,7 @@ __device__ __forceinline__ void publish_row(const StepParams& p, int traj, int l
         else if (lane < p.K + QC_AUX_COUNT) v = p.aux[(size_t)traj * QC_AUX_COUNT + (lane - p.K)];
         else v = (double)p.flags_out[traj];
         const size_t row = (size_t)(p.g_seq & (QC_GATHER_BUFS - 1)) * (size_t)p.g_world * p.B + (size_t)p.g_rank * p.B + traj;
-        for (int r = 0; r < p.g_world; r++) p.g_peer[r][row * cols + lane] = v;
+        p.g_peer[p.g_rank][row * cols + lane] = v;
         // no fence here: publish_done's CTA barrier + system-scope fence + release store order every row of the CTA before the flag
     }
 }

@@ -71,9 +71,10 @@ class _DeviceArray:
 
 
 class FusedGather:
-    """The per-control-step result block [world * B, K + 5] assembled on every rank by the SSE kernel itself: each rank's kernel stores its
-    rows into all ranks' gather areas (CUDA-IPC peer memory over NVLink) and publishes a sequence flag; `wait()` enqueues the consumer-side
-    spin kernel.  Replaces pack_block + all_gather_block (one NCCL collective and three small kernels per control step).
+    """The per-control-step result block [world * B, K + 5] without a collective: each rank's SSE kernel stores its rows into its own
+    gather area and publishes a sequence flag in every rank's flag array (CUDA-IPC peer memory over NVLink); `wait()` enqueues the
+    consumer kernel that waits for the flags and pulls the peers' rows.  Replaces pack_block + all_gather_block (one NCCL collective and
+    three small kernels per control step).
 
     Multi-process use (one rank per GPU, torch.distributed initialised):   fg = FusedGather(sim, rank, world)
     Single-process use (tests; several sims acting as ranks on one device): fgs = FusedGather.local_group(sims)

@@ -188,14 +188,18 @@ void qc_philox_normals(uint64_t seed, uint64_t traj, uint64_t step, double *out2
 /* ---- multi-GPU: fused result exchange over peer memory ------------------------------------------------------
  * Trajectories shard over ranks with no data-path collective; the only exchange is the per-control-step result block.  Instead of a
  * separate pack + all-gather, the SSE kernel itself stores every trajectory's row [moments K | aux 4 | flags 1] (float64) into row
- * rank*B + b of the current buffer of EVERY rank's gather area -- ordinary stores to CUDA-IPC mapped peer memory over NVLink /
- * NVSwitch, issued from the kernel's epilogue -- and its last CTA publishes a sequence number in every rank's flag array
- * (st.release.sys).  qc_gather_wait enqueues the consumer side: a one-warp kernel that spins (ld.acquire.sys) until all ranks have
- * published that sequence number (bounded: after ~2 s without the flag it gives up and records the missing ranks, see qc_gather_error).
+ * rank*B + b of the current buffer of ITS OWN gather area, and its last CTA publishes a sequence number in every rank's flag array
+ * (st.release.sys to CUDA-IPC mapped peer memory over NVLink / NVSwitch).  qc_gather_wait enqueues the consumer side: a kernel whose block r
+ * spins (ld.acquire.sys) until rank r has published that sequence number and then pulls rank r's rows from rank r's gather area into the
+ * same rows of the local one -- the transfer runs on the consumer's stream, off the critical path of the simulation
+ * (bounded: after ~2 s without the flag it gives up and records the missing ranks, see qc_gather_error).
  * Gather area per rank: double[4][world * B][K + 5] (buffer = sequence number mod 4), flag array: uint64[world], both zero-initialised by
- * qc_peer_alloc.  Four buffers allow the overlapped schedule: enqueue step k, THEN wait for / consume step k-1 -- a rank that runs ahead
- * writes buffer (k+1) mod 4 or (k+2) mod 4 while the slowest rank may still read (k-1) mod 4; it cannot reach step k+3 (the next user of that
- * buffer) before every rank has published step k+1, i.e. has consumed step k-1 in stream order.  Every rank must use the same B.
+ * qc_peer_alloc.  Every rank must use the same B.  A rank overwrites its buffer (k mod 4) when it runs step k+4, so every peer must have pulled
+ * step k by then.  Rule for the caller: step j+1 is enqueued behind the consumer (qc_gather_wait + whatever reads the block) of step j-1 --
+ * automatically true when the consumer sits in the stepping stream ("enqueue step k, then wait for / consume step k-1"), and one
+ * cudaStreamWaitEvent when it runs on a second stream (bench.py).  Then step k+4 of any rank starts after its consumer of step k+2, which
+ * needs every peer's flag k+2, i.e. every peer has started step k+2 and therefore finished its consumer of step k.  The simulation never
+ * idles until the slowest rank has finished the CURRENT step.
  *
  * qc_peer_alloc / qc_peer_open wrap cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle; the 64-byte handles travel between the
  * rank processes by any host channel (the Python mirror uses torch.distributed.all_gather_object). */
