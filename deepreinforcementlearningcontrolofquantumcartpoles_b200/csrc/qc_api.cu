@@ -498,10 +498,17 @@ extern "C" uint64_t qc_gather_seq(const qc_sim* s) { return s ? s->g_seq : 0; }
 extern "C" int qc_gather_wait(qc_sim* s, uint64_t seq, void* stream) {
     int rc = use_device(s); if (rc) return rc;
     if (s->g_world <= 0) return fail(QC_ERR_STATE, "qc_gather_wait: qc_set_gather first");
-    const long long cols = s->model.K + QC_AUX_COUNT + 1;
-    const long long block = (long long)s->batch.B * cols;                             // one rank's rows
-    const long long buf_off = (long long)(seq & (QC_GATHER_BUFS - 1)) * s->g_world * block;
-    if (launch_gather_wait(s->g_peer, s->g_rank, s->g_world, buf_off, block, s->g_flag[s->g_rank], seq, s->d_gerr, stream)) return fail(QC_ERR_CUDA, "wait kernel launch failed");
+    if (launch_gather_wait(s->g_flag[s->g_rank], s->g_world, seq, s->d_gerr, stream)) return fail(QC_ERR_CUDA, "wait kernel launch failed");
+    // pull: every peer's rows of this step from the peer's gather area into the same rows of the local one, by the copy engines (no SM
+    // resources: the SSE kernel of the next step may own every SM), stream-ordered behind the wait
+    const size_t cols = (size_t)s->model.K + QC_AUX_COUNT + 1;
+    const size_t block = (size_t)s->batch.B * cols;                                   // one rank's rows
+    const size_t buf_off = (size_t)(seq & (QC_GATHER_BUFS - 1)) * s->g_world * block;
+    for (int r = 0; r < s->g_world; r++) {
+        if (r == s->g_rank || s->g_peer[r] == s->g_peer[s->g_rank]) continue;
+        const size_t off = buf_off + (size_t)r * block;
+        QC_CUDA(cudaMemcpyAsync(s->g_peer[s->g_rank] + off, s->g_peer[r] + off, block * sizeof(double), cudaMemcpyDefault, (cudaStream_t)stream));
+    }
     s->launches++;
     return QC_OK;
 }

@@ -111,8 +111,7 @@ int launch_init_fock(double2* psi, int B, int n, const double* alpha, void* stre
 int launch_reset_accept(const double2* psi, int B, int n, int variant, int fail_len, double fail_thr2, const double* aux, double cutoff, unsigned char* pending,
                         double2* store, int* n_pending, void* stream);
 int launch_reset_scatter(double2* psi, int B, int n, const unsigned char* mask, const long long* slot, const double2* pool, long long pool_size, unsigned char* flags, void* stream);
-int launch_gather_wait(double* const* peers, int rank, int world, long long buf_offset_elems, long long block_elems, const unsigned long long* flags, unsigned long long seq,
-                       unsigned int* err_flag, void* stream);
+int launch_gather_wait(const unsigned long long* flags, int world, unsigned long long seq, unsigned int* err_flag, void* stream);
 int measure_fp64_peak(int device, double* flops);
 int measure_smem_peak(int device, double* bps);
 

@@ -354,39 +354,26 @@ __global__ void fp64_peak_kernel(double* out, int iters, double seed) {
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
-// Consumer side of the fused result exchange.  Block (r, *) waits (acquire, system scope) until rank r has published sequence number `seq`,
-// then pulls rank r's rows of that step from rank r's gather area (peer memory over NVLink, or local for r == rank: nothing to copy) into
-// the same rows of the local area.  The spin is bounded (~2 s): a peer that died must not hang this GPU; on time-out bit r of *err_flag is
-// set (qc_gather_error reports it) and nothing is copied for that rank.
-struct GatherPull { const double* src[QC_MAX_PEERS]; double* dst; const unsigned long long* flags; unsigned long long seq; long long block_elems; int rank; unsigned int* err_flag; };
-__global__ void gather_wait_kernel(const GatherPull a) {
-    const int r = blockIdx.x;
-    __shared__ int ok;
-    if (threadIdx.x == 0) {
+// Consumer side of the fused result exchange, part 1: thread r spins (acquire, system scope) until rank r has published sequence number
+// `seq`.  One warp on purpose: the block may spin for a while next to the CTAs of the running SSE kernel, which fill the register file up to
+// 57 K registers per SM -- a fat consumer block cannot co-reside and makes SSE CTAs wait for it (measured: 8 x 256-thread blocks per rank
+// doubled the SSE kernel's duration on 2 GPUs).  The spin is bounded (~2 s): a peer that died must not hang this GPU; on time-out bit r of
+// *err_flag is set (qc_gather_error reports it).  Part 2, the pull of the peers' rows, is done by the copy engines (qc_gather_wait).
+__global__ void gather_wait_kernel(const unsigned long long* __restrict__ flags, int world, unsigned long long seq, unsigned int* err_flag) {
+    if ((int)threadIdx.x < world) {
         unsigned long long v;
         long long spins = 0;
         const long long t0 = clock64();
-        ok = 1;
         for (;;) {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.flags + r) : "memory");
-            if (v >= a.seq) break;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+            if (v >= seq) break;
             __nanosleep(200);
-            if ((++spins & 1023) == 0 && clock64() - t0 > 4000000000ll) { atomicOr(a.err_flag, 1u << r); ok = 0; break; }
+            if ((++spins & 1023) == 0 && clock64() - t0 > 4000000000ll) { atomicOr(err_flag, 1u << threadIdx.x); break; }
         }
     }
-    __syncthreads();
-    if (!ok || r == a.rank) return;
-    const long long off = (long long)r * a.block_elems;                       // rows [r*B, (r+1)*B) of the buffer both sides address alike
-    const double* __restrict__ src = a.src[r] + off;             // (8-byte elements: B * (K + 5) may be odd, so no wider vector type)
-    double* __restrict__ dst = a.dst + off;
-    for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < a.block_elems; i += (long long)gridDim.y * blockDim.x) dst[i] = src[i];
 }
-int launch_gather_wait(double* const* peers, int rank, int world, long long buf_offset_elems, long long block_elems, const unsigned long long* flags, unsigned long long seq,
-                       unsigned int* err_flag, void* stream) {
-    GatherPull a;
-    for (int r = 0; r < QC_MAX_PEERS; r++) a.src[r] = (r < world) ? peers[r] + buf_offset_elems : nullptr;
-    a.dst = peers[rank] + buf_offset_elems; a.flags = flags; a.seq = seq; a.block_elems = block_elems; a.rank = rank; a.err_flag = err_flag;
-    gather_wait_kernel<<<dim3((unsigned)world, 8), 256, 0, (cudaStream_t)stream>>>(a);
+int launch_gather_wait(const unsigned long long* flags, int world, unsigned long long seq, unsigned int* err_flag, void* stream) {
+    gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, world, seq, err_flag);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

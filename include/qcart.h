@@ -189,10 +189,10 @@ void qc_philox_normals(uint64_t seed, uint64_t traj, uint64_t step, double *out2
  * Trajectories shard over ranks with no data-path collective; the only exchange is the per-control-step result block.  Instead of a
  * separate pack + all-gather, the SSE kernel itself stores every trajectory's row [moments K | aux 4 | flags 1] (float64) into row
  * rank*B + b of the current buffer of ITS OWN gather area, and its last CTA publishes a sequence number in every rank's flag array
- * (st.release.sys to CUDA-IPC mapped peer memory over NVLink / NVSwitch).  qc_gather_wait enqueues the consumer side: a kernel whose block r
- * spins (ld.acquire.sys) until rank r has published that sequence number and then pulls rank r's rows from rank r's gather area into the
- * same rows of the local one -- the transfer runs on the consumer's stream, off the critical path of the simulation
- * (bounded: after ~2 s without the flag it gives up and records the missing ranks, see qc_gather_error).
+ * (st.release.sys to CUDA-IPC mapped peer memory over NVLink / NVSwitch).  qc_gather_wait enqueues the consumer side: a one-warp kernel that
+ * spins (ld.acquire.sys) until all ranks have published that sequence number (bounded: after ~2 s without a flag it gives up and records the
+ * missing ranks, see qc_gather_error), followed by one peer copy per rank (copy engines) that pulls that rank's rows from its gather area
+ * into the same rows of the local one -- the transfer runs on the consumer's stream, off the critical path of the simulation.
  * Gather area per rank: double[4][world * B][K + 5] (buffer = sequence number mod 4), flag array: uint64[world], both zero-initialised by
  * qc_peer_alloc.  Every rank must use the same B.  A rank overwrites its buffer (k mod 4) when it runs step k+4, so every peer must have pulled
  * step k by then.  Rule for the caller: step j+1 is enqueued behind the consumer (qc_gather_wait + whatever reads the block) of step j-1 --
