@@ -603,9 +603,9 @@ __device__ __forceinline__ void publish_done(const StepParams& p) {
         const unsigned int ticket = atomicAdd(p.g_done, 1u);
         if (ticket == gridDim.x - 1) {
             *p.g_done = 0u;                           // ready for the next launch (stream-ordered)
-            __threadfence_system();
-            for (int r = 0; r < p.g_world; r++)
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.g_flag[r] + p.g_rank), "l"(p.g_seq) : "memory");
+            __threadfence_system();                   // ONE system-scope fence, then relaxed flag stores (fence + relaxed store = release); a
+            for (int r = 0; r < p.g_world; r++)       // st.release per rank serialised 8 fences in the kernel's tail (+18 us on 8 GPUs)
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.g_flag[r] + p.g_rank), "l"(p.g_seq) : "memory");
         }
     }
 }
