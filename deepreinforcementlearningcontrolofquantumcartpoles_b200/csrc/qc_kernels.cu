@@ -113,8 +113,10 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
         const PipeEntry* pe = qc_find_pipe(var, L, G, want_ne);
         const int GUc = (G == 32) ? 10 : ((var == QC_QUARTIC) ? 5 : 12);
         if (pe && W <= (GUc - 1) * L && (int)pe->smem(n_sub) <= smem_max) {
-            const int TT = 2 * pe->ne, cpt = 32 / pe->ne, GU = GUc;
-            int mult = (cols + cpt - 1) / cpt; mult |= 1;
+            const int ne = pe->ne & 15, nsw = (pe->ne >> 4) + 1;           // instance id: NE + 16 (NSW - 1), see qc_pipe_impl.cuh
+            const int TT = 2 * ne, cpt = 32 / (ne / nsw), GU = GUc;
+            int mult = (cols + cpt - 1) / cpt;
+            if (nsw == 1) mult |= 1; else mult = (mult + 1) & ~1;
             const int c_last = (cols - 1) / mult;
             // Binning pads every force level to whole CTAs.  Large batches: the padding is noise.  Small batches: only when even the worst
             // case (every bin one trajectory past a CTA) still fits one wave of CTAs, so that no SM ever runs a second, nearly empty round.
@@ -129,8 +131,8 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
                 memset(&plan, 0, sizeof(plan));
                 plan.L = L; plan.T = TT; plan.G = G; plan.P = cpt; plan.chunk = mult * L; plan.W = W; plan.NP = G * L; plan.threads = pe->threads;
                 plan.smem_bytes = (int)pe->smem(n_sub); plan.tstride = 0; plan.maxt = pe->threads; plan.gc = G; plan.tabs = true; plan.binned = 1; plan.pipe = pe->ne;
-                snprintf(plan.info, sizeof(plan.info), "sse_pipe_kernel<var=%d,L=%d,G=%d,NE=%d> traj/CTA=%d chunks/traj=%d chunk=%d W=%d bin=1 threads=%d smem=%d regs=%d lmem=%d",
-                         var, L, G, pe->ne, plan.T, cpt, plan.chunk, W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
+                snprintf(plan.info, sizeof(plan.info), "sse_pipe_kernel<var=%d,L=%d,G=%d,NE=%d,NSW=%d> traj/CTA=%d chunks/traj=%d chunk=%d W=%d bin=1 threads=%d smem=%d regs=%d lmem=%d",
+                         var, L, G, ne, nsw, plan.T, cpt, plan.chunk, W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
                 return QC_OK;
             }
         }

@@ -55,8 +55,11 @@ template <int L, int GD> __device__ __forceinline__ double2 ld_rel_g(const doubl
 // geometry shared by host (plan) and device
 // TABG: the factor table of the CTA's force level stays in global memory (L2 / L1 resident) instead of shared memory: grids whose table
 // (80 N bytes) would not leave room for the lines.
-template <int VAR, int L, int GC, int NE, bool TABG = false> struct PipeGeo {
-    static constexpr int G = GC, NWG = GC / 32, TT = 2 * NE, CPT = 32 / NE;
+// NSW: solver warps per set (one-warp groups only).  Each serves NES = NE / NSW trajectories with 32 / NES chunks per trajectory: shorter
+// chunks, i.e. a shorter serial recurrence per solve (the latency that bounds one-warp grid trajectories, config 2).
+template <int VAR, int L, int GC, int NE, bool TABG = false, int NSW = 1> struct PipeGeo {
+    static constexpr int G = GC, NWG = GC / 32, TT = 2 * NE, NES = NE / NSW, CPT = 32 / NES;
+    static_assert(NSW == 1 || GC == 32, "several solver warps per set: one-warp groups only");
     static constexpr int BA = VarTraits<VAR>::BA;
     // sweep lines per explicit group: two alternate in the Horner chain (the Fock systems first use them for Y+ / Y-); the inverted harmonic
     // oscillator needs a third one for the left halo of a (HERMITIAN-descriptor term).  Their guard: the widest halo in columns.
@@ -70,7 +73,8 @@ template <int VAR, int L, int GC, int NE, bool TABG = false> struct PipeGeo {
     static constexpr int LBU0 = L * GpU;
     // stride between the state lines of a set: = 8/NE (mod 8) in 16-byte units, so that the NE x 2 lanes of a quarter warp of the solver hit
     // distinct bank groups (chunk stride `mult` is odd)
-    static constexpr int LBU = LBU0 + ((8 / NE) - (LBU0 % 8) + 8) % 8;
+    // (NSW > 1: the chunk stride is even instead, and the line stride odd)
+    static constexpr int LBU = LBU0 + (((NSW > 1) ? 1 : (8 / NE)) - (LBU0 % 8) + 8) % 8;
     static constexpr int LBS = L * GpS;
     static constexpr int CS = (VAR == QC_QUARTIC) ? BA + 1 : BA + 2;    // factor row: l_1..l_BA, 1/d, (Fock) xl
     // Warp roles follow the SM sub-partition a warp runs on (warp id mod 4): ids with (id & 3) == 3 are the solver warps (3: set A, 7: set B;
@@ -79,8 +83,8 @@ template <int VAR, int L, int GC, int NE, bool TABG = false> struct PipeGeo {
     // One-warp groups (SOLO = false): a scheduler hosts at most two or three warps anyway, so the solver warps simply follow the explicit ones.
     static constexpr bool SOLO = NWG > 1;
     static constexpr int NXW = NE * NWG;                            // explicit warps
-    static constexpr int LASTW = SOLO ? (NXW - 1) + (NXW - 1) / 3 : NXW + 1;     // highest warp id in use
-    static constexpr int WARPS = ((LASTW > 7 || !SOLO ? LASTW : 7) + 4) / 4 * 4;
+    static constexpr int LASTW = SOLO ? (NXW - 1) + (NXW - 1) / 3 : NXW + 2 * NSW - 1;     // highest warp id in use
+static constexpr int WARPS = ((LASTW > 7 || !SOLO ? LASTW : 7) + 4) / 4 * 4;   // whole warp quads: the register file is per SM sub-partition, so a partial quad buys no registers (ptxas: 320 threads -> 168, not 200)
     static constexpr int THREADS = WARPS * 32;
     static constexpr size_t tab_bytes = TABG ? 0 : (size_t)CS * L * G * 16 + (size_t)HT * L * G * 8;
     static constexpr size_t fixed_bytes = tab_bytes + (size_t)TT * LBU * 16 + (size_t)NE * NS * LBS * 16 + (size_t)TT * 128 /* scal */ +
@@ -93,10 +97,10 @@ template <int VAR, int L, int GC, int NE, bool TABG = false> struct PipeGeo {
 // lane = cc*NE + tt: chunk cc (mult columns = mult*L points) of trajectory tt; both substitutions start wb columns outside the chunk with
 // zero history (same truncation as solve_traj).  z overwrites the right-hand side and x overwrites z: every lane reads its warm-up region
 // (which belongs to the neighbour chunk) before any lane writes, the warp runs converged and __syncwarp separates the two parts.
-template <int VAR, int L, int GC, int NE, bool TABG>
+template <class Geo, int VAR, int L, bool TABG>
 __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restrict__ Uset, const double2* __restrict__ tab, double* scal_set, int mult, int wb,
                                            int lane, int s, PipeTimers& tm) {
-    typedef PipeGeo<VAR, L, GC, NE, TABG> Geo;
+    constexpr int NE = Geo::NES;                               // trajectories served by this warp
     constexpr int BA = Geo::BA, CS = Geo::CS, G = Geo::G, Gp = Geo::GpU, GUARD = Geo::GU;
     const int tt = lane % NE, cc = lane / NE;
     double2* __restrict__ U = Uset + (size_t)tt * Geo::LBU;
@@ -255,9 +259,9 @@ __device__ __forceinline__ void pipe_sweep(const LaneOps<VAR, L>& ops, double2* 
 }
 
 // ------------------------------------------------------------------------------------------------------
-template <int VAR, int L, int GC, int NE, bool TABG>
-__global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG>::THREADS, 1) sse_pipe_kernel(const StepParams p) {
-    typedef PipeGeo<VAR, L, GC, NE, TABG> Geo;
+template <int VAR, int L, int GC, int NE, bool TABG, int NSW = 1>
+__global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG, NSW>::THREADS, 1) sse_pipe_kernel(const StepParams p) {
+    typedef PipeGeo<VAR, L, GC, NE, TABG, NSW> Geo;
     static_assert(!TABG || VAR == QC_QUARTIC, "global factor table: grid only");
     constexpr int G = Geo::G, NWG = Geo::NWG, TT = Geo::TT, GpU = Geo::GpU, GpS = Geo::GpS, LBU = Geo::LBU, LBS = Geo::LBS, CS = Geo::CS;
     constexpr int GU = Geo::GU, GS = Geo::GS, NS = Geo::NS, HT = Geo::HT, BA = Geo::BA;
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG>::THREADS, 1) sse
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, n = p.n, n_sub = p.n_sub;
     const int warp = tid >> 5, lane = tid & 31;
-    const bool is_solver = Geo::SOLO ? (warp & 3) == 3 : (warp >= Geo::NXW && warp < Geo::NXW + 2);
+    const bool is_solver = Geo::SOLO ? (warp & 3) == 3 : (warp >= Geo::NXW && warp < Geo::NXW + 2 * NSW);
     const int xw = Geo::SOLO ? warp - (warp >> 2) : warp;           // explicit warp number
     const bool is_idle = !is_solver && xw >= Geo::NXW;
     const int e = (is_solver || is_idle) ? 0 : xw / NWG;            // explicit group
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG>::THREADS, 1) sse
         int sl = 0;
         for (int q = 0; q < TT; q++) { const int ps = blockIdx.x * TT + q; if (ps < npos && p.order[ps] >= 0) { sl = min(max(p.slot[p.order[ps]], 0), p.n_slots - 1); break; } }
         cta_slot = sl;
-        mbar_init(&bars[0], NE * G); mbar_init(&bars[1], NE * G); mbar_init(&bars[2], 32); mbar_init(&bars[3], 32);
+        mbar_init(&bars[0], NE * G); mbar_init(&bars[1], NE * G); mbar_init(&bars[2], 32 * NSW); mbar_init(&bars[3], 32 * NSW);
     }
     __syncthreads();
     if constexpr (!TABG) {
@@ -345,15 +349,18 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG>::THREADS, 1) sse
     PipeTimers tm; tm.start();
     if (!cta_empty && is_solver) {
         // ================= solver warpgroup: warp X of it serves set X ==================================================================
-        const int X = Geo::SOLO ? warp >> 2 : warp - Geo::NXW;
+        const int X = Geo::SOLO ? warp >> 2 : (warp - Geo::NXW) / NSW;
+        const int sub = Geo::SOLO ? 0 : (warp - Geo::NXW) % NSW;           // which NES trajectories of the set
         if (X < 2) {
             const int cols = (n + L - 1) / L;
-            int mult = (cols + Geo::CPT - 1) / Geo::CPT; mult |= 1;         // odd chunk stride (bank-conflict-free factor and state loads)
+            int mult = (cols + Geo::CPT - 1) / Geo::CPT;
+            if (NSW == 1) mult |= 1; else mult = (mult + 1) & ~1;          // odd (NSW > 1: even) chunk stride: bank-conflict-free factor and state loads
             const int wb = p.W / L;
             for (int s = 0; s < n_sub; s++) {
                 mbar_wait(&bars[X], s & 1);
                 tm.tick(0);
-                pipe_solve<VAR, L, GC, NE, TABG>(p, Uall + (size_t)X * NE * LBU, TABG ? p.fac + (size_t)cta_slot * n * (BA + 1) : tab, scal_all + X * NE * 16, mult, wb, lane, s, tm);
+                pipe_solve<Geo, VAR, L, TABG>(p, Uall + (size_t)(X * NE + sub * Geo::NES) * LBU, TABG ? p.fac + (size_t)cta_slot * n * (BA + 1) : tab,
+                                              scal_all + (X * NE + sub * Geo::NES) * 16, mult, wb, lane, s, tm);
                 mbar_arrive(&bars[2 + X]);
                 tm.tick(3);
             }
@@ -851,7 +858,9 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG>::THREADS, 1) sse
 }
 
 
+// ne: groups per CTA; instances with NSW solver warps per set carry the id NE + 16 (NSW - 1)
 struct PipeEntry { int var, L, gc, ne, threads; kern_t fn; size_t (*smem)(int n_sub); };
+#define QC_PE_NSW(VAR, L, GC, NE, NSW) {VAR, L, GC, NE + 16 * (NSW - 1), PipeGeo<VAR, L, GC, NE, false, NSW>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, false, NSW>, PipeGeo<VAR, L, GC, NE, false, NSW>::smem_bytes}
 #define QC_PE(VAR, L, GC, NE) {VAR, L, GC, NE, PipeGeo<VAR, L, GC, NE>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, false>, PipeGeo<VAR, L, GC, NE>::smem_bytes}
 #define QC_PE_TABG(VAR, L, GC, NE) {VAR, L, GC, NE, PipeGeo<VAR, L, GC, NE, true>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, true>, PipeGeo<VAR, L, GC, NE, true>::smem_bytes}
 
