@@ -105,11 +105,11 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
     // QCART_PIPE_NE / QCART_PIPE_L: groups per CTA / points per lane (experiments).
     // Geometry per system (measured, 8192 trajectories): grid with several warps per trajectory L = 6 (config 4: 28.6 -> 17.5 ms);
     // inverted harmonic L = 3 with two-warp groups (5.18 -> 4.19 ms; one-warp groups with L = 6 spill at 168 registers and are latency bound
-    // at 255: 5.07 ms); harmonic L = 3, eight one-warp groups (1.81 -> 1.78 ms).  One-warp GRID trajectories (N <= 192) stay with the
+    // at 255: 5.07 ms); harmonic L = 3, eight one-warp groups (1.81 -> 1.73 ms; with two solver warps per set 1.61 ms).  One-warp GRID trajectories (N <= 192) stay with the
     // register-resident chunk-Jacobi kernel (0.55 vs 0.73 ms at 1024 and 3.7 vs 3.9 ms at 8192 trajectories of config 2).
     if (n_sub > 0 && env_int("QCART_PIPE", 1) && !forceL && env_int("QCART_BIN", -1) != 0) {
         const int L = env_int("QCART_PIPE_L", (var == QC_QUARTIC) ? 6 : 3), cols = (n + L - 1) / L, G = (cols + 31) / 32 * 32, W = (W_needed + L - 1) / L * L;
-        const int want_ne = env_int("QCART_PIPE_NE", (var == QC_HARMONIC) ? 8 : ((var == QC_INV_HARMONIC) ? 4 : (G >= 128 ? 1 : 0)));
+        const int want_ne = env_int("QCART_PIPE_NE", (var == QC_HARMONIC) ? 24 /* NE = 8, two solver warps per set */ : ((var == QC_INV_HARMONIC) ? 4 : (G >= 128 ? 1 : 0)));
         const PipeEntry* pe = qc_find_pipe(var, L, G, want_ne);
         const int GUc = (G == 32) ? 10 : ((var == QC_QUARTIC) ? 5 : 12);
         if (pe && W <= (GUc - 1) * L && (int)pe->smem(n_sub) <= smem_max) {
