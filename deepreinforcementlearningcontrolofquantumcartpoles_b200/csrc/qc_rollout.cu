@@ -13,8 +13,10 @@
 #include "qc_philox.cuh"
 #include "../../include/qcart_rollout.h"
 #include <cuda_runtime.h>
+#include <cuda.h>                      // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint (no link-time libcuda)
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 #include <string>
 #include <vector>
@@ -47,8 +49,17 @@ __global__ void obs_kernel(const double* __restrict__ m, int64_t count, float sc
 
 // h[b, o] = relu(b1[o] + sum_i W1[o, i] x[b, i]);  n_in is small (20 grid moments / 5 Fock moments): one CTA per 8 rows, one thread per output
 constexpr int FC1_ROWS = 8;
+// TF32 split of an fp32 value: hi = the value with its low 13 mantissa bits cleared (exactly representable in TF32), lo = the exact remainder.
+__device__ __forceinline__ float tf32_hi(float a) { return __uint_as_float(__float_as_uint(a) & 0xFFFFE000u); }
+
+__global__ void split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const float a = x[i], h = tf32_hi(a); hi[i] = h; lo[i] = a - h; }
+}
+
+// (h_hi / h_lo, nullable: the TF32 split of the output, which is what the TMA-fed tensor-core GEMM of the next layer loads)
 __global__ void __launch_bounds__(512) fc1_kernel(const float* __restrict__ obs, const float* __restrict__ W, const float* __restrict__ bias,
-                                                  float* __restrict__ h, int64_t B, int n_in, int n_out) {
+                                                  float* __restrict__ h, float* __restrict__ h_hi, float* __restrict__ h_lo, int64_t B, int n_in, int n_out) {
     extern __shared__ float xs[];                      // [FC1_ROWS][n_in]
     const int64_t m0 = (int64_t)blockIdx.x * FC1_ROWS;
     const int rows = (int)min((int64_t)FC1_ROWS, B - m0);
@@ -65,7 +76,42 @@ __global__ void __launch_bounds__(512) fc1_kernel(const float* __restrict__ obs,
             for (int r = 0; r < FC1_ROWS; r++) acc[r] = fmaf(xs[r * n_in + i], w, acc[r]);
         }
 #pragma unroll
-        for (int r = 0; r < FC1_ROWS; r++) if (r < rows) h[(m0 + r) * n_out + o] = fmaxf(acc[r], 0.0f);
+        for (int r = 0; r < FC1_ROWS; r++) if (r < rows) {
+            const float v = fmaxf(acc[r], 0.0f);
+            if (h) h[(m0 + r) * n_out + o] = v;
+            if (h_hi) { const float vh = tf32_hi(v); h_hi[(m0 + r) * n_out + o] = vh; h_lo[(m0 + r) * n_out + o] = v - vh; }
+        }
+    }
+}
+
+// The same layer for the reference's input widths (20 grid moments, 5 Fock moments): thread = output with its NI (zero-padded) weights in
+// registers, 32 rows per CTA whose observations are broadcast from shared memory as 16-byte loads -- NI FMA per NI/4 shared loads, so the kernel
+// is bound by its (coalesced) output stores instead of by L1 (fc1_kernel: 132 us at 65 536 trajectories, 20 cache lines per warp load of W).
+constexpr int FC1S_ROWS = 32;
+template <int NI>
+__global__ void __launch_bounds__(512) fc1_small_kernel(const float* __restrict__ obs, const float* __restrict__ W, const float* __restrict__ bias,
+                                                        float* __restrict__ h, float* __restrict__ h_hi, float* __restrict__ h_lo, int64_t B, int n_in, int n_out) {
+    __shared__ __align__(16) float xs[FC1S_ROWS * NI];
+    const int64_t m0 = (int64_t)blockIdx.x * FC1S_ROWS;
+    const int rows = (int)min((int64_t)FC1S_ROWS, B - m0);
+    for (int e = threadIdx.x; e < FC1S_ROWS * NI; e += blockDim.x) { const int r = e / NI, i = e % NI; xs[e] = (r < rows && i < n_in) ? obs[(m0 + r) * n_in + i] : 0.0f; }
+    __syncthreads();
+    for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+        float w[NI];
+#pragma unroll
+        for (int i = 0; i < NI; i++) w[i] = (i < n_in) ? __ldg(&W[(size_t)o * n_in + i]) : 0.0f;
+        const float b0 = bias[o];
+        for (int r = 0; r < rows; r++) {
+            float acc = b0;
+#pragma unroll
+            for (int i = 0; i < NI; i += 4) {
+                const float4 x = *reinterpret_cast<const float4*>(&xs[r * NI + i]);
+                acc = fmaf(x.x, w[i], acc); acc = fmaf(x.y, w[i + 1], acc); acc = fmaf(x.z, w[i + 2], acc); acc = fmaf(x.w, w[i + 3], acc);
+            }
+            const float v = fmaxf(acc, 0.0f);
+            if (h) h[(m0 + r) * n_out + o] = v;
+            if (h_hi) { const float vh = tf32_hi(v); h_hi[(m0 + r) * n_out + o] = vh; h_lo[(m0 + r) * n_out + o] = v - vh; }
+        }
     }
 }
 
@@ -325,6 +371,177 @@ __global__ void __launch_bounds__(128) gemm_umma_kernel(const GemmArgs g) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"((uint32_t)(UQ * NT)) : "memory");
 }
 
+// ---- TMA-fed variant (default): the same 3xTF32 tcgen05 GEMM with no thread touching an operand -------------------------------------
+// The operands arrive PRE-SPLIT in global memory (activations: written as hi / lo copies by the producing kernel's epilogue; weights: split
+// once when they are set), so a stage is four bulk tensor copies (cp.async.bulk.tensor.2d, one per operand copy: 128 or NT rows x 32 floats
+// = 128-byte rows in the 128-byte-swizzled K-major layout the tensor core reads directly) issued by ONE producer thread into a ring of
+// stages; ONE other thread issues the tcgen05.mma instructions (same order as gemm_umma_kernel, hence bitwise the same accumulators);
+// tcgen05.commit hands a stage back to the producer.  The four warps only meet again for the epilogue, which also writes the hi / lo split
+// (and the input-noise-scaled copy) the next layer loads.  Rows beyond M are zero-filled by the TMA unit (no bounds code).
+// Roles: warp 0 lane 0 = producer, warp 1 lane 0 = MMA issue; the other lanes of those warps wait at __syncwarp (no spinning next to the
+// role thread).
+struct TmaGemmArgs {
+    CUtensorMap a_hi[2], a_lo[2], w_hi[2], w_lo[2];      // index z = blockIdx.z (z = 1: the sigma_w half of a noisy layer)
+    const float* bias; const float* ei; int ldn;
+    float* C;                                            // raw fp32 output (nullable), [z][M][N]
+    float* C_hi; float* C_lo;                            // TF32 split of the output (nullable; z = 0 only)
+    float* C2_hi; float* C2_lo;                          // TF32 split of output * ei (nullable; z = 0 only)
+    int M, N, K; int relu_bias;
+};
+constexpr int TMA_KS = 32;                                // K floats per stage = one 128-byte swizzle row
+
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    // K-major, 128-byte swizzle: 8-row x 128-byte atoms 1024 bytes apart (SBO), LBO unused (1), descriptor version 1, layout type 2
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(128) gemm_tma_kernel(const __grid_constant__ TmaGemmArgs g) {
+    constexpr uint32_t A_BYTES = UM * 128, W_BYTES = NT * 128, STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    constexpr int S = (NT == 128) ? 3 : 4;                // ring depth: 3 x 64 KB / 4 x 48 KB
+    extern __shared__ unsigned char tsm_raw[];
+    __shared__ __align__(8) uint64_t bar_full[S], bar_empty[S], bar_acc;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int z = blockIdx.z, m0 = blockIdx.y * UM, n0 = blockIdx.x * NT;
+    const uint32_t ring = (smem_u32(tsm_raw) + 1023u) & ~1023u;          // the swizzle atoms need 1024-byte alignment
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"((uint32_t)(UQ * NT)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < S; i++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_full[i])), "r"(1u) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_empty[i])), "r"(1u) : "memory");
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_acc)), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = tmem_base;
+    const int nstages = g.K / TMA_KS, per_q = (nstages + UQ - 1) / UQ;
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- producer --------------------------------------------------------------------------------------------------
+            for (int s = 0; s < nstages; s++) {
+                const int slot = s % S, it = s / S;
+                if (it > 0) mbar_wait(smem_u32(&bar_empty[slot]), (uint32_t)((it - 1) & 1));     // the MMAs that read this slot have retired
+                const uint32_t fb = smem_u32(&bar_full[slot]), dst = ring + (uint32_t)slot * STAGE_BYTES;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(STAGE_BYTES) : "memory");
+                const int k0 = s * TMA_KS;
+                tma_load_2d(dst, &g.a_hi[z], k0, m0, fb);
+                tma_load_2d(dst + A_BYTES, &g.a_lo[z], k0, m0, fb);
+                tma_load_2d(dst + 2 * A_BYTES, &g.w_hi[z], k0, n0, fb);
+                tma_load_2d(dst + 2 * A_BYTES + W_BYTES, &g.w_lo[z], k0, n0, fb);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issue --------------------------------------------------------------------------------------------------
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+            for (int s = 0; s < nstages; s++) {
+                const int slot = s % S, it = s / S;
+                mbar_wait(smem_u32(&bar_full[slot]), (uint32_t)(it & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ah = ring + (uint32_t)slot * STAGE_BYTES, al = ah + A_BYTES, wh = al + A_BYTES, wl = wh + W_BYTES;
+                const uint32_t tacc = taddr + (uint32_t)((s / per_q) * NT);
+#pragma unroll
+                for (int ks = 0; ks < TMA_KS / 8; ks++) {
+                    const uint32_t ko = ks * 32;                          // 8 floats further inside the 128-byte swizzle row
+                    const uint64_t d_ah = umma_desc_sw128(ah + ko), d_al = umma_desc_sw128(al + ko), d_wh = umma_desc_sw128(wh + ko), d_wl = umma_desc_sw128(wl + ko);
+                    const uint32_t first = (s % per_q != 0 || ks > 0) ? 1u : 0u;        // each K quarter starts a fresh accumulator
+#define QC_UMMA(DA, DB, ACC)                                                                                                   \
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                               \
+                                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"              \
+                                 ::"r"(tacc), "l"(DA), "l"(DB), "r"(idesc), "r"(ACC), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory")
+                    QC_UMMA(d_al, d_wh, first);           // small terms first (same order as gemm_umma_kernel)
+                    QC_UMMA(d_ah, d_wl, 1u);
+                    QC_UMMA(d_ah, d_wh, 1u);
+#undef QC_UMMA
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_empty[slot])) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_acc)) : "memory");
+        }
+        __syncwarp();
+    }
+    // ---- epilogue: thread = output row (tensor-memory lane) -------------------------------------------------------------------
+    mbar_wait(smem_u32(&bar_acc), 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // Phase 1: thread = output row (tensor-memory lane): the K-quarter accumulators are summed in fp32, bias + ReLU applied, and the row goes
+    // into a padded tile in shared memory (the stage ring is free: every MMA has retired).  Phase 2: the CTA writes the tile out with whole
+    // 512-byte row segments per warp instruction -- up to five output streams (raw, hi / lo split, hi / lo split of the noise-scaled copy)
+    // would otherwise each be 16-byte pieces scattered over 32 rows (measured: 579 us instead of 284 us for fc2 at 65 536 trajectories).
+    const bool epi = g.relu_bias && z == 0;
+    constexpr int LDT_ = NT + 4;                           // floats per tile row (16-byte aligned, conflict-free for both phases)
+    float* tile = reinterpret_cast<float*>(tsm_raw + (ring - smem_u32(tsm_raw)));
+    const int nq = (nstages + per_q - 1) / per_q;        // accumulators actually used
+    for (int c0 = 0; c0 < NT; c0 += 16) {
+        float r[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) r[j] = 0.f;
+        for (int qd = 0; qd < nq; qd++) {
+            uint32_t t[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]),
+                           "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+                         : "r"(taddr + ((uint32_t)(warp * 32) << 16) + (uint32_t)(qd * NT + c0)) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; j++) r[j] += __uint_as_float(t[j]);
+        }
+        if (epi) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) r[j] = fmaxf(r[j] + __ldg(&g.bias[n0 + c0 + j]), 0.0f);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; v++) *reinterpret_cast<float4*>(tile + tid * LDT_ + c0 + 4 * v) = make_float4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    float* C = g.C ? g.C + (size_t)z * g.M * g.N : nullptr;
+    const bool split_out = g.C_hi != nullptr && z == 0, split2 = g.C2_hi != nullptr && z == 0;
+    constexpr int V4 = NT / 4;                            // float4 per tile row
+    constexpr int PB = 4;                                 // segments per thread and pass: their loads are issued together (memory-level parallelism
+                                                          // of a 128-thread CTA that is alone on its SM)
+    for (int e0 = tid; e0 < UM * V4; e0 += 128 * PB) {
+        float4 x[PB], ev[PB]; size_t o[PB]; bool ok[PB];
+#pragma unroll
+        for (int u = 0; u < PB; u++) {
+            const int e = e0 + 128 * u, row = e / V4, c = (e % V4) * 4, m = m0 + row;
+            ok[u] = (e < UM * V4) && m < g.M;
+            o[u] = (size_t)m * g.N + n0 + c;
+            x[u] = *reinterpret_cast<const float4*>(tile + (ok[u] ? row : 0) * LDT_ + c);
+            ev[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (split2 && ok[u]) ev[u] = __ldg(reinterpret_cast<const float4*>(g.ei + (size_t)m * g.ldn + n0 + c));
+        }
+#pragma unroll
+        for (int u = 0; u < PB; u++) {
+            if (!ok[u]) continue;
+            if (C) *reinterpret_cast<float4*>(C + o[u]) = x[u];
+            if (split_out) {
+                const float4 h = make_float4(tf32_hi(x[u].x), tf32_hi(x[u].y), tf32_hi(x[u].z), tf32_hi(x[u].w));
+                *reinterpret_cast<float4*>(g.C_hi + o[u]) = h;
+                *reinterpret_cast<float4*>(g.C_lo + o[u]) = make_float4(x[u].x - h.x, x[u].y - h.y, x[u].z - h.z, x[u].w - h.w);
+            }
+            if (split2) {
+                const float4 y = make_float4(x[u].x * ev[u].x, x[u].y * ev[u].y, x[u].z * ev[u].z, x[u].w * ev[u].w);
+                const float4 h = make_float4(tf32_hi(y.x), tf32_hi(y.y), tf32_hi(y.z), tf32_hi(y.w));
+                *reinterpret_cast<float4*>(g.C2_hi + o[u]) = h;
+                *reinterpret_cast<float4*>(g.C2_lo + o[u]) = make_float4(y.x - h.x, y.y - h.y, y.z - h.z, y.w - h.w);
+            }
+        }
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"((uint32_t)(UQ * NT)) : "memory");
+}
+
 // Output layer + argmax.  Input: the two raw halves y1 = h2 u_w31^T, y2 = (h2 * e_in31) sigma_w31^T of the (noisy) fc31 layer; this kernel
 // first forms  x = relu(y1 + u_b31 + e_out31 * (y2 + sigma_b31))  (layers.py:52-56), then the n_actions-wide noisy layer fc41 and the argmax.
 // The transposed u_w41 / sigma_w41 are staged in shared memory once per CTA; lane o of a warp owns output o, one trajectory per warp at a time.
@@ -336,13 +553,14 @@ struct HeadArgs {
     int A; int noisy31, noisy41;
     float* q; int32_t* greedy; int64_t B;
 };
-constexpr int HEAD_WARPS = 8, HLD = 33;                 // transposed weight rows padded to 33 floats: conflict-free staging and reads
-
+constexpr int HEAD_WARPS = 16, HLD = 33;                // transposed weight rows padded to 33 floats: conflict-free staging and reads
+constexpr int HEAD_R = 4;                                // trajectories per warp and pass: every weight read from shared memory serves HEAD_R rows
+                                                         // (one row at a time the kernel was bound by its shared-memory loads: 10 per 8 FMA, 202 us at 65 536 rows)
 __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs h) {
     extern __shared__ __align__(16) float hsm[];
     float* Ut = hsm;                                     // [256][33]  (u_w41 transposed)
     float* St = hsm + H3 * HLD;                          // [256][33]
-    float* xrow = hsm + 2 * H3 * HLD;                    // [HEAD_WARPS][2][256]: x and x * e_in41
+    float* xrow = hsm + 2 * H3 * HLD;                    // [HEAD_WARPS][HEAD_R][2][256]: x and x * e_in41
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int e = threadIdx.x; e < H3 * 32; e += blockDim.x) {
         const int o = e >> 8, i = e & (H3 - 1);          // coalesced along i
@@ -350,40 +568,61 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs h)
         St[i * HLD + o] = (o < h.A && h.noisy41) ? __ldg(&h.S[(size_t)o * H3 + i]) : 0.0f;
     }
     __syncthreads();
-    float* xs = xrow + (size_t)wid * 2 * H3;
+    float* xs = xrow + (size_t)wid * HEAD_R * 2 * H3;
     const float ubo = (lane < h.A) ? h.ub[lane] : 0.0f, sbo = (lane < h.A && h.noisy41) ? h.sb[lane] : 0.0f;
-    for (int64_t row = (int64_t)blockIdx.x * HEAD_WARPS + wid; row < h.B; row += (int64_t)gridDim.x * HEAD_WARPS) {
+    for (int64_t row0 = ((int64_t)blockIdx.x * HEAD_WARPS + wid) * HEAD_R; row0 < h.B; row0 += (int64_t)gridDim.x * HEAD_WARPS * HEAD_R) {
         __syncwarp();
 #pragma unroll
-        for (int t = 0; t < H3 / 32; t++) {
-            const int i = lane + 32 * t;
-            float x = h.y1[row * H3 + i] + h.ub31[i];
-            if (h.noisy31) x = fmaf(h.nz[row * h.ldn + H2 + i], h.y2[row * H3 + i] + h.sb31[i], x);
-            x = fmaxf(x, 0.0f);
-            xs[i] = x; xs[H3 + i] = h.noisy41 ? x * h.nz[row * h.ldn + H2 + H3 + i] : 0.0f;
-        }
-        __syncwarp();
-        float d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};          // four interleaved partial sums per output (ILP), fixed order
-#pragma unroll 4
-        for (int i = 0; i < H3; i += 4) {
-            const float4 xa = *reinterpret_cast<const float4*>(&xs[i]), xb = *reinterpret_cast<const float4*>(&xs[H3 + i]);
-            const float xav[4] = {xa.x, xa.y, xa.z, xa.w}, xbv[4] = {xb.x, xb.y, xb.z, xb.w};
+        for (int r = 0; r < HEAD_R; r++) {
+            const int64_t row = row0 + r;
+            const bool ok = row < h.B;
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                d1[c] = fmaf(xav[c], Ut[(i + c) * HLD + lane], d1[c]);
-                d2[c] = fmaf(xbv[c], St[(i + c) * HLD + lane], d2[c]);
+            for (int t = 0; t < H3 / 32; t++) {
+                const int i = lane + 32 * t;
+                float x = 0.0f, xe = 0.0f;
+                if (ok) {
+                    x = h.y1[row * H3 + i] + h.ub31[i];
+                    if (h.noisy31) x = fmaf(h.nz[row * h.ldn + H2 + i], h.y2[row * H3 + i] + h.sb31[i], x);
+                    x = fmaxf(x, 0.0f);
+                    xe = h.noisy41 ? x * h.nz[row * h.ldn + H2 + H3 + i] : 0.0f;
+                }
+                xs[(r * 2) * H3 + i] = x; xs[(r * 2 + 1) * H3 + i] = xe;
             }
         }
-        float v = ((d1[0] + d1[1]) + (d1[2] + d1[3])) + ubo;
-        if (h.noisy41) v = fmaf(h.nz[row * h.ldn + H2 + H3 + H3 + min(lane, h.A - 1)], ((d2[0] + d2[1]) + (d2[2] + d2[3])) + sbo, v);
-        if (lane < h.A && h.q) h.q[row * h.A + lane] = v;
-        float best = (lane < h.A) ? v : -INFINITY; int besti = lane;
+        __syncwarp();
+        // per row: four interleaved partial sums per output, fixed order (the arithmetic of the one-row version, bit for bit)
+        float d1[HEAD_R][4], d2[HEAD_R][4];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {         // first maximum, like torch.max(1)[1]
-            const float ob = __shfl_xor_sync(0xffffffffu, best, off); const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
-            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        for (int r = 0; r < HEAD_R; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) { d1[r][c] = 0.f; d2[r][c] = 0.f; }
+#pragma unroll 2
+        for (int i = 0; i < H3; i += 4) {
+            float u[4], sg[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) { u[c] = Ut[(i + c) * HLD + lane]; sg[c] = St[(i + c) * HLD + lane]; }
+#pragma unroll
+            for (int r = 0; r < HEAD_R; r++) {
+                const float4 xa = *reinterpret_cast<const float4*>(&xs[(r * 2) * H3 + i]), xb = *reinterpret_cast<const float4*>(&xs[(r * 2 + 1) * H3 + i]);
+                d1[r][0] = fmaf(xa.x, u[0], d1[r][0]); d1[r][1] = fmaf(xa.y, u[1], d1[r][1]); d1[r][2] = fmaf(xa.z, u[2], d1[r][2]); d1[r][3] = fmaf(xa.w, u[3], d1[r][3]);
+                d2[r][0] = fmaf(xb.x, sg[0], d2[r][0]); d2[r][1] = fmaf(xb.y, sg[1], d2[r][1]); d2[r][2] = fmaf(xb.z, sg[2], d2[r][2]); d2[r][3] = fmaf(xb.w, sg[3], d2[r][3]);
+            }
         }
-        if (lane == 0 && h.greedy) h.greedy[row] = besti;
+#pragma unroll
+        for (int r = 0; r < HEAD_R; r++) {
+            const int64_t row = row0 + r;
+            if (row >= h.B) break;                       // warp-uniform
+            float v = ((d1[r][0] + d1[r][1]) + (d1[r][2] + d1[r][3])) + ubo;
+            if (h.noisy41) v = fmaf(h.nz[row * h.ldn + H2 + H3 + H3 + min(lane, h.A - 1)], ((d2[r][0] + d2[r][1]) + (d2[r][2] + d2[r][3])) + sbo, v);
+            if (lane < h.A && h.q) h.q[row * h.A + lane] = v;
+            float best = (lane < h.A) ? v : -INFINITY; int besti = lane;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {     // first maximum, like torch.max(1)[1]
+                const float ob = __shfl_xor_sync(0xffffffffu, best, off); const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
+                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            }
+            if (lane == 0 && h.greedy) h.greedy[row] = besti;
+        }
     }
 }
 
@@ -415,12 +654,15 @@ __global__ void noise_kernel(float* __restrict__ out, int64_t B, int width, uint
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const float u1 = ((float)(o[2 * h] >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(o[2 * h + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-        const float rad = sqrtf(-2.0f * logf(u1));
-        float s, cc; sincospif(2.0f * u2, &s, &cc);
+        const float rad = sqrtf(-2.0f * __logf(u1));           // fast intrinsics: the law of the noise matters, not its last bits
+        float s, cc; __sincosf(6.283185307179586f * u2, &s, &cc);
         nrm[2 * h] = rad * cc; nrm[2 * h + 1] = rad * s;
     }
+    if (c * 4 + 3 < width && (width & 3) == 0) *reinterpret_cast<float4*>(out + b * width + c * 4) = make_float4(noisy_f(nrm[0]), noisy_f(nrm[1]), noisy_f(nrm[2]), noisy_f(nrm[3]));
+    else {
 #pragma unroll
-    for (int e = 0; e < 4; e++) if (c * 4 + e < width) out[b * width + c * 4 + e] = noisy_f(nrm[e]);
+        for (int e = 0; e < 4; e++) if (c * 4 + e < width) out[b * width + c * 4 + e] = noisy_f(nrm[e]);
+    }
 }
 
 __global__ void eps_greedy_kernel(const int32_t* __restrict__ greedy, int64_t B, int A, double eps, uint64_t seed, int64_t traj_offset, uint64_t counter,
@@ -540,10 +782,45 @@ struct qc_policy {
     int64_t psize[QC_P_COUNT] = {};
     bool pset[QC_P_COUNT] = {};
     float *h1 = nullptr, *h2 = nullptr, *h2n = nullptr, *a3 = nullptr, *hv = nullptr, *noise = nullptr;
+    // TMA-fed path: TF32 hi / lo copies of the activations ([cap][512] each) and of the four GEMM weight matrices (split when they are set)
+    float *h1s[2] = {}, *h2s[2] = {}, *h2ns[2] = {};
+    float *wsplit[QC_P_COUNT][2] = {};
+    TmaGemmArgs tm_fc2, tm_fc31, tm_fc32;                 // tensor maps + fixed arguments, rebuilt when the batch size or a buffer changes
+    int64_t maps_B = -1;
     int64_t cap = 0;
     int64_t launches = 0;
-    int gemm_kind = 0;       // 0: tcgen05 3xTF32 kernel (default), 1: CUDA-core fp32 kernel (cross-check; QCART_GEMM_SIMT=1 makes it the default)
+    int gemm_kind = 0;       // 0: TMA-fed tcgen05 3xTF32 kernel (default), 1: CUDA-core fp32 kernel (cross-check; QCART_GEMM_SIMT=1 makes it the default),
+                             // 2: tcgen05 3xTF32 with thread-staged operands (round-1 kernel; QCART_GEMM_STAGED=1)
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libqcart links cudart statically and has no link-time libcuda dependency)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+    static tmap_encode_fn fn = []() -> tmap_encode_fn {
+        void* f = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+        return reinterpret_cast<tmap_encode_fn>(f);
+    }();
+    return fn;
+}
+// fp32 matrix [rows][K] row-major -> tiles of box_rows x 32 floats (128-byte rows, 128-byte swizzle); rows past the end read as zeros
+static int make_tmap(CUtensorMap* m, const float* ptr, int64_t rows, int K, int box_rows) {
+    tmap_encode_fn enc = tmap_encoder();
+    if (!enc) return set_error(QC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)K * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)TMA_KS, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(QC_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return QC_OK;
+}
+static inline int tma_nt(int64_t M, int N, int nz) {       // tile width: 128 when that still gives every SM a CTA, else 64
+    static const int force_nt = getenv("QCART_TMA_NT") ? atoi(getenv("QCART_TMA_NT")) : 0;
+    if ((force_nt == 64 || force_nt == 128) && N % force_nt == 0) return force_nt;
+    const int64_t mt = (M + UM - 1) / UM;
+    return (N % 128 == 0 && mt * (N / 128) * nz >= 148) ? 128 : 64;
+}
 
 extern "C" int qc_obs_f32(const double* moments, int64_t count, double input_scaling, float* obs, void* stream) {
     if (!moments || !obs || count < 0) return set_error(QC_ERR_ARG, "qc_obs_f32: null pointer or negative count");
@@ -563,7 +840,7 @@ extern "C" int qc_policy_create(int32_t n_in, int32_t n_actions, int32_t noisy_l
     qc_policy* p = new (std::nothrow) qc_policy();
     if (!p) return set_error(QC_ERR_CUDA, "out of host memory");
     p->n_in = n_in; p->n_actions = n_actions; p->noisy_layers = noisy_layers; p->device = device;
-    p->gemm_kind = getenv("QCART_GEMM_SIMT") ? 1 : 0;
+    p->gemm_kind = getenv("QCART_GEMM_SIMT") ? 1 : (getenv("QCART_GEMM_STAGED") ? 2 : 0);
     int64_t* z = p->psize;
     z[QC_P_FC1_W] = (int64_t)H1 * n_in; z[QC_P_FC1_B] = H1; z[QC_P_FC2_W] = (int64_t)H2 * H1; z[QC_P_FC2_B] = H2;
     z[QC_P_FC31_UW] = (int64_t)H3 * H2; z[QC_P_FC31_UB] = H3;
@@ -574,6 +851,10 @@ extern "C" int qc_policy_create(int32_t n_in, int32_t n_actions, int32_t noisy_l
     for (int i = 0; i < QC_P_COUNT; i++) {
         if (z[i] == 0) { p->pset[i] = true; continue; }
         if (cudaMalloc(&p->param[i], sizeof(float) * (size_t)((z[i] + 3) / 4 * 4)) != cudaSuccess) { cudaGetLastError(); qc_policy_destroy(p); return set_error(QC_ERR_CUDA, "cudaMalloc failed for the policy parameters"); }
+        if (i == QC_P_FC2_W || i == QC_P_FC31_UW || i == QC_P_FC31_SW || i == QC_P_FC32_W) {
+            for (int h = 0; h < 2; h++)
+                if (cudaMalloc(&p->wsplit[i][h], sizeof(float) * (size_t)z[i]) != cudaSuccess) { cudaGetLastError(); qc_policy_destroy(p); return set_error(QC_ERR_CUDA, "cudaMalloc failed for the policy parameters"); }
+        }
     }
     *out = p;
     return QC_OK;
@@ -582,8 +863,9 @@ extern "C" int qc_policy_create(int32_t n_in, int32_t n_actions, int32_t noisy_l
 extern "C" int qc_policy_destroy(qc_policy* p) {
     if (!p) return QC_OK;
     cudaSetDevice(p->device);
-    for (int i = 0; i < QC_P_COUNT; i++) cudaFree(p->param[i]);
+    for (int i = 0; i < QC_P_COUNT; i++) { cudaFree(p->param[i]); cudaFree(p->wsplit[i][0]); cudaFree(p->wsplit[i][1]); }
     cudaFree(p->h1); cudaFree(p->h2); cudaFree(p->h2n); cudaFree(p->a3); cudaFree(p->hv); cudaFree(p->noise);
+    for (int h = 0; h < 2; h++) { cudaFree(p->h1s[h]); cudaFree(p->h2s[h]); cudaFree(p->h2ns[h]); }
     delete p;
     return QC_OK;
 }
@@ -601,7 +883,7 @@ extern "C" int64_t qc_policy_noise_width(const qc_policy* p) {
 extern "C" int64_t qc_policy_launch_count(const qc_policy* p) { return p ? p->launches : 0; }
 
 extern "C" int qc_policy_set_gemm(qc_policy* p, int32_t kind) {
-    if (!p || kind < 0 || kind > 1) return set_error(QC_ERR_ARG, "qc_policy_set_gemm: kind must be 0 (tcgen05 3xTF32) or 1 (CUDA-core fp32)");
+    if (!p || kind < 0 || kind > 2) return set_error(QC_ERR_ARG, "qc_policy_set_gemm: kind must be 0 (TMA-fed tcgen05 3xTF32), 1 (CUDA-core fp32) or 2 (tcgen05 3xTF32, thread-staged operands)");
     p->gemm_kind = kind;
     return QC_OK;
 }
@@ -612,22 +894,44 @@ extern "C" int qc_policy_set_param(qc_policy* p, int32_t which, const float* hos
     if (count != p->psize[which]) return set_error(QC_ERR_ARG, "qc_policy_set_param: wrong element count (expected " + std::to_string(p->psize[which]) + ", got " + std::to_string(count) + ")");
     RO_CUDA(cudaSetDevice(p->device));
     RO_CUDA(cudaMemcpy(p->param[which], host, sizeof(float) * (size_t)count, cudaMemcpyHostToDevice));
+    if (p->wsplit[which][0]) {                              // TF32 hi / lo copies for the TMA-fed GEMM
+        split_kernel<<<blocks_for(count, 256), 256>>>(p->param[which], p->wsplit[which][0], p->wsplit[which][1], count);
+        RO_CUDA(cudaGetLastError()); RO_CUDA(cudaDeviceSynchronize());
+    }
     p->pset[which] = true;
     return QC_OK;
 }
 
 constexpr size_t GEMM_SMEM_1 = sizeof(float) * (size_t)TILE_FLOATS;
 constexpr size_t GEMM_SMEM_4 = sizeof(float) * ((size_t)4 * TILE_FLOATS + (size_t)3 * BM * BN);
-constexpr size_t HEAD_SMEM = sizeof(float) * ((size_t)2 * H3 * HLD + (size_t)HEAD_WARPS * 2 * H3);
+constexpr size_t HEAD_SMEM = sizeof(float) * ((size_t)2 * H3 * HLD + (size_t)HEAD_WARPS * HEAD_R * 2 * H3);
 
-static int launch_gemm(const GemmArgs& g, int nz, cudaStream_t st, bool use_umma) {
+constexpr size_t TMA_SMEM_128 = 3 * (2 * 16384 + 2 * 128 * 128) + 1024, TMA_SMEM_64 = 4 * (2 * 16384 + 2 * 64 * 128) + 1024;   // stage ring + alignment slack
+
+// opt-in dynamic shared-memory sizes of the policy kernels, once per device and thread
+static int set_kernel_attributes() {
     static thread_local bool attr_set[64] = {};
     int dev = 0; cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
         RO_CUDA(cudaFuncSetAttribute(gemm_splitk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_4));
         RO_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM));
+        RO_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_128));
+        RO_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_64));
         attr_set[dev] = true;
     }
+    return QC_OK;
+}
+
+static int launch_tma_gemm(const TmaGemmArgs& t, int nz, int nt, cudaStream_t st) {
+    const int mt = (t.M + UM - 1) / UM;
+    if (nt == 128) gemm_tma_kernel<128><<<dim3(t.N / 128, mt, nz), 128, TMA_SMEM_128, st>>>(t);
+    else gemm_tma_kernel<64><<<dim3(t.N / 64, mt, nz), 128, TMA_SMEM_64, st>>>(t);
+    if (cudaError_t e = cudaGetLastError()) return set_error(QC_ERR_CUDA, std::string("gemm_tma_kernel launch: ") + cudaGetErrorString(e));
+    return QC_OK;
+}
+
+static int launch_gemm(const GemmArgs& g, int nz, cudaStream_t st, bool use_umma) {
+    int dev = 0; cudaGetDevice(&dev);
     if (use_umma && g.K % UK == 0 && g.N % 64 == 0) {
         auto smem_for = [](int nt) { return sizeof(float) * 2 * 2 * 8 * (size_t)((UM + 1) * 4 + (nt + 1) * 4); };
         static thread_local bool umma_attr[64] = {};
@@ -665,11 +969,17 @@ extern "C" int qc_policy_forward(qc_policy* p, const float* obs, int64_t B, int3
     for (int i = 0; i < QC_P_COUNT; i++) if (!p->pset[i]) return set_error(QC_ERR_STATE, "qc_policy_forward: parameter tensor " + std::to_string(i) + " was never set");
     if (B == 0) return QC_OK;
     RO_CUDA(cudaSetDevice(p->device));
+    if (int rc = set_kernel_attributes()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int NW = (int)qc_policy_noise_width(p);
     if (p->cap < B) {
         cudaFree(p->h1); cudaFree(p->h2); cudaFree(p->h2n); cudaFree(p->a3); cudaFree(p->hv); cudaFree(p->noise);
-        p->h1 = p->h2 = p->h2n = p->a3 = p->hv = p->noise = nullptr; p->cap = 0;
+        p->h1 = p->h2 = p->h2n = p->a3 = p->hv = p->noise = nullptr; p->cap = 0; p->maps_B = -1;
+        for (int h = 0; h < 2; h++) {
+            cudaFree(p->h1s[h]); cudaFree(p->h2s[h]); cudaFree(p->h2ns[h]); p->h1s[h] = p->h2s[h] = p->h2ns[h] = nullptr;
+            RO_CUDA(cudaMalloc(&p->h1s[h], sizeof(float) * (size_t)B * H1)); RO_CUDA(cudaMalloc(&p->h2s[h], sizeof(float) * (size_t)B * H2));
+            RO_CUDA(cudaMalloc(&p->h2ns[h], sizeof(float) * (size_t)B * H2));
+        }
         RO_CUDA(cudaMalloc(&p->h1, sizeof(float) * (size_t)B * H1)); RO_CUDA(cudaMalloc(&p->h2, sizeof(float) * (size_t)B * H2));
         RO_CUDA(cudaMalloc(&p->h2n, sizeof(float) * (size_t)B * H2));
         RO_CUDA(cudaMalloc(&p->a3, sizeof(float) * (size_t)B * H3 * 2)); RO_CUDA(cudaMalloc(&p->hv, sizeof(float) * (size_t)B * HV));
@@ -685,33 +995,80 @@ extern "C" int qc_policy_forward(qc_policy* p, const float* obs, int64_t B, int3
             nz = p->noise;
         } else nz = noise;
     }
-    fc1_kernel<<<blocks_for(B, FC1_ROWS), 512, sizeof(float) * FC1_ROWS * p->n_in, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], p->h1, B, p->n_in, H1);
-    GemmArgs g{};
     const bool n31 = any_noise && p->noisy_layers >= 2, n41 = any_noise && p->noisy_layers >= 1;
+    const bool tma = p->gemm_kind == 0;
+    auto launch_fc1 = [&](float* h, float* hh, float* hl) {
+        if (p->n_in <= 8) fc1_small_kernel<8><<<blocks_for(B, FC1S_ROWS), 512, 0, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], h, hh, hl, B, p->n_in, H1);
+        else if (p->n_in <= 24) fc1_small_kernel<24><<<blocks_for(B, FC1S_ROWS), 512, 0, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], h, hh, hl, B, p->n_in, H1);
+        else fc1_kernel<<<blocks_for(B, FC1_ROWS), 512, sizeof(float) * FC1_ROWS * p->n_in, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], h, hh, hl, B, p->n_in, H1);
+    };
+    if (tma) {
+        // ---- TMA-fed tensor-core path: every GEMM operand is a pre-split (hi, lo) pair described by tensor maps ----
+        if (p->maps_B != B) {
+            auto maps = [&](TmaGemmArgs& t, int zi, float* const* a, float* const* w, int N, int K, int nt) -> int {
+                if (int rc = make_tmap(&t.a_hi[zi], a[0], B, K, UM)) return rc;
+                if (int rc = make_tmap(&t.a_lo[zi], a[1], B, K, UM)) return rc;
+                if (int rc = make_tmap(&t.w_hi[zi], w[0], N, K, nt)) return rc;
+                return make_tmap(&t.w_lo[zi], w[1], N, K, nt);
+            };
+            memset(&p->tm_fc2, 0, sizeof(TmaGemmArgs)); memset(&p->tm_fc31, 0, sizeof(TmaGemmArgs)); memset(&p->tm_fc32, 0, sizeof(TmaGemmArgs));
+            const bool has31s = p->noisy_layers >= 2;
+            if (int rc = maps(p->tm_fc2, 0, p->h1s, p->wsplit[QC_P_FC2_W], H2, H1, tma_nt(B, H2, 1))) return rc;
+            if (int rc = maps(p->tm_fc2, 1, p->h1s, p->wsplit[QC_P_FC2_W], H2, H1, tma_nt(B, H2, 1))) return rc;
+            // (the tile width of fc31 is chosen for the noisy case, two GEMMs per launch, whenever the policy has that layer)
+            const int nt31 = tma_nt(B, H3, has31s ? 2 : 1);
+            if (int rc = maps(p->tm_fc31, 0, p->h2s, p->wsplit[QC_P_FC31_UW], H3, H2, nt31)) return rc;
+            if (int rc = maps(p->tm_fc31, 1, has31s ? p->h2ns : p->h2s, has31s ? p->wsplit[QC_P_FC31_SW] : p->wsplit[QC_P_FC31_UW], H3, H2, nt31)) return rc;
+            if (int rc = maps(p->tm_fc32, 0, p->h2s, p->wsplit[QC_P_FC32_W], HV, H2, tma_nt(B, HV, 1))) return rc;
+            if (int rc = maps(p->tm_fc32, 1, p->h2s, p->wsplit[QC_P_FC32_W], HV, H2, tma_nt(B, HV, 1))) return rc;
+            p->maps_B = B;
+        }
+        launch_fc1(nullptr, p->h1s[0], p->h1s[1]);
+        if (cudaError_t e = cudaGetLastError()) return set_error(QC_ERR_CUDA, std::string("fc1 launch: ") + cudaGetErrorString(e));
+        TmaGemmArgs t = p->tm_fc2;                          // fc2: relu(. + b) -> split copies of h2 (and of h2 * e_in31 for the sigma_w half of fc31)
+        t.bias = p->param[QC_P_FC2_B]; t.relu_bias = 1; t.M = (int)B; t.N = H2; t.K = H1; t.ldn = NW;
+        t.C = nullptr; t.C_hi = p->h2s[0]; t.C_lo = p->h2s[1];
+        if (n31) { t.C2_hi = p->h2ns[0]; t.C2_lo = p->h2ns[1]; t.ei = nz; }
+        if (int rc = launch_tma_gemm(t, 1, tma_nt(B, H2, 1), st)) return rc;
+        t = p->tm_fc31;                                     // fc31: raw halves y1 (z = 0) and y2 (z = 1); combined by the head kernel
+        t.relu_bias = 0; t.M = (int)B; t.N = H3; t.K = H2; t.ldn = NW; t.C = p->a3;
+        if (int rc = launch_tma_gemm(t, n31 ? 2 : 1, tma_nt(B, H3, p->noisy_layers >= 2 ? 2 : 1), st)) return rc;
+        p->launches += 3;
+    }
+    GemmArgs g{};
+    if (!tma) {
+    launch_fc1(p->h1, nullptr, nullptr);
     g.A = p->h1; g.W = p->param[QC_P_FC2_W]; g.bias = p->param[QC_P_FC2_B]; g.C = p->h2; g.M = (int)B; g.N = H2; g.K = H1; g.ldn = NW; g.relu_bias = 1;
     if (n31) { g.C2 = p->h2n; g.ei = nz; }              // h2 * e_in31 for the sigma_w half of fc31
-    if (int rc = launch_gemm(g, 1, st, p->gemm_kind == 0)) return rc;
+    if (int rc = launch_gemm(g, 1, st, p->gemm_kind == 2)) return rc;
     g = GemmArgs{};                                     // fc31: raw halves y1 (z = 0) and y2 (z = 1); combined by the head kernel
     g.A = p->h2; g.A2 = p->h2n; g.W = p->param[QC_P_FC31_UW]; g.S = p->param[QC_P_FC31_SW]; g.ldn = NW; g.C = p->a3; g.M = (int)B; g.N = H3; g.K = H2; g.relu_bias = 0;
-    if (int rc = launch_gemm(g, n31 ? 2 : 1, st, p->gemm_kind == 0)) return rc;
+    if (int rc = launch_gemm(g, n31 ? 2 : 1, st, p->gemm_kind == 2)) return rc;
     p->launches += 3;
+    }
     if (q || greedy) {
         HeadArgs h{};
         h.y1 = p->a3; h.y2 = p->a3 + (size_t)B * H3; h.ub31 = p->param[QC_P_FC31_UB]; h.sb31 = p->param[QC_P_FC31_SB];
         h.U = p->param[QC_P_FC41_UW]; h.S = p->param[QC_P_FC41_SW]; h.ub = p->param[QC_P_FC41_UB]; h.sb = p->param[QC_P_FC41_SB];
         h.nz = nz; h.ldn = NW; h.A = p->n_actions; h.noisy31 = n31 ? 1 : 0; h.noisy41 = n41 ? 1 : 0; h.q = q; h.greedy = greedy; h.B = B;
-        const unsigned nb = (unsigned)std::min<int64_t>((B + HEAD_WARPS - 1) / HEAD_WARPS, 148 * 2);
+        const unsigned nb = (unsigned)std::min<int64_t>((B + HEAD_WARPS * HEAD_R - 1) / (HEAD_WARPS * HEAD_R), 148);        // 199 KB of shared memory: one CTA per SM
         head_kernel<<<nb, HEAD_WARPS * 32, HEAD_SMEM, st>>>(h);
         p->launches++;
     }
-    if (value) {
+    if (value && tma) {
+        TmaGemmArgs t = p->tm_fc32;
+        t.bias = p->param[QC_P_FC32_B]; t.relu_bias = 1; t.M = (int)B; t.N = HV; t.K = H2; t.ldn = NW; t.C = p->hv;
+        if (int rc = launch_tma_gemm(t, 1, tma_nt(B, HV, 1), st)) return rc;
+        value_kernel<<<blocks_for(B, 8), 256, 0, st>>>(p->hv, p->param[QC_P_FC42_W], p->param[QC_P_FC42_B], value, B);
+        p->launches += 2;
+    } else if (value) {
         g = GemmArgs{};
         g.A = p->h2; g.W = p->param[QC_P_FC32_W]; g.bias = p->param[QC_P_FC32_B]; g.C = p->hv; g.M = (int)B; g.N = HV; g.K = H2; g.ldn = NW; g.relu_bias = 1;
-        if (int rc = launch_gemm(g, 1, st, p->gemm_kind == 0)) return rc;
+        if (int rc = launch_gemm(g, 1, st, p->gemm_kind == 2)) return rc;
         value_kernel<<<blocks_for(B, 8), 256, 0, st>>>(p->hv, p->param[QC_P_FC42_W], p->param[QC_P_FC42_B], value, B);
         p->launches += 2;
     }
-    RO_CUDA(cudaGetLastError());
+    if (cudaError_t e = cudaGetLastError()) return set_error(QC_ERR_CUDA, std::string("qc_policy_forward (head / value kernels): ") + cudaGetErrorString(e));
     return QC_OK;
 }
 

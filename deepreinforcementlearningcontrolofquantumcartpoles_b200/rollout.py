@@ -136,8 +136,9 @@ class DirectDQNPolicy:
         return int(self.lib.qc_policy_launch_count(self.h))
 
     def set_gemm(self, kind):
-        """"tcgen05" (default: 3xTF32 on the tensor cores) or "simt" (fp32 FMA on the CUDA cores, the cross-check)."""
-        L.check(self.lib.qc_policy_set_gemm(self.h, {"tcgen05": 0, "simt": 1}[kind]))
+        """"tcgen05" (default: 3xTF32 on the tensor cores, pre-split operands fed by TMA), "simt" (fp32 FMA on the CUDA cores, the cross-check)
+        or "tcgen05_staged" (the same tensor-core arithmetic with operands split and staged by the CTA's threads)."""
+        L.check(self.lib.qc_policy_set_gemm(self.h, {"tcgen05": 0, "simt": 1, "tcgen05_staged": 2}[kind]))
 
 
 def observation(moments, input_scaling=1.0):
