@@ -386,6 +386,7 @@ struct TmaGemmArgs {
     float* C;                                            // raw fp32 output (nullable), [z][M][N]
     float* C_hi; float* C_lo;                            // TF32 split of the output (nullable; z = 0 only)
     float* C2_hi; float* C2_lo;                          // TF32 split of output * ei (nullable; z = 0 only)
+    float* C2;                                           // output * ei, raw fp32 (nullable; z = 0 only)
     int M, N, K; int relu_bias;
 };
 constexpr int TMA_KS = 32;                                // K floats per stage = one 128-byte swizzle row
@@ -399,12 +400,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
-template <int NT>
+// RAW = true (qc_policy_set_gemm kind 3): the copies in global memory are the plain fp32 matrices (a_hi / w_hi maps); the tensor core reads them
+// as TF32, i.e. ignores the low 13 mantissa bits, which IS the hi part (verified bitwise against the masked copies), and warps 2-3 derive the
+// lo parts in shared memory (lo = a - hi, an elementwise pass over the stage that does not care about the swizzle) while the MMAs of the
+// previous stage run.  Half the L2 -> SM traffic and no split copies in HBM -- but measured slower (65 536 trajectories: fc31 147 vs 122 us
+// per GEMM): the three SS-mode products already read 96 KB of shared memory per stage, and the split pass adds 64 KB to the same pipe.
+template <int NT, bool RAW>
 __global__ void __launch_bounds__(128) gemm_tma_kernel(const __grid_constant__ TmaGemmArgs g) {
     constexpr uint32_t A_BYTES = UM * 128, W_BYTES = NT * 128, STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    constexpr uint32_t TX_BYTES = RAW ? A_BYTES + W_BYTES : STAGE_BYTES;
     constexpr int S = (NT == 128) ? 3 : 4;                // ring depth: 3 x 64 KB / 4 x 48 KB
     extern __shared__ unsigned char tsm_raw[];
-    __shared__ __align__(8) uint64_t bar_full[S], bar_empty[S], bar_acc;
+    __shared__ __align__(8) uint64_t bar_full[S], bar_empty[S], bar_split[S], bar_acc;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int z = blockIdx.z, m0 = blockIdx.y * UM, n0 = blockIdx.x * NT;
@@ -417,6 +424,7 @@ __global__ void __launch_bounds__(128) gemm_tma_kernel(const __grid_constant__ T
         for (int i = 0; i < S; i++) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_full[i])), "r"(1u) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_empty[i])), "r"(1u) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_split[i])), "r"(2u) : "memory");
         }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar_acc)), "r"(1u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -433,12 +441,12 @@ __global__ void __launch_bounds__(128) gemm_tma_kernel(const __grid_constant__ T
                 const int slot = s % S, it = s / S;
                 if (it > 0) mbar_wait(smem_u32(&bar_empty[slot]), (uint32_t)((it - 1) & 1));     // the MMAs that read this slot have retired
                 const uint32_t fb = smem_u32(&bar_full[slot]), dst = ring + (uint32_t)slot * STAGE_BYTES;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(STAGE_BYTES) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(TX_BYTES) : "memory");
                 const int k0 = s * TMA_KS;
                 tma_load_2d(dst, &g.a_hi[z], k0, m0, fb);
-                tma_load_2d(dst + A_BYTES, &g.a_lo[z], k0, m0, fb);
+                if (!RAW) tma_load_2d(dst + A_BYTES, &g.a_lo[z], k0, m0, fb);
                 tma_load_2d(dst + 2 * A_BYTES, &g.w_hi[z], k0, n0, fb);
-                tma_load_2d(dst + 2 * A_BYTES + W_BYTES, &g.w_lo[z], k0, n0, fb);
+                if (!RAW) tma_load_2d(dst + 2 * A_BYTES + W_BYTES, &g.w_lo[z], k0, n0, fb);
             }
         }
         __syncwarp();
@@ -448,7 +456,7 @@ __global__ void __launch_bounds__(128) gemm_tma_kernel(const __grid_constant__ T
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
             for (int s = 0; s < nstages; s++) {
                 const int slot = s % S, it = s / S;
-                mbar_wait(smem_u32(&bar_full[slot]), (uint32_t)(it & 1));
+                mbar_wait(smem_u32(RAW ? &bar_split[slot] : &bar_full[slot]), (uint32_t)(it & 1));      // (RAW: the lo parts are in place, which implies the loads)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ah = ring + (uint32_t)slot * STAGE_BYTES, al = ah + A_BYTES, wh = al + A_BYTES, wl = wh + W_BYTES;
                 const uint32_t tacc = taddr + (uint32_t)((s / per_q) * NT);
@@ -471,6 +479,29 @@ __global__ void __launch_bounds__(128) gemm_tma_kernel(const __grid_constant__ T
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_acc)) : "memory");
         }
         __syncwarp();
+    } else if (RAW) {
+        // ---- split warps (2, 3): lo = a - hi for both operand tiles of the stage, same (swizzled) position in the lo buffers ----------------
+        const int st = tid - 64;
+        for (int s = 0; s < nstages; s++) {
+            const int slot = s % S, it = s / S;
+            mbar_wait(smem_u32(&bar_full[slot]), (uint32_t)(it & 1));
+            unsigned char* base = tsm_raw + (ring - smem_u32(tsm_raw)) + (size_t)slot * STAGE_BYTES;
+            const float4* a_raw = reinterpret_cast<const float4*>(base); float4* a_lo = reinterpret_cast<float4*>(base + A_BYTES);
+            const float4* w_raw = reinterpret_cast<const float4*>(base + 2 * A_BYTES); float4* w_lo = reinterpret_cast<float4*>(base + 2 * A_BYTES + W_BYTES);
+#pragma unroll 8
+            for (int e = st; e < (int)(A_BYTES / 16); e += 64) {
+                const float4 a = a_raw[e];
+                a_lo[e] = make_float4(a.x - tf32_hi(a.x), a.y - tf32_hi(a.y), a.z - tf32_hi(a.z), a.w - tf32_hi(a.w));
+            }
+#pragma unroll 8
+            for (int e = st; e < (int)(W_BYTES / 16); e += 64) {
+                const float4 a = w_raw[e];
+                w_lo[e] = make_float4(a.x - tf32_hi(a.x), a.y - tf32_hi(a.y), a.z - tf32_hi(a.z), a.w - tf32_hi(a.w));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_split[slot])) : "memory");
+        }
     }
     // ---- epilogue: thread = output row (tensor-memory lane) -------------------------------------------------------------------
     mbar_wait(smem_u32(&bar_acc), 0u);
@@ -507,7 +538,7 @@ __global__ void __launch_bounds__(128) gemm_tma_kernel(const __grid_constant__ T
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     float* C = g.C ? g.C + (size_t)z * g.M * g.N : nullptr;
-    const bool split_out = g.C_hi != nullptr && z == 0, split2 = g.C2_hi != nullptr && z == 0;
+    const bool split_out = g.C_hi != nullptr && z == 0, split2 = g.C2_hi != nullptr && z == 0, raw2 = g.C2 != nullptr && z == 0;
     constexpr int V4 = NT / 4;                            // float4 per tile row
     constexpr int PB = 4;                                 // segments per thread and pass: their loads are issued together (memory-level parallelism
                                                           // of a 128-thread CTA that is alone on its SM)
@@ -520,7 +551,7 @@ __global__ void __launch_bounds__(128) gemm_tma_kernel(const __grid_constant__ T
             o[u] = (size_t)m * g.N + n0 + c;
             x[u] = *reinterpret_cast<const float4*>(tile + (ok[u] ? row : 0) * LDT_ + c);
             ev[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (split2 && ok[u]) ev[u] = __ldg(reinterpret_cast<const float4*>(g.ei + (size_t)m * g.ldn + n0 + c));
+            if ((split2 || raw2) && ok[u]) ev[u] = __ldg(reinterpret_cast<const float4*>(g.ei + (size_t)m * g.ldn + n0 + c));
         }
 #pragma unroll
         for (int u = 0; u < PB; u++) {
@@ -531,6 +562,7 @@ __global__ void __launch_bounds__(128) gemm_tma_kernel(const __grid_constant__ T
                 *reinterpret_cast<float4*>(g.C_hi + o[u]) = h;
                 *reinterpret_cast<float4*>(g.C_lo + o[u]) = make_float4(x[u].x - h.x, x[u].y - h.y, x[u].z - h.z, x[u].w - h.w);
             }
+            if (raw2) *reinterpret_cast<float4*>(g.C2 + o[u]) = make_float4(x[u].x * ev[u].x, x[u].y * ev[u].y, x[u].z * ev[u].z, x[u].w * ev[u].w);
             if (split2) {
                 const float4 y = make_float4(x[u].x * ev[u].x, x[u].y * ev[u].y, x[u].z * ev[u].z, x[u].w * ev[u].w);
                 const float4 h = make_float4(tf32_hi(y.x), tf32_hi(y.y), tf32_hi(y.z), tf32_hi(y.w));
@@ -786,11 +818,12 @@ struct qc_policy {
     float *h1s[2] = {}, *h2s[2] = {}, *h2ns[2] = {};
     float *wsplit[QC_P_COUNT][2] = {};
     TmaGemmArgs tm_fc2, tm_fc31, tm_fc32;                 // tensor maps + fixed arguments, rebuilt when the batch size or a buffer changes
-    int64_t maps_B = -1;
+    int64_t maps_B = -1; int maps_raw = -1;
     int64_t cap = 0;
     int64_t launches = 0;
-    int gemm_kind = 0;       // 0: TMA-fed tcgen05 3xTF32 kernel (default), 1: CUDA-core fp32 kernel (cross-check; QCART_GEMM_SIMT=1 makes it the default),
-                             // 2: tcgen05 3xTF32 with thread-staged operands (round-1 kernel; QCART_GEMM_STAGED=1)
+    int gemm_kind = 0;       // 0: TMA-fed tcgen05 3xTF32 kernel, pre-split operands (default), 1: CUDA-core fp32 kernel (cross-check; QCART_GEMM_SIMT=1 makes it
+                             // the default), 2: tcgen05 3xTF32 with thread-staged operands (round-1 kernel; QCART_GEMM_STAGED=1), 3: TMA-fed from the plain
+                             // fp32 matrices, lo parts derived in shared memory (half the HBM / L2 traffic, but the extra shared-memory pass costs more)
 };
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (libqcart links cudart statically and has no link-time libcuda dependency)
@@ -883,7 +916,7 @@ extern "C" int64_t qc_policy_noise_width(const qc_policy* p) {
 extern "C" int64_t qc_policy_launch_count(const qc_policy* p) { return p ? p->launches : 0; }
 
 extern "C" int qc_policy_set_gemm(qc_policy* p, int32_t kind) {
-    if (!p || kind < 0 || kind > 2) return set_error(QC_ERR_ARG, "qc_policy_set_gemm: kind must be 0 (TMA-fed tcgen05 3xTF32), 1 (CUDA-core fp32) or 2 (tcgen05 3xTF32, thread-staged operands)");
+    if (!p || kind < 0 || kind > 3) return set_error(QC_ERR_ARG, "qc_policy_set_gemm: kind must be 0 (TMA-fed tcgen05 3xTF32), 1 (CUDA-core fp32), 2 (tcgen05 3xTF32, thread-staged operands) or 3 (TMA-fed, plain fp32 operands)");
     p->gemm_kind = kind;
     return QC_OK;
 }
@@ -915,17 +948,22 @@ static int set_kernel_attributes() {
     if (dev < 64 && !attr_set[dev]) {
         RO_CUDA(cudaFuncSetAttribute(gemm_splitk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_4));
         RO_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM));
-        RO_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_128));
-        RO_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_64));
+        RO_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_128));
+        RO_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_64));
+        RO_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_128));
+        RO_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_64));
         attr_set[dev] = true;
     }
     return QC_OK;
 }
 
-static int launch_tma_gemm(const TmaGemmArgs& t, int nz, int nt, cudaStream_t st) {
+static int launch_tma_gemm(const TmaGemmArgs& t, int nz, int nt, cudaStream_t st, bool raw) {
     const int mt = (t.M + UM - 1) / UM;
-    if (nt == 128) gemm_tma_kernel<128><<<dim3(t.N / 128, mt, nz), 128, TMA_SMEM_128, st>>>(t);
-    else gemm_tma_kernel<64><<<dim3(t.N / 64, mt, nz), 128, TMA_SMEM_64, st>>>(t);
+    if (raw) {
+        if (nt == 128) gemm_tma_kernel<128, true><<<dim3(t.N / 128, mt, nz), 128, TMA_SMEM_128, st>>>(t);
+        else gemm_tma_kernel<64, true><<<dim3(t.N / 64, mt, nz), 128, TMA_SMEM_64, st>>>(t);
+    } else if (nt == 128) gemm_tma_kernel<128, false><<<dim3(t.N / 128, mt, nz), 128, TMA_SMEM_128, st>>>(t);
+    else gemm_tma_kernel<64, false><<<dim3(t.N / 64, mt, nz), 128, TMA_SMEM_64, st>>>(t);
     if (cudaError_t e = cudaGetLastError()) return set_error(QC_ERR_CUDA, std::string("gemm_tma_kernel launch: ") + cudaGetErrorString(e));
     return QC_OK;
 }
@@ -996,43 +1034,50 @@ extern "C" int qc_policy_forward(qc_policy* p, const float* obs, int64_t B, int3
         } else nz = noise;
     }
     const bool n31 = any_noise && p->noisy_layers >= 2, n41 = any_noise && p->noisy_layers >= 1;
-    const bool tma = p->gemm_kind == 0;
+    const bool tma = p->gemm_kind == 0 || p->gemm_kind == 3, raw = p->gemm_kind == 3;
     auto launch_fc1 = [&](float* h, float* hh, float* hl) {
         if (p->n_in <= 8) fc1_small_kernel<8><<<blocks_for(B, FC1S_ROWS), 512, 0, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], h, hh, hl, B, p->n_in, H1);
         else if (p->n_in <= 24) fc1_small_kernel<24><<<blocks_for(B, FC1S_ROWS), 512, 0, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], h, hh, hl, B, p->n_in, H1);
         else fc1_kernel<<<blocks_for(B, FC1_ROWS), 512, sizeof(float) * FC1_ROWS * p->n_in, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], h, hh, hl, B, p->n_in, H1);
     };
     if (tma) {
-        // ---- TMA-fed tensor-core path: every GEMM operand is a pre-split (hi, lo) pair described by tensor maps ----
-        if (p->maps_B != B) {
+        // ---- TMA-fed tensor-core path: every GEMM operand is described by tensor maps -- the plain fp32 matrices (raw: the lo parts are derived
+        // in shared memory), or pre-split (hi, lo) pairs ----
+        if (p->maps_B != B || p->maps_raw != (raw ? 1 : 0)) {
             auto maps = [&](TmaGemmArgs& t, int zi, float* const* a, float* const* w, int N, int K, int nt) -> int {
                 if (int rc = make_tmap(&t.a_hi[zi], a[0], B, K, UM)) return rc;
-                if (int rc = make_tmap(&t.a_lo[zi], a[1], B, K, UM)) return rc;
+                if (!raw) { if (int rc = make_tmap(&t.a_lo[zi], a[1], B, K, UM)) return rc; }
                 if (int rc = make_tmap(&t.w_hi[zi], w[0], N, K, nt)) return rc;
-                return make_tmap(&t.w_lo[zi], w[1], N, K, nt);
+                return raw ? QC_OK : make_tmap(&t.w_lo[zi], w[1], N, K, nt);
             };
             memset(&p->tm_fc2, 0, sizeof(TmaGemmArgs)); memset(&p->tm_fc31, 0, sizeof(TmaGemmArgs)); memset(&p->tm_fc32, 0, sizeof(TmaGemmArgs));
             const bool has31s = p->noisy_layers >= 2;
-            if (int rc = maps(p->tm_fc2, 0, p->h1s, p->wsplit[QC_P_FC2_W], H2, H1, tma_nt(B, H2, 1))) return rc;
-            if (int rc = maps(p->tm_fc2, 1, p->h1s, p->wsplit[QC_P_FC2_W], H2, H1, tma_nt(B, H2, 1))) return rc;
+            float* const h1r[2] = {p->h1, nullptr}; float* const h2r[2] = {p->h2, nullptr}; float* const h2nr[2] = {p->h2n, nullptr};
+            float* const w2r[2] = {p->param[QC_P_FC2_W], nullptr}; float* const w31ur[2] = {p->param[QC_P_FC31_UW], nullptr};
+            float* const w31sr[2] = {p->param[QC_P_FC31_SW], nullptr}; float* const w32r[2] = {p->param[QC_P_FC32_W], nullptr};
+            float* const* a1 = raw ? h1r : p->h1s; float* const* a2 = raw ? h2r : p->h2s; float* const* a2n = raw ? h2nr : p->h2ns;
+            float* const* w2 = raw ? w2r : p->wsplit[QC_P_FC2_W]; float* const* w31u = raw ? w31ur : p->wsplit[QC_P_FC31_UW];
+            float* const* w31s = raw ? w31sr : p->wsplit[QC_P_FC31_SW]; float* const* w32 = raw ? w32r : p->wsplit[QC_P_FC32_W];
+            if (int rc = maps(p->tm_fc2, 0, a1, w2, H2, H1, tma_nt(B, H2, 1))) return rc;
+            if (int rc = maps(p->tm_fc2, 1, a1, w2, H2, H1, tma_nt(B, H2, 1))) return rc;
             // (the tile width of fc31 is chosen for the noisy case, two GEMMs per launch, whenever the policy has that layer)
             const int nt31 = tma_nt(B, H3, has31s ? 2 : 1);
-            if (int rc = maps(p->tm_fc31, 0, p->h2s, p->wsplit[QC_P_FC31_UW], H3, H2, nt31)) return rc;
-            if (int rc = maps(p->tm_fc31, 1, has31s ? p->h2ns : p->h2s, has31s ? p->wsplit[QC_P_FC31_SW] : p->wsplit[QC_P_FC31_UW], H3, H2, nt31)) return rc;
-            if (int rc = maps(p->tm_fc32, 0, p->h2s, p->wsplit[QC_P_FC32_W], HV, H2, tma_nt(B, HV, 1))) return rc;
-            if (int rc = maps(p->tm_fc32, 1, p->h2s, p->wsplit[QC_P_FC32_W], HV, H2, tma_nt(B, HV, 1))) return rc;
-            p->maps_B = B;
+            if (int rc = maps(p->tm_fc31, 0, a2, w31u, H3, H2, nt31)) return rc;
+            if (int rc = maps(p->tm_fc31, 1, has31s ? a2n : a2, has31s ? w31s : w31u, H3, H2, nt31)) return rc;
+            if (int rc = maps(p->tm_fc32, 0, a2, w32, HV, H2, tma_nt(B, HV, 1))) return rc;
+            if (int rc = maps(p->tm_fc32, 1, a2, w32, HV, H2, tma_nt(B, HV, 1))) return rc;
+            p->maps_B = B; p->maps_raw = raw ? 1 : 0;
         }
-        launch_fc1(nullptr, p->h1s[0], p->h1s[1]);
+        if (raw) launch_fc1(p->h1, nullptr, nullptr); else launch_fc1(nullptr, p->h1s[0], p->h1s[1]);
         if (cudaError_t e = cudaGetLastError()) return set_error(QC_ERR_CUDA, std::string("fc1 launch: ") + cudaGetErrorString(e));
         TmaGemmArgs t = p->tm_fc2;                          // fc2: relu(. + b) -> split copies of h2 (and of h2 * e_in31 for the sigma_w half of fc31)
         t.bias = p->param[QC_P_FC2_B]; t.relu_bias = 1; t.M = (int)B; t.N = H2; t.K = H1; t.ldn = NW;
-        t.C = nullptr; t.C_hi = p->h2s[0]; t.C_lo = p->h2s[1];
-        if (n31) { t.C2_hi = p->h2ns[0]; t.C2_lo = p->h2ns[1]; t.ei = nz; }
-        if (int rc = launch_tma_gemm(t, 1, tma_nt(B, H2, 1), st)) return rc;
+        if (raw) { t.C = p->h2; if (n31) { t.C2 = p->h2n; t.ei = nz; } }
+        else { t.C = nullptr; t.C_hi = p->h2s[0]; t.C_lo = p->h2s[1]; if (n31) { t.C2_hi = p->h2ns[0]; t.C2_lo = p->h2ns[1]; t.ei = nz; } }
+        if (int rc = launch_tma_gemm(t, 1, tma_nt(B, H2, 1), st, raw)) return rc;
         t = p->tm_fc31;                                     // fc31: raw halves y1 (z = 0) and y2 (z = 1); combined by the head kernel
         t.relu_bias = 0; t.M = (int)B; t.N = H3; t.K = H2; t.ldn = NW; t.C = p->a3;
-        if (int rc = launch_tma_gemm(t, n31 ? 2 : 1, tma_nt(B, H3, p->noisy_layers >= 2 ? 2 : 1), st)) return rc;
+        if (int rc = launch_tma_gemm(t, n31 ? 2 : 1, tma_nt(B, H3, p->noisy_layers >= 2 ? 2 : 1), st, raw)) return rc;
         p->launches += 3;
     }
     GemmArgs g{};
@@ -1058,7 +1103,7 @@ extern "C" int qc_policy_forward(qc_policy* p, const float* obs, int64_t B, int3
     if (value && tma) {
         TmaGemmArgs t = p->tm_fc32;
         t.bias = p->param[QC_P_FC32_B]; t.relu_bias = 1; t.M = (int)B; t.N = HV; t.K = H2; t.ldn = NW; t.C = p->hv;
-        if (int rc = launch_tma_gemm(t, 1, tma_nt(B, HV, 1), st)) return rc;
+        if (int rc = launch_tma_gemm(t, 1, tma_nt(B, HV, 1), st, raw)) return rc;
         value_kernel<<<blocks_for(B, 8), 256, 0, st>>>(p->hv, p->param[QC_P_FC42_W], p->param[QC_P_FC42_B], value, B);
         p->launches += 2;
     } else if (value) {

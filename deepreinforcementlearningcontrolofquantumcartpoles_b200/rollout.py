@@ -137,8 +137,9 @@ class DirectDQNPolicy:
 
     def set_gemm(self, kind):
         """"tcgen05" (default: 3xTF32 on the tensor cores, pre-split operands fed by TMA), "simt" (fp32 FMA on the CUDA cores, the cross-check)
-        or "tcgen05_staged" (the same tensor-core arithmetic with operands split and staged by the CTA's threads)."""
-        L.check(self.lib.qc_policy_set_gemm(self.h, {"tcgen05": 0, "simt": 1, "tcgen05_staged": 2}[kind]))
+        "tcgen05_staged" (the same tensor-core arithmetic with operands split and staged by the CTA's threads) or "tcgen05_raw" (TMA-fed
+        from the plain fp32 matrices, lo parts derived in shared memory)."""
+        L.check(self.lib.qc_policy_set_gemm(self.h, {"tcgen05": 0, "simt": 1, "tcgen05_staged": 2, "tcgen05_raw": 3}[kind]))
 
 
 def observation(moments, input_scaling=1.0):

@@ -76,7 +76,9 @@ int qc_action_forces(const int32_t *action, int64_t B, int32_t n_levels, double 
 
 int64_t qc_policy_launch_count(const qc_policy *p);
 /* Hidden-layer GEMM kernel: 0 (default) = tcgen05 tensor cores with a 3xTF32 split (fp32-level accuracy, fp32 accumulation in tensor memory),
- * 1 = fp32 FMA on the CUDA cores (the cross-check; bit-for-bit fp32 products). */
+ * operands pre-split in global memory and fed by TMA; 1 = fp32 FMA on the CUDA cores (the cross-check; bit-for-bit fp32 products);
+ * 2 = the tensor-core arithmetic of 0 with operands split and staged by the CTA's threads; 3 = TMA-fed from the plain fp32 matrices with
+ * the low parts derived in shared memory.  0, 2 and 3 give bitwise identical results. */
 int qc_policy_set_gemm(qc_policy *p, int32_t kind);
 
 /* ---- experience rows --------------------------------------------------------------------------------------------------------

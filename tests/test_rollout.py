@@ -122,7 +122,7 @@ def test_tensor_core_and_cuda_core_gemm_agree():
     n = [RO.noisy_f(rng.standard_normal(s)).astype(np.float32) for s in ((B, 512), (B, 256), (B, 256), (B, 21))]
     a, m = RO.direct_dqn_forward(sd, x, (n[0], n[1]), (n[2], n[3]))
     res = {}
-    for kind in ("tcgen05", "simt", "tcgen05_staged"):
+    for kind in ("tcgen05", "simt", "tcgen05_staged", "tcgen05_raw"):
         pol.set_gemm(kind)
         out = pol.forward(torch.as_tensor(x, device="cuda"), noise=pol.pack_noise(*n), want_value=True)
         res[kind] = out["q"].cpu().numpy()
@@ -131,6 +131,7 @@ def test_tensor_core_and_cuda_core_gemm_agree():
     assert np.abs(res["tcgen05"] - res["simt"]).max() <= 0.25 * QTOL * max(1.0, np.abs(a).max()), np.abs(res["tcgen05"] - res["simt"]).max()
     # TMA-fed and thread-staged kernels issue the same tensor-core instructions on the same split operands: bitwise equal
     assert np.array_equal(res["tcgen05"], res["tcgen05_staged"]), np.abs(res["tcgen05"] - res["tcgen05_staged"]).max()
+    assert np.array_equal(res["tcgen05_raw"], res["tcgen05_staged"]), np.abs(res["tcgen05_raw"] - res["tcgen05_staged"]).max()
 
 
 @pytest.mark.gpu
