@@ -551,6 +551,35 @@ def test_pipeline_kernel_fock_systems_match_oracle(task, monkeypatch):
     assert np.array_equal(flags, out0["flags"].cpu().numpy())
 
 
+@pytest.mark.parametrize("task,ne", [("quartic", "4"), ("quartic", "20"), ("harmonic", "8"), ("harmonic", "24")])
+def test_one_warp_group_pipeline_variants_match_oracle(task, ne, monkeypatch):
+    """One-warp explicit groups with one (NE) or two (NE + 16) solver warps per set -- the shorter recurrence of the second form is the default
+    for the harmonic oscillator, and an option (QCART_PIPE=2) for config 2's grid -- against the oracle with ragged budgets, and both forms
+    against each other (same chunked substitution up to the chunk length: rounding level)."""
+    monkeypatch.setenv("QCART_PIPE", "2"); monkeypatch.setenv("QCART_PIPE_NE", ne)
+    B, n_sub = 2800, 6
+    params, sim, out, psi0, actions, noise, budget = _pipe_case(B, n_sub, 41, ragged_budget=True, want_q=True, task=task)
+    want = "NE=%d,NSW=%d" % (int(ne) & 15, (int(ne) >> 4) + 1)
+    assert "sse_pipe_kernel" in sim.kernel_info() and want in sim.kernel_info(), sim.kernel_info()
+    got = sim.get_state(); flags = out["flags"].cpu().numpy(); xm = out["x_mean"].cpu().numpy()
+    orc = oracle_for(params)
+    pick = np.random.default_rng(3).choice(B, 16, replace=False)
+    pick[:2] = [0, B - 1]
+    for b in pick:
+        st = psi0[b].copy()
+        nb = int(budget[b])
+        f, qq, xx = orc.run(st, params["dt"], level_force(params, int(actions[b])), params["gamma"], noise[b][:nb], want_q=True)
+        assert rel_err(got[b][None], st[None]) < TOL_STEP
+        assert bool(flags[b] & L.QC_FLAG_FAIL) == bool(f)
+        if nb: assert np.max(np.abs(xm[b][:nb] - xx)) < 1e-10
+    assert np.allclose(out["aux"].cpu().numpy()[:, L.QC_AUX_NORM], 1.0, atol=1e-12)
+    monkeypatch.setenv("QCART_PIPE", "0")
+    _, sim0, out0, *_ = _pipe_case(B, n_sub, 41, ragged_budget=True, task=task)
+    assert "sse_step_kernel" in sim0.kernel_info()
+    assert rel_err(got, sim0.get_state()) < 1e-12
+    assert np.array_equal(flags, out0["flags"].cpu().numpy())
+
+
 @pytest.mark.parametrize("npts,B", [(1281, 340), (2049, 340)])
 def test_wide_grid_pipeline_matches_oracle(npts, B):
     """Single-group pipeline instances with the factor table in global memory (N = 577 .. 2112): a subset against the oracle."""
