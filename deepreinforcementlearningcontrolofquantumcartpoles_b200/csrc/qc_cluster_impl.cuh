@@ -184,7 +184,12 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
     const double e5 = dt * dt * dt * dt * dt * dt / 360.0, e4 = dt * dt * dt * dt * dt / 80.0, e3 = dt * dt * dt * dt / 24.0, e2 = dt * dt * dt / 12.0;
     const double q_scale = 1.0 / sqrt(2.0 * p.gamma) / dt;
     const int cols = (n + L - 1) / L;
-    constexpr int mult = GSL / 32;                                 // solver: 32 chunks of `mult` columns per slice (odd stride)
+    // Solver geometry.  The phases are bulk-synchronous, so during the substitution the explicit warps have nothing else to do: instead of one
+    // solver warp with 32 chunks of GSL/32 columns (66 recurrence rows per sweep at N = 4097: 16.7 k of the 31.5 k cycles of a substep), the
+    // first NSV warps of the CTA solve, thread t the chunk of SM = 3 columns [3 t - 1, 3 t + 2) (odd stride: conflict-free 16-byte loads of
+    // the state line and of the factor rows; 18 + W rows per sweep).  Columns -1 and >= GSL belong to the neighbours: computed as warm-up only.
+    constexpr int SM = 3, NCHK = (GSL + 1 + SM - 1) / SM, NSV = (NCHK + 31) / 32, NSVT = NSV * 32;
+    static_assert(NSVT <= GSL, "solver threads must be explicit threads");
     const int wb = p.W / L;
 
     // psi / solution on relative point r of lane g (r in [-4, L+4)): the first and the last lane of a slice read their outer halo straight
@@ -308,15 +313,15 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
         QC_CT(3);
         // ---- implicit solve: forward sweep (solver warp), z of the first 4 columns to the left neighbour, backward sweep ----------------
         double part[5] = {0.0, 0.0, 0.0, 0.0, 0.0};               // norm, sum x|psi|^2, centre probability, low / high boundary norms
-        const int col0 = lane * mult;
-        static_assert(GSL % 32 == 0 && ((GSL / 32) & 1) == 1, "slice width: 32 chunks of an odd number of columns");
-        const bool act = is_solver && (col_base + col0) < cols + wb;
+        const int col0 = tid * SM - 1;
+        const bool solves = tid < NSVT;                            // whole warps (named barrier between the warm-up reads and the in-place writes)
+        const bool act = tid < NCHK && (col_base + col0) < cols + wb;
         struct Row { double2 v; double2 cf[BA + 1]; };
         constexpr int PF = 1, NR = PF + 1, CS = Geo::CS, GT = Geo::GT;
         static_assert(L % NR == 0, "row ring: L must be a multiple of PF + 1");
         auto tabv = [&](int j, int k, int col) -> double2 { return tab[(j * CS + k) * GT + GU + col]; };      // col in [-GU, GSL + GU)
-        if (act) {
-            // forward: L y = rhs in column (scatter) form, z = D^{-1} y (see pipe_solve)
+        // forward: L y = rhs in column (scatter) form, z = D^{-1} y (see pipe_solve)
+        {
             auto load_fwd = [&](Row& r, int col, int j) {
                 r.v = U[j * GpU + GU + col];
 #pragma unroll
@@ -328,8 +333,6 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
             for (int k = 0; k < BA; k++) pend[k] = mk2(0.0, 0.0);
             Row ring[NR];
             int col = col0 - wb;
-#pragma unroll
-            for (int q = 0; q < PF; q++) load_fwd(ring[q], col, q);
             auto fwd_col = [&](bool own) {
 #pragma unroll
                 for (int j = 0; j < L; j++) {
@@ -343,38 +346,46 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
                         pend[k].x = fma(-yr, r.cf[k].x, fma(yi, r.cf[k].y, pr));
                         pend[k].y = fma(-yr, r.cf[k].y, fma(-yi, r.cf[k].x, pi));
                     }
-                    if (own) U[j * GpU + GU + col] = mk2(yr * r.cf[BA].x - yi * r.cf[BA].y, yr * r.cf[BA].y + yi * r.cf[BA].x);
+                    if (own && col >= 0 && col < GSL) U[j * GpU + GU + col] = mk2(yr * r.cf[BA].x - yi * r.cf[BA].y, yr * r.cf[BA].y + yi * r.cf[BA].x);
                 }
             };
-            for (int b = 0; b < wb; b++, col++) fwd_col(false);
-            __syncwarp(__activemask());
-            for (int b = 0; b < mult; b++, col++) fwd_col(true);
-        }
-        if (is_solver) {
-            __syncwarp();
-            // z of my first wb columns -> right guard of the left neighbour (warm-up of its backward sweep)
-            if (rank > 0) {
-                double2* nb = cluster.map_shared_rank(U, rank - 1);
-                for (int e = lane; e < wb * L; e += 32) { const int c = e / L, j = e % L; nb[j * GpU + GU + GSL + c] = U[j * GpU + GU + c]; }
+            if (act) {
+#pragma unroll
+                for (int q = 0; q < PF; q++) load_fwd(ring[q], col, q);
+                for (int b = 0; b < wb; b++, col++) fwd_col(false);
+            }
+            // z overwrites the right-hand side in place: every chunk must have read its warm-up columns (they belong to the chunks before it).
+            // Whole warps arrive (solves is warp-uniform), whether or not their lanes have a chunk.
+            if (solves) asm volatile("bar.sync 1, %0;" ::"n"(NSVT) : "memory");
+            if (act) {
+                for (int b = 0; b < SM; b++, col++) fwd_col(true);
+                // z of the slice's first wb columns -> right guard of the left neighbour (warm-up of its backward sweep), by the threads that own them
+                if (rank > 0) {
+                    double2* nb = cluster.map_shared_rank(U, rank - 1);
+                    for (int b = 0; b < SM; b++) {
+                        const int c = col0 + b;
+                        if (c >= 0 && c < wb) {
+#pragma unroll
+                            for (int j = 0; j < L; j++) nb[j * GpU + GU + GSL + c] = U[j * GpU + GU + c];
+                        }
+                    }
+                }
             }
         }
         QC_CT(4);
-        cluster_rendezvous(is_solver);
+        cluster_rendezvous(tid < NCHK);
         QC_CT(5);
-        if (act) {
+        {
             double2 pend[BA];
 #pragma unroll
             for (int k = 0; k < BA; k++) pend[k] = mk2(0.0, 0.0);
-            const bool do_cen = p.cen_hi > p.cen_lo;
             auto load_row = [&](Row& r, int col, int j) {
                 r.v = U[j * GpU + GU + col];
 #pragma unroll
                 for (int k = 0; k < BA; k++) r.cf[k] = tabv(j, k, col);
             };
             Row ring[NR];
-            int col = col0 + mult + wb - 1;
-#pragma unroll
-            for (int q = 0; q < PF; q++) load_row(ring[q], col, L - 1 - q);
+            int col = col0 + SM + wb - 1;
             auto bwd_col = [&](bool own) {
 #pragma unroll
                 for (int jr = 0; jr < L; jr++) {
@@ -389,21 +400,33 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
                         pend[k].x = fma(-xr, r.cf[k].x, fma(xi, r.cf[k].y, pr));
                         pend[k].y = fma(-xr, r.cf[k].y, fma(-xi, r.cf[k].x, pi));
                     }
-                    if (own) {
-                        U[j * GpU + GU + col] = mk2(xr, xi);
-                        const double a2 = xr * xr + xi * xi;
-                        const int i = (col_base + col) * L + j;
-                        part[0] += a2;
-                        part[1] = fma(p.h * (double)(i - p.half), a2, part[1]);
-                        if (do_cen && i >= p.cen_lo && i < p.cen_hi) part[2] += a2;
-                        if (i < p.fail_len) part[3] += a2;
-                        if (i >= n - p.fail_len && i < n) part[4] += a2;
-                    }
+                    if (own && col >= 0 && col < GSL) U[j * GpU + GU + col] = mk2(xr, xi);
                 }
             };
-            for (int b = 0; b < wb; b++, col--) bwd_col(false);
-            __syncwarp(__activemask());
-            for (int b = 0; b < mult; b++, col--) bwd_col(true);
+            if (act) {
+#pragma unroll
+                for (int q = 0; q < PF; q++) load_row(ring[q], col, L - 1 - q);
+                for (int b = 0; b < wb; b++, col--) bwd_col(false);
+            }
+            if (solves) asm volatile("bar.sync 1, %0;" ::"n"(NSVT) : "memory");
+            if (act) { for (int b = 0; b < SM; b++, col--) bwd_col(true); }
+        }
+        // norm, <x>, escape probability and boundary norms of the solution: by the explicit lanes on their own points, in parallel, instead of
+        // inside the serial recurrence (the backward rows were 60 % slower than the forward ones: 161 vs 100 cycles)
+        __syncthreads();
+        if (!is_solver) {
+            const bool do_cen = p.cen_hi > p.cen_lo;
+#pragma unroll
+            for (int j = 0; j < L; j++) {
+                const double2 c = U[j * GpU + GU + g];
+                const double a2 = c.x * c.x + c.y * c.y;
+                const int i = (col_base + g) * L + j;
+                part[0] += a2;
+                part[1] = fma(xs[j], a2, part[1]);
+                if (do_cen && i >= p.cen_lo && i < p.cen_hi) part[2] += a2;
+                if (i < p.fail_len) part[3] += a2;
+                if (i >= n - p.fail_len && i < n) part[4] += a2;
+            }
         }
         QC_CT(6);
         cluster_reduce<5, C, NWT>(cluster, part, wred, cred, phase, rank);

@@ -90,11 +90,11 @@ __global__ void __launch_bounds__(512) fc1_kernel(const float* __restrict__ obs,
 constexpr int FC1S_ROWS = 32;
 template <int NI>
 __global__ void __launch_bounds__(512) fc1_small_kernel(const float* __restrict__ obs, const float* __restrict__ W, const float* __restrict__ bias,
-                                                        float* __restrict__ h, float* __restrict__ h_hi, float* __restrict__ h_lo, int64_t B, int n_in, int n_out) {
+                                                        float* __restrict__ h, float* __restrict__ h_hi, float* __restrict__ h_lo, int64_t B, int n_in, int n_out, int rpc) {
     __shared__ __align__(16) float xs[FC1S_ROWS * NI];
-    const int64_t m0 = (int64_t)blockIdx.x * FC1S_ROWS;
-    const int rows = (int)min((int64_t)FC1S_ROWS, B - m0);
-    for (int e = threadIdx.x; e < FC1S_ROWS * NI; e += blockDim.x) { const int r = e / NI, i = e % NI; xs[e] = (r < rows && i < n_in) ? obs[(m0 + r) * n_in + i] : 0.0f; }
+    const int64_t m0 = (int64_t)blockIdx.x * rpc;          // rpc <= FC1S_ROWS rows per CTA (fewer for small batches: more CTAs)
+    const int rows = (int)min((int64_t)rpc, B - m0);
+    for (int e = threadIdx.x; e < rpc * NI; e += blockDim.x) { const int r = e / NI, i = e % NI; xs[e] = (r < rows && i < n_in) ? obs[(m0 + r) * n_in + i] : 0.0f; }
     __syncthreads();
     for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
         float w[NI];
@@ -585,9 +585,11 @@ struct HeadArgs {
     int A; int noisy31, noisy41;
     float* q; int32_t* greedy; int64_t B;
 };
-constexpr int HEAD_WARPS = 16, HLD = 33;                // transposed weight rows padded to 33 floats: conflict-free staging and reads
-constexpr int HEAD_R = 4;                                // trajectories per warp and pass: every weight read from shared memory serves HEAD_R rows
-                                                         // (one row at a time the kernel was bound by its shared-memory loads: 10 per 8 FMA, 202 us at 65 536 rows)
+constexpr int HLD = 33;                                  // transposed weight rows padded to 33 floats: conflict-free staging and reads
+// HEAD_R trajectories per warp and pass: every weight read from shared memory serves HEAD_R rows (one row at a time the kernel is bound by its
+// shared-memory loads, 10 per 8 FMA: 202 us at 65 536 rows).  Large batches: <4, 16> (one CTA per SM); small batches: <1, 8>, the one-row form,
+// whose grid of B / 8 CTAs covers the SMs at the reference's batch sizes (~1000 trajectories).
+template <int HEAD_R, int HEAD_WARPS>
 __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(const HeadArgs h) {
     extern __shared__ __align__(16) float hsm[];
     float* Ut = hsm;                                     // [256][33]  (u_w41 transposed)
@@ -937,7 +939,7 @@ extern "C" int qc_policy_set_param(qc_policy* p, int32_t which, const float* hos
 
 constexpr size_t GEMM_SMEM_1 = sizeof(float) * (size_t)TILE_FLOATS;
 constexpr size_t GEMM_SMEM_4 = sizeof(float) * ((size_t)4 * TILE_FLOATS + (size_t)3 * BM * BN);
-constexpr size_t HEAD_SMEM = sizeof(float) * ((size_t)2 * H3 * HLD + (size_t)HEAD_WARPS * HEAD_R * 2 * H3);
+constexpr size_t HEAD_SMEM_BIG = sizeof(float) * ((size_t)2 * H3 * HLD + (size_t)16 * 4 * 2 * H3), HEAD_SMEM_SMALL = sizeof(float) * ((size_t)2 * H3 * HLD + (size_t)8 * 1 * 2 * H3);
 
 constexpr size_t TMA_SMEM_128 = 3 * (2 * 16384 + 2 * 128 * 128) + 1024, TMA_SMEM_64 = 4 * (2 * 16384 + 2 * 64 * 128) + 1024;   // stage ring + alignment slack
 
@@ -947,7 +949,8 @@ static int set_kernel_attributes() {
     int dev = 0; cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
         RO_CUDA(cudaFuncSetAttribute(gemm_splitk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_4));
-        RO_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM));
+        RO_CUDA(cudaFuncSetAttribute(head_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM_BIG));
+        RO_CUDA(cudaFuncSetAttribute(head_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM_SMALL));
         RO_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_128));
         RO_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_64));
         RO_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM_128));
@@ -1036,8 +1039,9 @@ extern "C" int qc_policy_forward(qc_policy* p, const float* obs, int64_t B, int3
     const bool n31 = any_noise && p->noisy_layers >= 2, n41 = any_noise && p->noisy_layers >= 1;
     const bool tma = p->gemm_kind == 0 || p->gemm_kind == 3, raw = p->gemm_kind == 3;
     auto launch_fc1 = [&](float* h, float* hh, float* hl) {
-        if (p->n_in <= 8) fc1_small_kernel<8><<<blocks_for(B, FC1S_ROWS), 512, 0, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], h, hh, hl, B, p->n_in, H1);
-        else if (p->n_in <= 24) fc1_small_kernel<24><<<blocks_for(B, FC1S_ROWS), 512, 0, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], h, hh, hl, B, p->n_in, H1);
+        const int rpc = B >= (int64_t)4 * 148 * FC1S_ROWS ? FC1S_ROWS : (B >= (int64_t)2 * 148 * 8 ? 8 : 4);        // small batches: enough CTAs to cover the SMs
+        if (p->n_in <= 8) fc1_small_kernel<8><<<blocks_for(B, rpc), 512, 0, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], h, hh, hl, B, p->n_in, H1, rpc);
+        else if (p->n_in <= 24) fc1_small_kernel<24><<<blocks_for(B, rpc), 512, 0, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], h, hh, hl, B, p->n_in, H1, rpc);
         else fc1_kernel<<<blocks_for(B, FC1_ROWS), 512, sizeof(float) * FC1_ROWS * p->n_in, st>>>(obs, p->param[QC_P_FC1_W], p->param[QC_P_FC1_B], h, hh, hl, B, p->n_in, H1);
     };
     if (tma) {
@@ -1096,8 +1100,11 @@ extern "C" int qc_policy_forward(qc_policy* p, const float* obs, int64_t B, int3
         h.y1 = p->a3; h.y2 = p->a3 + (size_t)B * H3; h.ub31 = p->param[QC_P_FC31_UB]; h.sb31 = p->param[QC_P_FC31_SB];
         h.U = p->param[QC_P_FC41_UW]; h.S = p->param[QC_P_FC41_SW]; h.ub = p->param[QC_P_FC41_UB]; h.sb = p->param[QC_P_FC41_SB];
         h.nz = nz; h.ldn = NW; h.A = p->n_actions; h.noisy31 = n31 ? 1 : 0; h.noisy41 = n41 ? 1 : 0; h.q = q; h.greedy = greedy; h.B = B;
-        const unsigned nb = (unsigned)std::min<int64_t>((B + HEAD_WARPS * HEAD_R - 1) / (HEAD_WARPS * HEAD_R), 148);        // 199 KB of shared memory: one CTA per SM
-        head_kernel<<<nb, HEAD_WARPS * 32, HEAD_SMEM, st>>>(h);
+        if (B >= (int64_t)2 * 148 * 64) {                  // 199 KB of shared memory: one CTA of 16 warps per SM, four rows per warp and pass
+            head_kernel<4, 16><<<(unsigned)std::min<int64_t>((B + 63) / 64, 148), 16 * 32, HEAD_SMEM_BIG, st>>>(h);
+        } else {
+            head_kernel<1, 8><<<(unsigned)std::min<int64_t>((B + 7) / 8, 148 * 2), 8 * 32, HEAD_SMEM_SMALL, st>>>(h);
+        }
         p->launches++;
     }
     if (value && tma) {
