@@ -38,14 +38,14 @@ __device__ __forceinline__ void cluster_rendezvous(bool remote) {
 }
 
 template <int L, int GSL, int C> struct ClusterGeo {
-    static constexpr int NW = GSL / 32, GU = 5, GS = 1, BA = 4;
+    static constexpr int NW = GSL / 32, GU = 5, GS = 5, HG = 4, BA = 4;       // HG: ghost columns either side (see sse_cluster_kernel)
     static constexpr int GpU = GSL + 2 * GU, GpS = GSL + 2 * GS, LBU = L * GpU, LBS = L * GpS;
     static constexpr int THREADS = GSL + 32;                     // explicit lanes + one solver warp
     static constexpr int NWT = THREADS / 32;
     // factor rows {l_1..l_4, 1/d} of the slice AND of the 5 columns either side of it (warm-up rows of the substitutions), zero outside the grid
     static constexpr int GT = GSL + 2 * GU, CS = BA + 1;
     static constexpr size_t tab_bytes = (size_t)CS * L * GT * 16;
-    static constexpr size_t fixed_bytes = tab_bytes + (size_t)(LBU + 2 * LBS) * 16 + (size_t)2 * C * QC_MAXRED * 8 /* cluster partials */ + (size_t)NWT * QC_MAXRED * 8 /* warp partials */ + 256;
+    static constexpr size_t fixed_bytes = tab_bytes + (size_t)(LBU + 2 * LBS) * 16 + (size_t)2 * C * QC_MAXRED * 8 /* cluster partials */ + (size_t)NWT * QC_MAXRED * 8 /* warp partials */ + 256 + (size_t)2 * GU * L * 16 /* psi halo */;
     static size_t smem_bytes(int n_sub) { return fixed_bytes + (size_t)n_sub * 16; }
 };
 
@@ -102,8 +102,16 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
     const int tid = threadIdx.x, lane = tid & 31, n = p.n, n_sub = p.n_sub;
     const int rank = (int)cluster.block_rank();
     const int traj = blockIdx.x / C;                              // one cluster per trajectory
-    const bool is_solver = tid >= GSL;
-    const int g = tid;                                            // lane inside the slice (explicit threads)
+    const bool is_solver = tid >= GSL;                            // the spare warp (named after its round-2 role; the substitution now runs on explicit warps)
+    // Ghost lanes: 2*HG lanes of the spare warp recompute the Horner chain on the HG columns either side of the slice (24 points: the chain
+    // of five 9-point sweeps reaches 20), so that the sweeps need no halo exchange between CTAs at all -- a CTA barrier each instead of
+    // store-to-neighbour + cluster barrier (1850 cycles per sweep, of which ~450 were arithmetic).  A ghost column's outer rows go stale by 4
+    // points per sweep, exactly as fast as the region that is still needed shrinks.  Ghost lanes never contribute to sums or to the state.
+    constexpr int HG = Geo::HG;
+    const int gq = tid - GSL;
+    const bool ghost = is_solver && gq < 2 * HG;
+    const bool works = !is_solver || ghost;                       // does the explicit arithmetic
+    const int g = !is_solver ? tid : (ghost ? (gq < HG ? gq - HG : GSL + gq - HG) : 0);      // column inside the slice ([-HG, 0) and [GSL, GSL+HG): ghosts)
     const int col_base = rank * GSL;                              // first global column of this CTA
 
     double2* tab = reinterpret_cast<double2*>(smem);              // [L][CS][GT]
@@ -114,7 +122,9 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
     double* wred = cred + 2 * C * QC_MAXRED;                      // [NWT][QC_MAXRED]
     double* scal = wred + NWT * QC_MAXRED;                        // misc
     int* iflag = reinterpret_cast<int*>(scal + 8);
-    double* nz = scal + 32;                                       // [n_sub][2]
+    double2* PH = reinterpret_cast<double2*>(scal + 32);          // [2][GU][L]: the neighbours' edge columns of the state (left: columns -GU..-1, right: GSL..GSL+GU-1),
+                                                                  // pushed by them after every solve: the halo of psi without a remote load on the critical path
+    double* nz = reinterpret_cast<double*>(PH + 2 * GU * L);      // [n_sub][2]
     int phase = 0;
 #ifdef QC_DEBUG_HOOKS
     long long t_last = clock64(); const long long t_begin = t_last; unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -131,6 +141,7 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
 
     // ---- prologue -----------------------------------------------------------------------------------------------------------------
     for (int e = tid; e < LBU + 2 * LBS; e += blockDim.x) U[e] = mk2(0.0, 0.0);
+    for (int e = tid; e < 2 * GU * L; e += blockDim.x) PH[e] = mk2(0.0, 0.0);
     for (int s = tid; s < my_nsub; s += blockDim.x) {
         double r0, r1;
         if (p.noise) { r0 = p.noise[((size_t)traj * n_sub + s) * 2]; r1 = p.noise[((size_t)traj * n_sub + s) * 2 + 1]; }
@@ -146,15 +157,29 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
     }
     cluster.sync();                                               // every CTA's lines are zero before anybody stores a halo into them
 
+    // my GU edge columns of the state -> the neighbours' halo buffers (own lanes g < GU and g >= GSL - GU, values just read from / written to U)
+    auto push_state = [&](const double2 (&val)[L]) {
+        if (g < GU && rank > 0) {
+            double2* nb = cluster.map_shared_rank(PH, rank - 1) + (GU + g) * L;
+#pragma unroll
+            for (int j = 0; j < L; j++) nb[j] = val[j];
+        }
+        if (g >= GSL - GU && rank + 1 < C) {
+            double2* nb = cluster.map_shared_rank(PH, rank + 1) + (g - (GSL - GU)) * L;
+#pragma unroll
+            for (int j = 0; j < L; j++) nb[j] = val[j];
+        }
+    };
     LaneOps<QC_QUARTIC, L> ops;
     double xs[L];
-    bool valid[L];
+    bool valid[L], gvalid[L];                                     // own point inside the grid / own or ghost point inside the grid
 #pragma unroll
     for (int j = 0; j < L; j++) {
         const int i = (col_base + g) * L + j;
+        gvalid[j] = works && i >= 0 && i < n;
         valid[j] = !is_solver && i < n;
-        xs[j] = valid[j] ? __ldg(&p.x[i]) : 0.0;
-        ops.dg[j] = valid[j] ? (__ldg(&p.hdiag[i]) - p.kappa * F * xs[j]) : 0.0;
+        xs[j] = gvalid[j] ? __ldg(&p.x[i]) : 0.0;
+        ops.dg[j] = gvalid[j] ? (__ldg(&p.hdiag[i]) - p.kappa * F * xs[j]) : 0.0;
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) ops.tk[k] = p.tk[k];
@@ -174,6 +199,7 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
         if (!is_solver) {
 #pragma unroll
             for (int j = 0; j < L; j++) U[j * GpU + GU + g] = own[j];
+            push_state(own);
         }
         cluster_reduce<2, C, NWT>(cluster, v, wred, cred, phase, rank);
         xbar = p.w * v[0];
@@ -188,29 +214,30 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
     // solver warp with 32 chunks of GSL/32 columns (66 recurrence rows per sweep at N = 4097: 16.7 k of the 31.5 k cycles of a substep), the
     // first NSV warps of the CTA solve, thread t the chunk of SM = 3 columns [3 t - 1, 3 t + 2) (odd stride: conflict-free 16-byte loads of
     // the state line and of the factor rows; 18 + W rows per sweep).  Columns -1 and >= GSL belong to the neighbours: computed as warm-up only.
-    constexpr int SM = 3, NCHK = (GSL + 1 + SM - 1) / SM, NSV = (NCHK + 31) / 32, NSVT = NSV * 32;
-    static_assert(NSVT <= GSL, "solver threads must be explicit threads");
+#ifndef QC_CLUSTER_SM
+#define QC_CLUSTER_SM 3
+#endif
+    constexpr int SM = QC_CLUSTER_SM, NCHK = (GSL + 1 + SM - 1) / SM, NSV = (NCHK + 31) / 32, NSVT = NSV * 32;
+    static_assert(NSVT <= Geo::THREADS && (SM & 1) == 1, "solver threads: whole warps of the CTA; odd column stride");
     const int wb = p.W / L;
 
-    // psi / solution on relative point r of lane g (r in [-4, L+4)): the first and the last lane of a slice read their outer halo straight
-    // from the neighbour CTA's state line (ld.shared::cluster).  Safe without an extra barrier: a state line is only rewritten (right-hand
-    // side) after six more cluster barriers of the same substep.
+    // psi / solution on relative point r of lane g (r in [-4, L+4)): columns outside the slice come from the halo buffer PH, which the
+    // neighbours fill (push_state below) between their backward sweep and the cluster barrier of the norm reduction.
     auto ld_state = [&](int r) -> double2 {
         const int q = (r >= 0) ? r / L : -((-r + L - 1) / L);
         const int rr = r - q * L, col = g + q;
-        if (col < 0) return rank > 0 ? cluster.map_shared_rank(U, rank - 1)[rr * GpU + GU + GSL - 1] : mk2(0.0, 0.0);
-        if (col >= GSL) return rank + 1 < C ? cluster.map_shared_rank(U, rank + 1)[rr * GpU + GU] : mk2(0.0, 0.0);
+        if (col < 0) return PH[(col + GU) * L + rr];               // (zero at the ends of the grid: never written there)
+        if (col >= GSL) return PH[(GU + col - GSL) * L + rr];
         return U[rr * GpU + GU + col];
     };
-    // one Horner sweep (all threads: the solver warp only takes part in the barrier)
+    // one Horner sweep, local to the CTA (own and ghost lanes; the rest of the spare warp only takes part in the barrier)
     auto sweep = [&](double2* buf, const double2 (&w)[L], double2 (&hw)[L]) {
-        if (!is_solver) {
+        if (works) {
 #pragma unroll
             for (int j = 0; j < L; j++) buf[j * GpS + GS + g] = w[j];
-            push_halo<L>(cluster, buf, GpS, GS, GSL, 1, g, rank, C, w);
         }
-        cluster_rendezvous(!is_solver && (g < 1 || g >= GSL - 1));
-        if (!is_solver) {
+        __syncthreads();
+        if (works) {
             double2 ext[L + 8];
 #pragma unroll
             for (int r = -4; r < L + 4; r++) ext[r + 4] = (r >= 0 && r < L) ? w[r] : ld_rel_g<L, GS>(buf, g, GpS, r);
@@ -231,7 +258,7 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
         }
         double2 psi[L], a[L], acc[L], v1[L], w[L], hw[L];
         double m[4] = {0.0, 0.0, 0.0, 0.0};
-        if (!is_solver) {
+        if (works) {
             double2 ext[L + 8];
 #pragma unroll
             for (int r = -4; r < L + 4; r++) { const double2 c = ld_state(r); ext[r + 4] = mk2(sc * c.x, sc * c.y); }
@@ -242,7 +269,7 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
                 const double2 h = ops.h0(ext, j);
                 const double x = xs[j], x2 = x * x;
                 const double d2g = fma(Q1, x, fma(g4, x2, Q0)), gsd = fma(gs, x, G0);
-                a[j] = valid[j] ? mk2(fma(-d2g, psi[j].x, h.y), fma(-d2g, psi[j].y, -h.x)) : mk2(0.0, 0.0);      // D1 (Q:434-449)
+                a[j] = gvalid[j] ? mk2(fma(-d2g, psi[j].x, h.y), fma(-d2g, psi[j].y, -h.x)) : mk2(0.0, 0.0);      // D1 (Q:434-449)
                 const double bx_ = gsd * psi[j].x, by_ = gsd * psi[j].y;                                       // D2 (Q:473-486)
                 const double ux = fma(dt, a[j].x, psi[j].x), uy = fma(dt, a[j].y, psi[j].y);
                 const double ypx = fma(sdt, bx_, ux), ypy = fma(sdt, by_, uy), ymx = fma(-sdt, bx_, ux), ymy = fma(-sdt, by_, uy);
@@ -250,11 +277,12 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
                 const double xp2 = x * p2;
                 m[0] += xp2; m[1] = fma(x, xp2, m[1]); m[2] = fma(x2, xp2, m[2]); m[3] = fma(x, m2, m[3]);
             }
+            if (ghost) { m[0] = 0.0; m[1] = 0.0; m[2] = 0.0; m[3] = 0.0; }      // ghost columns belong to the neighbour's sums
         }
         QC_CT(0);
         cluster_reduce<4, C, NWT>(cluster, m, wred, cred, phase, rank);
         QC_CT(1);
-        if (!is_solver) {
+        if (works) {
             const double xbp = p.w * m[0], xbm = p.w * m[3];       // un-normalised <x> of Y+-, Phi+- (Q:457-460, 605-615, 479-482)
             const double t1 = m[1] - xbp * m[0], t2 = m[2] - 2.0 * xbp * m[1] + xbp * xbp * m[0];
             const double xfp = p.w * (m[0] + 2.0 * sig * t1 + sig * sig * t2), xfm = p.w * (m[0] - 2.0 * sig * t1 + sig * sig * t2);
@@ -281,24 +309,24 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
             for (int j = 0; j < L; j++) w[j] = mk2(-e5 * a[j].y, e5 * a[j].x);
         }
         sweep(S0, w, hw);
-        if (!is_solver) {
+        if (works) {
 #pragma unroll
-            for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(-e4, a[j].x, hw[j].x), fma(-e4, a[j].y, hw[j].y)) : mk2(0.0, 0.0);
+            for (int j = 0; j < L; j++) w[j] = gvalid[j] ? mk2(fma(-e4, a[j].x, hw[j].x), fma(-e4, a[j].y, hw[j].y)) : mk2(0.0, 0.0);
         }
         sweep(S1, w, hw);
-        if (!is_solver) {
+        if (works) {
 #pragma unroll
-            for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(e3, a[j].y, hw[j].x), fma(-e3, a[j].x, hw[j].y)) : mk2(0.0, 0.0);
+            for (int j = 0; j < L; j++) w[j] = gvalid[j] ? mk2(fma(e3, a[j].y, hw[j].x), fma(-e3, a[j].x, hw[j].y)) : mk2(0.0, 0.0);
         }
         sweep(S0, w, hw);
-        if (!is_solver) {
+        if (works) {
 #pragma unroll
-            for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(fma(e2, a[j].x, hw[j].x), fma(e2, a[j].y, hw[j].y)) : mk2(0.0, 0.0);
+            for (int j = 0; j < L; j++) w[j] = gvalid[j] ? mk2(fma(e2, a[j].x, hw[j].x), fma(e2, a[j].y, hw[j].y)) : mk2(0.0, 0.0);
         }
         sweep(S1, w, hw);
-        if (!is_solver) {
+        if (works) {
 #pragma unroll
-            for (int j = 0; j < L; j++) w[j] = valid[j] ? mk2(v1[j].x + hw[j].x, v1[j].y + hw[j].y) : mk2(0.0, 0.0);
+            for (int j = 0; j < L; j++) w[j] = gvalid[j] ? mk2(v1[j].x + hw[j].x, v1[j].y + hw[j].y) : mk2(0.0, 0.0);
         }
         sweep(S0, w, hw);
         QC_CT(2);
@@ -416,9 +444,13 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
         __syncthreads();
         if (!is_solver) {
             const bool do_cen = p.cen_hi > p.cen_lo;
+            double2 xown[L];
+#pragma unroll
+            for (int j = 0; j < L; j++) xown[j] = U[j * GpU + GU + g];
+            push_state(xown);
 #pragma unroll
             for (int j = 0; j < L; j++) {
-                const double2 c = U[j * GpU + GU + g];
+                const double2 c = xown[j];
                 const double a2 = c.x * c.x + c.y * c.y;
                 const int i = (col_base + g) * L + j;
                 part[0] += a2;
