@@ -32,6 +32,9 @@ struct PipeTimers { __device__ void start() {} __device__ __forceinline__ void t
 #ifndef QC_PIPE_PF
 #define QC_PIPE_PF 1          // rows the solver's loads run ahead of its arithmetic
 #endif
+#ifndef QC_PIPE_PF_TABG
+#define QC_PIPE_PF_TABG 1     // the same for instances whose factor table stays in global memory
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
@@ -85,7 +88,16 @@ template <int VAR, int L, int GC, int NE, bool TABG = false, int NSW = 1> struct
     //  harmonic oscillator: 5.63 instead of 4.17 ms -- the exclusive solver scheduler matters more than the shorter recurrence.)
     static_assert(NSW == 1 || GC == 32, "several solver warps per set: one-warp groups only");
     static constexpr int NXW = NE * NWG;                            // explicit warps
-    static constexpr int LASTW = SOLO ? (NXW - 1) + (NXW - 1) / 3 : NXW + 2 * NSW - 1;     // highest warp id in use
+    // Single-group CTAs (NE = 1: wide grids, one trajectory per set): the explicit group idles half the time because BOTH solver warps share
+    // sub-partition 3, whose issue slots they saturate (137-176 cycles per recurrence row, explicit warps waiting 50-58 % of a substep at
+    // N = 1025 / 2049).  There the two solver warps go to different sub-partitions instead (warp ids 3 and 6), each next to explicit warps
+    // that have time to spare.  QC_PIPE_SPLIT=0 restores ids 3 / 7.
+#ifndef QC_PIPE_SPLIT
+#define QC_PIPE_SPLIT 1
+#endif
+    static constexpr bool SPLIT = SOLO && NE == 1 && QC_PIPE_SPLIT;
+    static constexpr int LASTW_SPLIT = (NXW - 1) + (NXW - 1 >= 3 ? 1 : 0) + (NXW - 1 >= 5 ? 1 : 0);
+    static constexpr int LASTW = SPLIT ? (LASTW_SPLIT > 6 ? LASTW_SPLIT : 6) : (SOLO ? (NXW - 1) + (NXW - 1) / 3 : NXW + 2 * NSW - 1);     // highest warp id in use
 static constexpr int WARPS = ((LASTW > 7 || !SOLO ? LASTW : 7) + 4) / 4 * 4;   // whole warp quads: the register file is per SM sub-partition, so a partial quad buys no registers (ptxas: 320 threads -> 168, not 200)
     static constexpr int THREADS = WARPS * 32;
     static constexpr size_t tab_bytes = TABG ? 0 : (size_t)CS * L * G * 16 + (size_t)HT * L * G * 8;
@@ -119,7 +131,9 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
         if constexpr (!TABG) return tab[(j * CS + k) * G + min(max(col, 0), G - 1)];
         else { const int i = col * L + j; return (i >= 0 && i < npts) ? __ldg(&tab[(size_t)i * (BA + 1) + k]) : mk2(0.0, 0.0); }
     };
-    constexpr int PF = (L % (QC_PIPE_PF + 1) == 0) ? QC_PIPE_PF : 2, NR = PF + 1;      // the row ring restarts with every column: L must be a multiple of NR
+    // (factor rows from global memory, TABG: L2 latency instead of shared-memory latency per row -> a deeper ring)
+    constexpr int PFW = TABG ? QC_PIPE_PF_TABG : QC_PIPE_PF;
+    constexpr int PF = (L % (PFW + 1) == 0) ? PFW : 2, NR = PF + 1;      // the row ring restarts with every column: L must be a multiple of NR
     static_assert(L % NR == 0, "row ring: L must be a multiple of PF + 1");
     // ---- forward: L y = rhs in column (scatter) form, z = D^{-1} y --------------------------------------------------------------
     // As soon as y_i is final its contributions l_{i+k,k} y_i to the next BA rows are subtracted from their pending sums: the loop-carried
@@ -271,8 +285,8 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG, NSW>::THREADS, 1
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, n = p.n, n_sub = p.n_sub;
     const int warp = tid >> 5, lane = tid & 31;
-    const bool is_solver = Geo::SOLO ? (warp & 3) == 3 : (warp >= Geo::NXW && warp < Geo::NXW + 2 * NSW);
-    const int xw = Geo::SOLO ? warp - (warp >> 2) : warp;           // explicit warp number
+    const bool is_solver = Geo::SPLIT ? (warp == 3 || warp == 6) : (Geo::SOLO ? (warp & 3) == 3 : (warp >= Geo::NXW && warp < Geo::NXW + 2 * NSW));
+    const int xw = Geo::SPLIT ? warp - (warp > 3 ? 1 : 0) - (warp > 6 ? 1 : 0) : (Geo::SOLO ? warp - (warp >> 2) : warp);           // explicit warp number
     const bool is_idle = !is_solver && xw >= Geo::NXW;
     const int e = (is_solver || is_idle) ? 0 : xw / NWG;            // explicit group
     const int wq = (is_solver || is_idle) ? 0 : xw % NWG, g = wq * 32 + lane;   // warp / lane inside the group
@@ -351,7 +365,7 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG, NSW>::THREADS, 1
     PipeTimers tm; tm.start();
     if (!cta_empty && is_solver) {
         // ================= solver warpgroup: warp X of it serves set X ==================================================================
-        const int X = Geo::SOLO ? warp >> 2 : (warp - Geo::NXW) / NSW;
+        const int X = Geo::SPLIT ? (warp == 6 ? 1 : 0) : (Geo::SOLO ? warp >> 2 : (warp - Geo::NXW) / NSW);
         const int sub = Geo::SOLO ? 0 : (warp - Geo::NXW) % NSW;           // which NES trajectories of the set
         if (X < 2) {
             const int cols = (n + L - 1) / L;
