@@ -109,14 +109,14 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
     // register-resident chunk-Jacobi kernel (0.55 vs 0.73 ms at 1024 and 3.7 vs 3.9 ms at 8192 trajectories of config 2).
     if (n_sub > 0 && env_int("QCART_PIPE", 1) && !forceL && env_int("QCART_BIN", -1) != 0) {
         const int L = env_int("QCART_PIPE_L", (var == QC_QUARTIC) ? 6 : 3), cols = (n + L - 1) / L, G = (cols + 31) / 32 * 32, W = (W_needed + L - 1) / L * L;
-        const int want_ne = env_int("QCART_PIPE_NE", (var == QC_HARMONIC) ? 24 /* NE = 8, two solver warps per set */ : ((var == QC_INV_HARMONIC) ? 4 : (G >= 128 ? 1 : 0)));
+        const int want_ne = env_int("QCART_PIPE_NE", (var == QC_HARMONIC) ? 24 /* NE = 8, two solver warps per set */ : ((var == QC_INV_HARMONIC) ? 4 : (G >= 288 ? 17 /* NE = 1, two solver warps per trajectory */ : (G >= 128 ? 1 : 0))));
         const PipeEntry* pe = qc_find_pipe(var, L, G, want_ne);
         const int GUc = (G == 32) ? 10 : ((var == QC_QUARTIC) ? 5 : 12);
         if (pe && W <= (GUc - 1) * L && (int)pe->smem(n_sub) <= smem_max) {
             const int ne = pe->ne & 15, nsw = (pe->ne >> 4) + 1;           // instance id: NE + 16 (NSW - 1), see qc_pipe_impl.cuh
-            const int TT = 2 * ne, cpt = 32 / (ne / nsw), GU = GUc;
+            const int TT = 2 * ne, cpt = (ne == 1) ? 32 * nsw : 32 / (ne / nsw), GU = GUc;       // ne == 1: the nsw solver warps split the chunks of one trajectory
             int mult = (cols + cpt - 1) / cpt;
-            if (nsw == 1) mult |= 1; else mult = (mult + 1) & ~1;
+            if (nsw == 1 || ne == 1) mult |= 1; else mult = (mult + 1) & ~1;
             const int c_last = (cols - 1) / mult;
             // Binning pads every force level to whole CTAs.  Large batches: the padding is noise.  Small batches: only when even the worst
             // case (every bin one trajectory past a CTA) still fits one wave of CTAs, so that no SM ever runs a second, nearly empty round.

@@ -61,7 +61,9 @@ template <int L, int GD> __device__ __forceinline__ double2 ld_rel_g(const doubl
 // NSW: solver warps per set (one-warp groups only).  Each serves NES = NE / NSW trajectories with 32 / NES chunks per trajectory: shorter
 // chunks, i.e. a shorter serial recurrence per solve (the latency that bounds one-warp grid trajectories, config 2).
 template <int VAR, int L, int GC, int NE, bool TABG = false, int NSW = 1> struct PipeGeo {
-    static constexpr int G = GC, NWG = GC / 32, TT = 2 * NE, NES = NE / NSW, CPT = 32 / NES;
+    // CSW: solver warps that share ONE trajectory (single-group CTAs, NE = 1, with NSW > 1): warp `sub` takes chunks [32 sub, 32 sub + 32)
+    static constexpr int CSW = (NE == 1) ? NSW : 1;
+    static constexpr int G = GC, NWG = GC / 32, TT = 2 * NE, NES = (NE == 1) ? 1 : NE / NSW, CPT = 32 * CSW / NES;
     static constexpr int BA = VarTraits<VAR>::BA;
     // sweep lines per explicit group: two alternate in the Horner chain (the Fock systems first use them for Y+ / Y-); the inverted harmonic
     // oscillator needs a third one for the left halo of a (HERMITIAN-descriptor term).  Their guard: the widest halo in columns.
@@ -76,7 +78,7 @@ template <int VAR, int L, int GC, int NE, bool TABG = false, int NSW = 1> struct
     // stride between the state lines of a set: = 8/NE (mod 8) in 16-byte units, so that the NE x 2 lanes of a quarter warp of the solver hit
     // distinct bank groups (chunk stride `mult` is odd)
     // (NSW > 1: the chunk stride is even instead, and the line stride odd)
-    static constexpr int LBU = LBU0 + (((NSW > 1) ? 1 : (8 / NE)) - (LBU0 % 8) + 8) % 8;
+    static constexpr int LBU = LBU0 + (((NSW > 1 && NE > 1) ? 1 : (8 / NE)) - (LBU0 % 8) + 8) % 8;
     static constexpr int LBS = L * GpS;
     static constexpr int CS = (VAR == QC_QUARTIC) ? BA + 1 : BA + 2;    // factor row: l_1..l_BA, 1/d, (Fock) xl
     // Warp roles follow the SM sub-partition a warp runs on (warp id mod 4): ids with (id & 3) == 3 are the solver warps (3: set A, 7: set B;
@@ -86,7 +88,7 @@ template <int VAR, int L, int GC, int NE, bool TABG = false, int NSW = 1> struct
     static constexpr bool SOLO = NWG > 1;
     // (NSW > 1 with multi-warp groups, i.e. four solver warps that share the schedulers with the explicit warps, was measured on the inverted
     //  harmonic oscillator: 5.63 instead of 4.17 ms -- the exclusive solver scheduler matters more than the shorter recurrence.)
-    static_assert(NSW == 1 || GC == 32, "several solver warps per set: one-warp groups only");
+    static_assert(NSW == 1 || GC == 32 || NE == 1, "several solver warps per set: one-warp groups, or single-group CTAs (chunks of one trajectory split over the warps)");
     static constexpr int NXW = NE * NWG;                            // explicit warps
     // Single-group CTAs (NE = 1: wide grids, one trajectory per set): the explicit group idles half the time because BOTH solver warps share
     // sub-partition 3, whose issue slots they saturate (137-176 cycles per recurrence row, explicit warps waiting 50-58 % of a substep at
@@ -97,7 +99,11 @@ template <int VAR, int L, int GC, int NE, bool TABG = false, int NSW = 1> struct
 #endif
     static constexpr bool SPLIT = SOLO && NE == 1 && QC_PIPE_SPLIT;
     static constexpr int LASTW_SPLIT = (NXW - 1) + (NXW - 1 >= 3 ? 1 : 0) + (NXW - 1 >= 5 ? 1 : 0);
-    static constexpr int LASTW = SPLIT ? (LASTW_SPLIT > 6 ? LASTW_SPLIT : 6) : (SOLO ? (NXW - 1) + (NXW - 1) / 3 : NXW + 2 * NSW - 1);     // highest warp id in use
+    // (with CSW = 2 the second solver warp of set A / B is the second / first warp id after the explicit ones)
+    static constexpr int XLAST = (LASTW_SPLIT > 6 ? LASTW_SPLIT : 6);                        // last id taken by explicit warps and the solver ids 3, 6
+    static constexpr int LASTW = SPLIT ? XLAST + 2 * (CSW - 1) : (SOLO ? (NXW - 1) + (NXW - 1) / 3 : NXW + 2 * NSW - 1);     // highest warp id in use
+    static_assert(CSW == 1 || SPLIT, "chunk-split solver warps need the single-group layout");
+    static_assert(CSW <= 2, "at most two solver warps per trajectory");
 static constexpr int WARPS = ((LASTW > 7 || !SOLO ? LASTW : 7) + 4) / 4 * 4;   // whole warp quads: the register file is per SM sub-partition, so a partial quad buys no registers (ptxas: 320 threads -> 168, not 200)
     static constexpr int THREADS = WARPS * 32;
     static constexpr size_t tab_bytes = TABG ? 0 : (size_t)CS * L * G * 16 + (size_t)HT * L * G * 8;
@@ -113,10 +119,12 @@ static constexpr int WARPS = ((LASTW > 7 || !SOLO ? LASTW : 7) + 4) / 4 * 4;   /
 // (which belongs to the neighbour chunk) before any lane writes, the warp runs converged and __syncwarp separates the two parts.
 template <class Geo, int VAR, int L, bool TABG>
 __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restrict__ Uset, const double2* __restrict__ tab, double* scal_set, int mult, int wb,
-                                           int lane, int s, PipeTimers& tm) {
+                                           int lane, int s, PipeTimers& tm, int sub = 0, int pair_bar = 0) {
     constexpr int NE = Geo::NES;                               // trajectories served by this warp
-    constexpr int BA = Geo::BA, CS = Geo::CS, G = Geo::G, Gp = Geo::GpU, GUARD = Geo::GU;
-    const int tt = lane % NE, cc = lane / NE;
+    constexpr int BA = Geo::BA, CS = Geo::CS, G = Geo::G, Gp = Geo::GpU, GUARD = Geo::GU, CSW = Geo::CSW;
+    const int tt = lane % NE, cc = lane / NE + sub * (32 / NE);
+    // ordering point between the solver lanes of a trajectory: the warp, or (CSW = 2) the pair of warps on a named barrier
+    auto solver_sync = [&]() { if constexpr (CSW == 1) __syncwarp(); else asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
     double2* __restrict__ U = Uset + (size_t)tt * Geo::LBU;
     double* scal = scal_set + tt * 16;
     int* iflag = reinterpret_cast<int*>(scal + 8);
@@ -176,10 +184,10 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
             }
         };
         if (act) { for (int b = 0; b < wb; b++, col++) fwd_col(false); }
-        __syncwarp();
+        solver_sync();
         if (act) { for (int b = 0; b < mult; b++, col++) fwd_col(true); }
     }
-    __syncwarp();
+    solver_sync();
     tm.tick(1);
     // ---- backward: L^T x = z (column oriented) -------------------------------------------------------------
     {
@@ -231,7 +239,7 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
             }
         };
         if (act) { for (int b = 0; b < wb; b++, col--) bwd_col(false); }
-        __syncwarp();
+        solver_sync();
         if (act) { for (int b = 0; b < mult; b++, col--) bwd_col(true); }
     }
     tm.tick(2);
@@ -240,7 +248,12 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
     for (int o = NE; o < 32; o <<= 1) {
         nrm += __shfl_xor_sync(0xffffffffu, nrm, o); sx += __shfl_xor_sync(0xffffffffu, sx, o); cen += __shfl_xor_sync(0xffffffffu, cen, o);
     }
-    __syncwarp();
+    if constexpr (CSW > 1) {
+        // two warps per trajectory: partial sums through the scratch slots of the trajectory's scalar block, added in a fixed order
+        if (lane == 0) { scal[2 + 3 * sub] = nrm; scal[3 + 3 * sub] = sx; scal[4 + 3 * sub] = cen; }
+        solver_sync();
+        nrm = scal[2] + scal[5]; sx = scal[3] + scal[6]; cen = scal[4] + scal[7];
+    } else __syncwarp();
     if (cc == 0 && s < iflag[1]) {
         const double sc = rsqrt(nrm * p.w);                    // normalize(): psi / (||psi||_2 sqrt(w))   (Q:259-263)
         const double s2 = sc * sc;
@@ -285,7 +298,8 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG, NSW>::THREADS, 1
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, n = p.n, n_sub = p.n_sub;
     const int warp = tid >> 5, lane = tid & 31;
-    const bool is_solver = Geo::SPLIT ? (warp == 3 || warp == 6) : (Geo::SOLO ? (warp & 3) == 3 : (warp >= Geo::NXW && warp < Geo::NXW + 2 * NSW));
+    const bool is_solver = Geo::SPLIT ? (warp == 3 || warp == 6 || (warp > Geo::XLAST && warp <= Geo::XLAST + 2 * (Geo::CSW - 1)))
+                                      : (Geo::SOLO ? (warp & 3) == 3 : (warp >= Geo::NXW && warp < Geo::NXW + 2 * NSW));
     const int xw = Geo::SPLIT ? warp - (warp > 3 ? 1 : 0) - (warp > 6 ? 1 : 0) : (Geo::SOLO ? warp - (warp >> 2) : warp);           // explicit warp number
     const bool is_idle = !is_solver && xw >= Geo::NXW;
     const int e = (is_solver || is_idle) ? 0 : xw / NWG;            // explicit group
@@ -312,7 +326,7 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG, NSW>::THREADS, 1
         int sl = 0;
         for (int q = 0; q < TT; q++) { const int ps = blockIdx.x * TT + q; if (ps < npos && p.order[ps] >= 0) { sl = min(max(p.slot[p.order[ps]], 0), p.n_slots - 1); break; } }
         cta_slot = sl;
-        mbar_init(&bars[0], NE * G); mbar_init(&bars[1], NE * G); mbar_init(&bars[2], 32 * NSW); mbar_init(&bars[3], 32 * NSW);
+        mbar_init(&bars[0], NE * G); mbar_init(&bars[1], NE * G); mbar_init(&bars[2], 32 * NSW); mbar_init(&bars[3], 32 * NSW);      // (NSW solver warps arrive per set, whichever way they share the work)
     }
     __syncthreads();
     if constexpr (!TABG) {
@@ -365,18 +379,20 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG, NSW>::THREADS, 1
     PipeTimers tm; tm.start();
     if (!cta_empty && is_solver) {
         // ================= solver warpgroup: warp X of it serves set X ==================================================================
-        const int X = Geo::SPLIT ? (warp == 6 ? 1 : 0) : (Geo::SOLO ? warp >> 2 : (warp - Geo::NXW) / NSW);
-        const int sub = Geo::SOLO ? 0 : (warp - Geo::NXW) % NSW;           // which NES trajectories of the set
+        // single-group layout: ids 3 / 6 = first solver warp of set A / B; ids XLAST + 2 / XLAST + 1 = their second warps (CSW = 2)
+        const int X = Geo::SPLIT ? ((warp == 6 || warp == Geo::XLAST + 1) ? 1 : 0) : (Geo::SOLO ? warp >> 2 : (warp - Geo::NXW) / NSW);
+        const int sub = Geo::SPLIT ? (warp > Geo::XLAST ? 1 : 0) : (Geo::SOLO ? 0 : (warp - Geo::NXW) % NSW);      // which trajectories (or, CSW = 2, which chunks) of the set
         if (X < 2) {
             const int cols = (n + L - 1) / L;
             int mult = (cols + Geo::CPT - 1) / Geo::CPT;
-            if (NSW == 1) mult |= 1; else mult = (mult + 1) & ~1;          // odd (NSW > 1: even) chunk stride: bank-conflict-free factor and state loads
+            if (NSW == 1 || NE == 1) mult |= 1; else mult = (mult + 1) & ~1;          // odd (several trajectories per solver warp: even) chunk stride: bank-conflict-free factor and state loads
             const int wb = p.W / L;
             for (int s = 0; s < n_sub; s++) {
                 mbar_wait(&bars[X], s & 1);
                 tm.tick(0);
-                pipe_solve<Geo, VAR, L, TABG>(p, Uall + (size_t)(X * NE + sub * Geo::NES) * LBU, TABG ? p.fac + (size_t)cta_slot * n * (BA + 1) : tab,
-                                              scal_all + (X * NE + sub * Geo::NES) * 16, mult, wb, lane, s, tm);
+                const int tsub = (Geo::CSW > 1) ? 0 : sub * Geo::NES;     // first trajectory of the set served by this warp
+                pipe_solve<Geo, VAR, L, TABG>(p, Uall + (size_t)(X * NE + tsub) * LBU, TABG ? p.fac + (size_t)cta_slot * n * (BA + 1) : tab,
+                                              scal_all + (X * NE + tsub) * 16, mult, wb, lane, s, tm, (Geo::CSW > 1) ? sub : 0, 8 + X);
                 mbar_arrive(&bars[2 + X]);
                 tm.tick(3);
             }
@@ -878,6 +894,7 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG, NSW>::THREADS, 1
 struct PipeEntry { int var, L, gc, ne, threads; kern_t fn; size_t (*smem)(int n_sub); };
 #define QC_PE_NSW(VAR, L, GC, NE, NSW) {VAR, L, GC, NE + 16 * (NSW - 1), PipeGeo<VAR, L, GC, NE, false, NSW>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, false, NSW>, PipeGeo<VAR, L, GC, NE, false, NSW>::smem_bytes}
 #define QC_PE(VAR, L, GC, NE) {VAR, L, GC, NE, PipeGeo<VAR, L, GC, NE>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, false>, PipeGeo<VAR, L, GC, NE>::smem_bytes}
+#define QC_PE_TABG_NSW(VAR, L, GC, NE, NSW) {VAR, L, GC, NE + 16 * (NSW - 1), PipeGeo<VAR, L, GC, NE, true, NSW>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, true, NSW>, PipeGeo<VAR, L, GC, NE, true, NSW>::smem_bytes}
 #define QC_PE_TABG(VAR, L, GC, NE) {VAR, L, GC, NE, PipeGeo<VAR, L, GC, NE, true>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, true>, PipeGeo<VAR, L, GC, NE, true>::smem_bytes}
 
 }  // namespace qc

@@ -593,7 +593,7 @@ def test_wide_grid_pipeline_matches_oracle(npts, B):
     sim.set_state(psi0)
     out = sim.step(torch.as_tensor(actions, device="cuda"), noise=torch.as_tensor(noise, device="cuda"))
     torch.cuda.synchronize()
-    assert "sse_pipe_kernel" in sim.kernel_info() and "NE=1" in sim.kernel_info(), sim.kernel_info()
+    assert "sse_pipe_kernel" in sim.kernel_info() and "NE=1,NSW=%d" % (2 if npts > 1700 else 1) in sim.kernel_info(), sim.kernel_info()
     pick = np.array([0, 1, B // 2, B - 1])
     orc = oracle_for(params)
     ref, fails, _ = oracle_control_step(orc, params, psi0[pick], actions[pick], noise[pick])
