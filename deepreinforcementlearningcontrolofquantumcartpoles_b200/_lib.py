@@ -61,6 +61,8 @@ SYMBOLS = [
     ("qc_simulate_10_steps1", C.c_int, [_vp, _dp, C.c_double, C.c_double, C.c_double, _dp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     ("qc_get_moments1", C.c_int, [_vp, _dp, _dp]),
     ("qc_x_expectation1", C.c_int, [_vp, _dp, C.POINTER(C.c_double)]),
+    ("qc_hamiltonian_dot_psi1", C.c_int, [_vp, _dp]),
+    ("qc_solve_ab1", C.c_int, [_vp, _dp, C.c_double]),
     ("qc_philox_normals", None, [C.c_uint64, C.c_uint64, C.c_uint64, _dp]),
     ("qc_measure_fp64_peak", C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     ("qc_measure_smem_peak", C.c_int, [C.c_int, C.POINTER(C.c_double)]),

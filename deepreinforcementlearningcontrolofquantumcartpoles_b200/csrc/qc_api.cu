@@ -49,6 +49,7 @@ struct qc_sim {
     // single-trajectory shim state
     BatchView one; int32_t* d_slot1 = nullptr; double* d_noise1 = nullptr; double* d_out1 = nullptr;  // d_out1: moments[20] aux[4] q[16] xm[16]
     unsigned char* d_flag1 = nullptr;
+    double2* d_tmp1 = nullptr;              // input copy of qc_hamiltonian_dot_psi1
     int32_t* d_order = nullptr; int32_t* d_order_count = nullptr; int64_t order_cap = 0;
     double2* d_vglobal = nullptr; size_t vglobal_cap = 0;
     int64_t launches = 0;
@@ -57,6 +58,7 @@ struct qc_sim {
     int g_world = 0, g_rank = 0; uint64_t g_seq = 0;
     double* g_peer[QC_MAX_PEERS] = {}; unsigned long long* g_flag[QC_MAX_PEERS] = {};
     unsigned int* d_gdone = nullptr; unsigned int* d_gerr = nullptr;
+    double* mir_mom = nullptr; double* mir_aux = nullptr; unsigned char* mir_flags = nullptr;   // set by qc_step_host around run(): StepParams::h_*
     std::vector<uint64_t> slot_stamp; uint64_t call_id = 0;      // LRU of the on-demand factor slots (qc_step_forces / qc_step1)
 };
 
@@ -179,7 +181,7 @@ extern "C" int qc_create(const qc_config* cfg, qc_sim** out) {
 extern "C" int qc_destroy(qc_sim* s) {
     if (!s) return QC_OK;
     cudaSetDevice(s->device);
-    cudaFree(s->raw_x); cudaFree(s->raw_hd); cudaFree(s->raw_h2); cudaFree(s->d_fac); cudaFree(s->d_slot_force); cudaFree(s->d_herm);
+    cudaFree(s->raw_x); cudaFree(s->raw_hd); cudaFree(s->raw_h2); cudaFree(s->d_fac); cudaFree(s->d_slot_force); cudaFree(s->d_herm); cudaFree(s->d_tmp1);
     cudaFree(s->batch.psi); cudaFree(s->batch.step); cudaFree(s->batch.flags);
     cudaFree(s->d_gdone); cudaFree(s->d_vglobal); cudaFree(s->d_order); cudaFree(s->d_order_count); cudaFree(s->d_action); cudaFree(s->d_noise); cudaFree(s->d_mom); cudaFree(s->d_aux); cudaFree(s->d_flagout);
     cudaFree(s->one.psi); cudaFree(s->one.step); cudaFree(s->one.flags); cudaFree(s->d_slot1); cudaFree(s->d_noise1); cudaFree(s->d_out1); cudaFree(s->d_flag1);
@@ -267,6 +269,12 @@ extern "C" int qc_clear_flags(qc_sim* s, void* stream) {
     return leave_user(s, stream);
 }
 
+// device alias of a page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) host buffer, or null for pageable memory
+static void* mapped_alias(const void* host) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (at.type == cudaMemoryTypeHost) ? at.devicePointer : nullptr;
+}
 static int stage_in(qc_sim* s, const double* host, size_t count, double** dev_out, cudaStream_t st) {
     // small helper for nullable per-trajectory host arrays
     if (!host) { *dev_out = nullptr; return QC_OK; }
@@ -378,6 +386,7 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
     p.fac = s->d_fac; p.slot_force = s->d_slot_force; p.slot = slot_dev; p.n_slots = s->n_slots; p.herm_tab = s->d_herm;
     p.psi = b.psi; p.noise = noise; p.seed = s->seed; p.traj_offset = s->traj_offset; p.step_count = b.step; p.nsub_traj = nsub_traj;
     p.moments = moments; p.aux = aux; p.flags_out = flags; p.flags_latch = b.flags; p.q_out = q_out; p.xmean_out = xmean_out;
+    p.h_moments = s->mir_mom; p.h_aux = s->mir_aux; p.h_flags = s->mir_flags;
     p.moments_only = moments_only; p.stagger = pl.stagger; p.jacobi = pl.jacobi; p.xfer = pl.xfer; p.herm_smem = pl.herm_smem;
     if (s->g_world > 0 && &b == &s->batch && !moments_only) {          // fused result exchange: rows + sequence flag to every rank
         if (!moments || !aux || !flags) return fail(QC_ERR_ARG, "qc_set_gather is active: qc_step needs moments, aux and flags buffers");
@@ -569,11 +578,18 @@ extern "C" int qc_step_host(qc_sim* s, const int32_t* action, const double* nois
     QC_CUDA(cudaMemcpyAsync(s->d_action, action, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
     double* dn = nullptr;
     rc = stage_in(s, noise, (size_t)B * n_sub * 2, &dn, st); if (rc) return rc;
+    // Page-locked result buffers are written by the kernel itself through their mapped device alias (mirror_row); pageable ones are
+    // copied behind the launch.  (With the fused exchange active the rows travel to the peers instead and the copies stay.)
+    double* zm = (moments && s->g_world == 0) ? (double*)mapped_alias(moments) : nullptr;
+    double* za = (aux && s->g_world == 0) ? (double*)mapped_alias(aux) : nullptr;
+    unsigned char* zf = (flags && s->g_world == 0) ? (unsigned char*)mapped_alias(flags) : nullptr;
+    s->mir_mom = zm; s->mir_aux = za; s->mir_flags = zf;
     rc = run(s, s->batch, s->d_action, dn, n_sub, nullptr, moments ? s->d_mom : nullptr, aux ? s->d_aux : nullptr, flags ? s->d_flagout : nullptr, nullptr, nullptr, 0, st);
+    s->mir_mom = nullptr; s->mir_aux = nullptr; s->mir_flags = nullptr;
     if (rc) return rc;
-    if (moments) QC_CUDA(cudaMemcpyAsync(moments, s->d_mom, sizeof(double) * B * K, cudaMemcpyDeviceToHost, st));
-    if (aux) QC_CUDA(cudaMemcpyAsync(aux, s->d_aux, sizeof(double) * B * QC_AUX_COUNT, cudaMemcpyDeviceToHost, st));
-    if (flags) QC_CUDA(cudaMemcpyAsync(flags, s->d_flagout, (size_t)B, cudaMemcpyDeviceToHost, st));
+    if (moments && !zm) QC_CUDA(cudaMemcpyAsync(moments, s->d_mom, sizeof(double) * B * K, cudaMemcpyDeviceToHost, st));
+    if (aux && !za) QC_CUDA(cudaMemcpyAsync(aux, s->d_aux, sizeof(double) * B * QC_AUX_COUNT, cudaMemcpyDeviceToHost, st));
+    if (flags && !zf) QC_CUDA(cudaMemcpyAsync(flags, s->d_flagout, (size_t)B, cudaMemcpyDeviceToHost, st));
     rc = leave_host(s); if (rc) return rc;
     QC_CUDA(cudaStreamSynchronize(st));
     return QC_OK;
@@ -664,6 +680,36 @@ extern "C" int qc_get_moments1(qc_sim* s, const double* psi, double* out) {
 extern "C" int qc_x_expectation1(qc_sim* s, const double* psi, double* out) {
     if (!out) return fail(QC_ERR_ARG, "null output");
     return moments1_common(s, psi, nullptr, out);
+}
+
+// Hamiltonian_dot_psi(state) / solve_ab(state) of the reference's Fock modules (H:566-597, I:585-616), for every system; see qcart.h
+extern "C" int qc_hamiltonian_dot_psi1(qc_sim* s, double* psi) {
+    int rc = use_device(s); if (rc) return rc;
+    if (!psi) return fail(QC_ERR_ARG, "The input object cannot be identified as an array of complex128");
+    const Model& m = s->model;
+    cudaStream_t st = s->stream;
+    if (!s->d_tmp1) QC_CUDA(cudaMalloc(&s->d_tmp1, sizeof(double2) * m.n));
+    QC_CUDA(cudaMemcpyAsync(s->d_tmp1, psi, sizeof(double2) * m.n, cudaMemcpyHostToDevice, st));
+    double tk[4] = {0, 0, 0, 0};
+    if (m.cfg.variant == QC_QUARTIC) for (int k = 0; k < 4; k++) tk[k] = m.hoff[k];
+    if (launch_hdot(s->d_tmp1, s->one.psi, m.n, m.cfg.variant, s->raw_hd + 8, s->raw_h2 ? s->raw_h2 + 8 : nullptr, tk, st)) return fail(QC_ERR_CUDA, "hdot kernel launch failed");
+    s->launches++;
+    QC_CUDA(cudaMemcpyAsync(psi, s->one.psi, sizeof(double2) * m.n, cudaMemcpyDeviceToHost, st));
+    QC_CUDA(cudaStreamSynchronize(st));
+    return QC_OK;
+}
+extern "C" int qc_solve_ab1(qc_sim* s, double* psi, double F) {
+    int rc = use_device(s); if (rc) return rc;
+    if (!psi) return fail(QC_ERR_ARG, "The input object cannot be identified as an array of complex128");
+    const Model& m = s->model;
+    int slot; rc = find_or_add_slot(s, F, &slot); if (rc) return rc;
+    cudaStream_t st = s->stream;
+    QC_CUDA(cudaMemcpyAsync(s->one.psi, psi, sizeof(double2) * m.n, cudaMemcpyHostToDevice, st));
+    if (launch_solve_exact(s->one.psi, m.n, m.ba, s->d_fac + (size_t)slot * m.n * (m.ba + 1), st)) return fail(QC_ERR_CUDA, "solve kernel launch failed");
+    s->launches++;
+    QC_CUDA(cudaMemcpyAsync(psi, s->one.psi, sizeof(double2) * m.n, cudaMemcpyDeviceToHost, st));
+    QC_CUDA(cudaStreamSynchronize(st));
+    return QC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -605,6 +605,7 @@ __global__ void __launch_bounds__(ClusterGeo<L, GSL, C>::THREADS, 1) sse_cluster
             ax[QC_AUX_NORM] = p.w * v0[0];
         }
     }
+    if ((p.h_moments || p.h_aux || p.h_flags) && rank == 0 && tid < 32) mirror_row(p, traj, lane);
     if (p.g_world > 0) {                                          // fused result exchange (uniform over the grid)
         if (rank == 0 && tid < 32) publish_row(p, traj, lane);
         publish_done(p);

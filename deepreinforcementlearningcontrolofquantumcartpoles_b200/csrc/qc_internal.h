@@ -81,6 +81,9 @@ struct StepParams {
     const int32_t* nsub_traj;// [B] or null
     // outputs
     double* moments; double* aux; unsigned char* flags_out; unsigned char* flags_latch; double* q_out; double* xmean_out;
+    // qc_step_host with page-locked result buffers: mapped device aliases of the caller's HOST arrays; the first warp of every trajectory
+    // mirrors its output row there (coalesced posted writes over PCIe) instead of three copy-engine transfers behind the launch.  null = off.
+    double* h_moments; double* h_aux; unsigned char* h_flags;
     int jacobi;              // 1: register-resident chunk-Jacobi solve (one-warp trajectories, chunk == L)
     int xfer;                // 1: chunk-Jacobi with interface iteration (boundary transfer matrices in shared memory after the noise block)
     int debug;               // development builds only (-DQC_DEBUG_HOOKS, QCART_DEBUG): 1 = skip the implicit solve, 2 = skip the explicit part; results are then wrong
@@ -111,6 +114,8 @@ int launch_init_fock(double2* psi, int B, int n, const double* alpha, void* stre
 int launch_reset_accept(const double2* psi, int B, int n, int variant, int fail_len, double fail_thr2, const double* aux, double cutoff, unsigned char* pending,
                         double2* store, int* n_pending, void* stream);
 int launch_reset_scatter(double2* psi, int B, int n, const unsigned char* mask, const long long* slot, const double2* pool, long long pool_size, unsigned char* flags, void* stream);
+int launch_hdot(const double2* in, double2* out, int n, int variant, const double* hdiag, const double* h2, const double* tk, void* stream);
+int launch_solve_exact(double2* psi, int n, int ba, const double2* fac, void* stream);
 int launch_gather_wait(const unsigned long long* flags, int world, unsigned long long seq, unsigned int* err_flag, void* stream);
 int measure_fp64_peak(int device, double* flops);
 int measure_smem_peak(int device, double* bps);

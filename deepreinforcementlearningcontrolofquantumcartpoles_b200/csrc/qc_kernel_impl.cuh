@@ -595,6 +595,14 @@ __device__ __forceinline__ void publish_row(const StepParams& p, int traj, int l
         // no fence here: publish_done's CTA barrier + system-scope fence + release store order every row of the CTA before the flag
     }
 }
+// Mirror of the trajectory's output row in the caller's mapped host buffers (StepParams::h_*, see qc_step_host).  Visible to the host once
+// the launch has completed (the entry point synchronises its stream before it returns).
+__device__ __forceinline__ void mirror_row(const StepParams& p, int traj, int lane) {
+    __syncwarp();                                     // lane 0 wrote moments / aux / flags_out of this trajectory
+    if (p.h_moments && lane < p.K) p.h_moments[(size_t)traj * p.K + lane] = p.moments[(size_t)traj * p.K + lane];
+    if (p.h_aux && lane < QC_AUX_COUNT) p.h_aux[(size_t)traj * QC_AUX_COUNT + lane] = p.aux[(size_t)traj * QC_AUX_COUNT + lane];
+    if (p.h_flags && lane == 0) p.h_flags[traj] = p.flags_out[traj];
+}
 // Last CTA of the launch: publish the sequence number in slot `rank` of every rank's flag array (release at system scope).
 __device__ __forceinline__ void publish_done(const StepParams& p) {
     __syncthreads();
@@ -814,6 +822,9 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
     // trajectory index lets the solve of one overlap the explicit part of another.  Results do not depend on it.
     if constexpr (MULTI) {
         if (p.stagger > 0 && t > 0) { const long long c0 = clock64(), wait = (long long)t * p.stagger; while (clock64() - c0 < wait) __nanosleep(64); }
+    } else {
+        // one-warp trajectories: the second warp of every scheduler (warps 4..) starts late, so that the two run in opposite phases
+        if (p.stagger > 0 && (int)(threadIdx.x >> 5) >= 4) { const long long c0 = clock64(); while (clock64() - c0 < (long long)p.stagger) __nanosleep(64); }
     }
     // ---- substep loop ---------------------------------------------------------------------------------------
     for (int s = 0; s < p.n_sub; s++) {
@@ -1214,6 +1225,7 @@ __global__ void __launch_bounds__(MAXT, 1) sse_step_kernel(const StepParams p) {
         }
     }
 #endif
+    if (p.h_moments || p.h_aux || p.h_flags) { if (have && g < 32) mirror_row(p, traj, lane); }
     if (p.g_world > 0) {                              // uniform over the grid
         if (have && g < 32) publish_row(p, traj, lane);
         publish_done(p);

@@ -206,7 +206,10 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
             if (P == 1) { W = 0; mult = cols; }
             if (jac) { P = cols; mult = 1; }
             plan.L = L; plan.T = T; plan.G = G; plan.P = P; plan.chunk = mult * L; plan.W = W; plan.jacobi = jac ? 1 : 0; plan.xfer = (jac && want_xfer) ? 1 : 0;
-            plan.pipe = 0; plan.stagger = env_int("QCART_STAGGER", 0);
+            plan.pipe = 0;
+            // one-warp grid trajectories: the second warp of each scheduler starts 3000 cycles late (opposite phases of explicit part and
+            // solve; config 2: 0.549 -> 0.543 ms, results do not depend on it).  Multi-warp trajectories: off (measured: no effect).
+            plan.stagger = env_int("QCART_STAGGER", (var == QC_QUARTIC && G == 32 && jac && T > 4) ? 3000 : 0);
             plan.vglobal = vglobal ? 1 : 0; plan.vglobal_elems_per_traj = (long long)(nbuf - 1) * L * Gp;
             plan.binned = binned ? 1 : 0; plan.herm_smem = herm_smem ? 1 : 0; plan.smem_cta_extra = binned ? tab_bytes : 0;
             plan.NP = NP; plan.threads = T * G; plan.tstride = tstride; plan.smem_bytes = T * tstride + plan.smem_cta_extra; plan.gc = ke->gc; plan.maxt = ke->maxt; plan.tabs = tabs != 0;
@@ -341,6 +344,106 @@ int launch_init_packets(double2* psi, int B, int n, double h, int half, const do
 }
 int launch_init_fock(double2* psi, int B, int n, const double* alpha, void* stream) {
     init_fock_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(psi, B, n, alpha);
+    return cudaGetLastError() == cudaSuccess ? QC_OK : QC_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Diagnostics of the reference's modules for ONE state (harmonic simulation.cpp:566-597, simulation_i.cpp:585-616; unused by its Python):
+//   Hamiltonian_dot_psi:  out = H psi at zero force (band of H: grid 9-point stencil + V, harmonic diagonal, inverted harmonic +-2);
+//   solve_ab:             psi <- A(F)^-1 psi, the EXACT band substitution with the L D L^T factors of one force slot (no truncation:
+//                         this is the check of the truncated solvers of the step kernels, not a hot path).
+__global__ void hdot_kernel(const double2* __restrict__ in, double2* __restrict__ out, int n, int variant, const double* __restrict__ hdiag,
+                            const double* __restrict__ h2, double t1, double t2, double t3, double t4) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 c = in[i];
+    double re = hdiag[i] * c.x, im = hdiag[i] * c.y;
+    if (variant == QC_QUARTIC) {
+        const double tk[4] = {t1, t2, t3, t4};
+#pragma unroll
+        for (int k = 1; k <= 4; k++) {
+            if (i - k >= 0) { const double2 a = in[i - k]; re = fma(tk[k - 1], a.x, re); im = fma(tk[k - 1], a.y, im); }
+            if (i + k < n) { const double2 b = in[i + k]; re = fma(tk[k - 1], b.x, re); im = fma(tk[k - 1], b.y, im); }
+        }
+    } else if (variant == QC_INV_HARMONIC) {
+        if (i + 2 < n) { const double2 b = in[i + 2]; re = fma(h2[i], b.x, re); im = fma(h2[i], b.y, im); }
+        if (i - 2 >= 0) { const double2 a = in[i - 2]; re = fma(h2[i - 2], a.x, re); im = fma(h2[i - 2], a.y, im); }
+    }
+    out[i] = make_double2(re, im);
+}
+// one warp: the factor rows are fetched 32 at a time (coalesced) into shared memory, lane 0 runs the recurrence on them
+template <int BA>
+__global__ void solve_exact_kernel(double2* __restrict__ psi, int n, const double2* __restrict__ fac) {
+    __shared__ double2 rows[32 * (BA + 1)];
+    __shared__ double2 v[32];
+    const int lane = threadIdx.x;
+    double2 y[BA];
+#pragma unroll
+    for (int k = 0; k < BA; k++) y[k] = make_double2(0.0, 0.0);
+    // forward: L y = rhs, z = D^-1 y   (row i = { l[i][i-1..i-BA], 1/d_i })
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int m = min(32, n - i0);
+        for (int e = lane; e < m * (BA + 1); e += 32) rows[e] = fac[(size_t)i0 * (BA + 1) + e];
+        if (lane < m) v[lane] = psi[i0 + lane];
+        __syncwarp();
+        if (lane == 0) {
+            for (int r = 0; r < m; r++) {
+                double re = v[r].x, im = v[r].y;
+#pragma unroll
+                for (int k = BA - 1; k >= 0; k--) {
+                    const double2 l = rows[r * (BA + 1) + k];
+                    re = fma(-l.x, y[k].x, re); re = fma(l.y, y[k].y, re);
+                    im = fma(-l.x, y[k].y, im); im = fma(-l.y, y[k].x, im);
+                }
+#pragma unroll
+                for (int k = BA - 1; k > 0; k--) y[k] = y[k - 1];
+                y[0] = make_double2(re, im);
+                const double2 d = rows[r * (BA + 1) + BA];
+                v[r] = make_double2(re * d.x - im * d.y, re * d.y + im * d.x);
+            }
+        }
+        __syncwarp();
+        if (lane < m) psi[i0 + lane] = v[lane];
+        __syncwarp();
+    }
+    // backward: L^T x = z, column oriented: x_i final -> its contributions l[i][i-k] x_i are subtracted from the k-th row before it
+    double2 pend[BA];                                   // pend[k] = accumulated update of row (current - 1 - k)
+#pragma unroll
+    for (int k = 0; k < BA; k++) pend[k] = make_double2(0.0, 0.0);
+    for (int hi = n; hi > 0; hi -= 32) {
+        const int i0 = max(0, hi - 32), m = hi - i0;
+        for (int e = lane; e < m * (BA + 1); e += 32) rows[e] = fac[(size_t)i0 * (BA + 1) + e];
+        if (lane < m) v[lane] = psi[i0 + lane];
+        __syncwarp();
+        if (lane == 0) {
+            for (int r = m - 1; r >= 0; r--) {
+                const double xr = v[r].x + pend[0].x, xi = v[r].y + pend[0].y;
+#pragma unroll
+                for (int k = 0; k + 1 < BA; k++) pend[k] = pend[k + 1];
+                pend[BA - 1] = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int k = 0; k < BA; k++) {
+                    const double2 l = rows[r * (BA + 1) + k];
+                    pend[k].x = fma(-xr, l.x, fma(xi, l.y, pend[k].x));
+                    pend[k].y = fma(-xr, l.y, fma(-xi, l.x, pend[k].y));
+                }
+                v[r] = make_double2(xr, xi);
+            }
+        }
+        __syncwarp();
+        if (lane < m) psi[i0 + lane] = v[lane];
+        __syncwarp();
+    }
+}
+int launch_hdot(const double2* in, double2* out, int n, int variant, const double* hdiag, const double* h2, const double* tk, void* stream) {
+    hdot_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(in, out, n, variant, hdiag, h2, tk[0], tk[1], tk[2], tk[3]);
+    return cudaGetLastError() == cudaSuccess ? QC_OK : QC_ERR_CUDA;
+}
+int launch_solve_exact(double2* psi, int n, int ba, const double2* fac, void* stream) {
+    if (ba == 4) solve_exact_kernel<4><<<1, 32, 0, (cudaStream_t)stream>>>(psi, n, fac);
+    else if (ba == 2) solve_exact_kernel<2><<<1, 32, 0, (cudaStream_t)stream>>>(psi, n, fac);
+    else if (ba == 1) solve_exact_kernel<1><<<1, 32, 0, (cudaStream_t)stream>>>(psi, n, fac);
+    else return QC_ERR_UNSUPPORTED;
     return cudaGetLastError() == cudaSuccess ? QC_OK : QC_ERR_CUDA;
 }
 

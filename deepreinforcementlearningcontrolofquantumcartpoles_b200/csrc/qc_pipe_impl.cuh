@@ -864,6 +864,7 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG, NSW>::THREADS, 1
                     }
                 }
             }
+            if ((p.h_moments || p.h_aux || p.h_flags) && have && g < 32) mirror_row(p, traj, lane);
             if (p.g_world > 0 && have && g < 32) publish_row(p, traj, lane);
         }
     }

@@ -267,6 +267,14 @@ class BatchedSim:
         L.check(self.lib.qc_x_expectation1(self.h, state.ctypes.data, C.byref(v)))
         return v.value
 
+    def hamiltonian_dot_psi1(self, state):
+        """state <- H state (zero force), in place (harmonic simulation.cpp:566-582)."""
+        L.check(self.lib.qc_hamiltonian_dot_psi1(self.h, state.ctypes.data))
+
+    def solve_ab1(self, state, F):
+        """state <- (I + i dt/2 (H - kappa F x))^-1 state, in place, exact band substitution (harmonic simulation.cpp:584-597)."""
+        L.check(self.lib.qc_solve_ab1(self.h, state.ctypes.data, float(F)))
+
 
 def philox_normals(seed, traj, step):
     """Host restatement of the in-kernel noise: the (r0, r1) of (seed, global trajectory id, substep counter)."""

@@ -10,6 +10,8 @@ setupC.py, and the module-level functions keep the reference's names, argument m
     x_expectation(state)                                   :244-258
     set_seed(seed)                                         :645-650
     check_settings()                                       :652-654 / harmonic simulation.cpp:562-564
+    Hamiltonian_dot_psi(state) -> 0.0                      harmonic simulation.cpp:566-582 (state <- H state, in place)
+    solve_ab(state) -> 0.0                                 harmonic simulation.cpp:584-597 (state <- A^-1 state with the force of the last step)
 
 Every call runs on the GPU (batch of one); there is no CPU path.
 """
@@ -21,12 +23,13 @@ _params = None
 _device = 0
 _sims = {}
 _seed = 0
+_last = None        # (dt, gamma, F) of the most recent step: the factorisation the reference's solve_ab would use
 
 
 def configure(params, device=0):
     """Select the system (a dict from configs.py).  Equivalent of compiling the reference module with setupC.py."""
-    global _params, _device, _sims
-    _params, _device, _sims = dict(params), device, {}
+    global _params, _device, _sims, _last
+    _params, _device, _sims, _last = dict(params), device, {}, None
 
 
 def _sim(dt=None, gamma=None):
@@ -61,14 +64,18 @@ def step(state, dt, F, gamma, normals=None):
     """One SSE substep in place.  `normals` (extension): the two N(0,1) draws, else the seeded Philox stream."""
     if not all(isinstance(v, (int, float, np.floating)) for v in (dt, F, gamma)):
         raise TypeError("The input does not match the required input signature (state (numpy array), dt (double), F (double), \\gamma (double))")
+    global _last
     s = _sim(dt, gamma)
     _check_state(state, s.n)
+    _last = (float(dt), float(gamma), float(F))
     return s.step1(state, float(dt), float(F), float(gamma), normals)
 
 
 def simulate_10_steps(state, dt, F, gamma, normals=None):
+    global _last
     s = _sim(dt, gamma)
     _check_state(state, s.n)
+    _last = (float(dt), float(gamma), float(F))
     return s.simulate_10_steps1(state, float(dt), float(F), float(gamma), normals)
 
 
@@ -92,6 +99,24 @@ def x_expectation(state):
     s = _sim()
     _check_state(state, s.n)
     return s.x_expectation1(state)
+
+
+def Hamiltonian_dot_psi(state):
+    s = _sim()
+    _check_state(state, s.n)
+    s.hamiltonian_dot_psi1(state)
+    return 0.0
+
+
+def solve_ab(state):
+    """Solves with the factorisation of the most recent step()'s (dt, gamma, F), like the reference's cached LU; before any step the
+    reference's LU is uninitialised -- here that is a RuntimeError."""
+    if _last is None:
+        raise RuntimeError("solve_ab before the first step(): no factorisation has been set")
+    s = _sim(_last[0], _last[1])
+    _check_state(state, s.n)
+    s.solve_ab1(state, _last[2])
+    return 0.0
 
 
 def set_seed(seed):

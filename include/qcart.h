@@ -156,7 +156,10 @@ int qc_step_forces(qc_sim *sim, const double *force_host, const double *noise, i
                    double *moments, double *aux, uint8_t *flags, double *q_out, double *xmean_out, void *stream);
 
 /* End-to-end variant with HOST buffers (pinned or pageable): copies action (and noise if given) host->device, runs
- * qc_step, copies moments / aux / flags back, and synchronises.  This is the call a host-side actor loop makes. */
+ * qc_step, brings moments / aux / flags back, and synchronises.  This is the call a host-side actor loop makes.
+ * Result buffers in page-locked memory (cudaHostAlloc / cudaHostRegister, torch pin_memory) are written by the kernel itself through
+ * their mapped device alias -- each trajectory's row crosses PCIe as a coalesced posted write when the trajectory finishes; pageable
+ * buffers (and all buffers while qc_set_gather is active) are filled by copies behind the launch.  Same bytes either way. */
 int qc_step_host(qc_sim *sim, const int32_t *action, const double *noise, int n_sub,
                  double *moments, double *aux, uint8_t *flags);
 
@@ -179,6 +182,15 @@ int qc_simulate_10_steps1(qc_sim *sim, double *psi, double dt, double F, double 
 int qc_get_moments1(qc_sim *sim, const double *psi, double *out);
 /* x_expectation(state) (Q:244-258, H:185-196) */
 int qc_x_expectation1(qc_sim *sim, const double *psi, double *out);
+/* Hamiltonian_dot_psi(state) of the reference's Fock modules (harmonic simulation.cpp:566-582, simulation_i.cpp:585-601; not called by
+ * its Python): psi <- H psi in place with the drift Hamiltonian at zero force.  Offered for all three systems. */
+int qc_hamiltonian_dot_psi1(qc_sim *sim, double *psi);
+/* solve_ab(state) (harmonic simulation.cpp:584-597, simulation_i.cpp:603-616): psi <- (I + i dt/2 (H - kappa F x))^-1 psi in place.
+ * The reference solves with the LU of the force of its most recent step() call; here that force is the argument F.  This is the exact
+ * band substitution (no truncation of the factor's decay): the cross-check of the step kernels' truncated solvers.
+ * (simulation_i.cpp:613 calls zgbtrs with kl = ku = 1 on a kl = ku = 2 factorisation and returns garbage; this entry point solves with
+ * the factorisation step() uses, I:487.) */
+int qc_solve_ab1(qc_sim *sim, double *psi, double F);
 
 /* ---- utilities -------------------------------------------------------------------------------------------- */
 /* The (r0, r1) pair the kernel draws for (seed, global trajectory id, substep counter): host restatement of the

@@ -84,6 +84,42 @@ def test_simulation_module_mirror_fock():
         assert abs(simulation.x_expectation(psi) - orc.x_expectation(ref)) < 1e-10
 
 
+def test_simulation_module_diagnostics_all_systems():
+    """Hamiltonian_dot_psi / solve_ab (harmonic simulation.cpp:566-597, simulation_i.cpp:585-616) through the C-ABI against the oracle
+    (pivoted LAPACK-style LU) and, where it was built, the reference's own module.  solve_ab is the exact band substitution: 1e-12."""
+    from oracle.ref_module import RefModule, available
+    rng = np.random.default_rng(21)
+    for task in ("harmonic", "inverted_harmonic", "quartic", "inverted_quartic"):
+        params = configs.PRESETS[task]()
+        simulation.configure(params)
+        orc = oracle_for(params)
+        n = orc.n
+        psi = initial_states(params, 1, 2)[0]
+        with pytest.raises(RuntimeError):
+            simulation.solve_ab(psi.copy())                       # no factorisation before the first step
+        for F in (level_force(params, 19), 0.0, -1.234567):
+            r = rng.standard_normal(2)
+            st = psi.copy()
+            simulation.step(st, params["dt"], F, params["gamma"], normals=r)
+            v = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * np.exp(-0.02 * np.arange(n))
+            x_gpu, x_orc = v.copy(), v.copy()
+            assert simulation.solve_ab(x_gpu) == 0.0
+            orc.solve_ab(params["dt"], F, x_orc)
+            assert np.linalg.norm(x_gpu - x_orc) / np.linalg.norm(x_orc) < 1e-12
+            assert np.linalg.norm(orc.A_dense(params["dt"], F) @ x_gpu - v) / np.linalg.norm(v) < 1e-12
+            if task == "harmonic" and available(task):            # (simulation_i.cpp:613 solves with the wrong band width: not a reference)
+                ref = RefModule(task)
+                ref.step(psi.copy(), params["dt"], F, params["gamma"], r)
+                x_ref = v.copy(); ref.mod.solve_ab(x_ref)
+                assert np.linalg.norm(x_gpu - x_ref) / np.linalg.norm(x_ref) < 1e-12
+        h_gpu, h_orc = v.copy(), v.copy()
+        assert simulation.Hamiltonian_dot_psi(h_gpu) == 0.0
+        orc.hamiltonian_dot_psi(h_orc)
+        assert np.linalg.norm(h_gpu - h_orc) / np.linalg.norm(h_orc) < 1e-13
+        with pytest.raises(ValueError):
+            simulation.Hamiltonian_dot_psi(np.zeros(n - 1, np.complex128))
+
+
 def test_host_buffer_entry_point_equals_device_entry_point():
     torch = _torch()
     params = configs.quartic(n_sub=8)
@@ -97,6 +133,31 @@ def test_host_buffer_entry_point_equals_device_entry_point():
     assert np.array_equal(out["moments"].cpu().numpy(), mom) and np.array_equal(out["aux"].cpu().numpy(), aux)
     assert np.array_equal(out["flags"].cpu().numpy(), flags)
     assert np.array_equal(a.get_state(), b.get_state())
+
+
+def test_host_entry_point_pinned_buffers_equal_pageable_buffers():
+    """qc_step_host writes page-locked result buffers from inside the kernel (mapped alias, mirror_row) and copies into pageable ones:
+    bitwise the same rows, for the per-trajectory kernel, the pipeline kernel and the cluster kernel, and with only some buffers pinned."""
+    torch = _torch()
+    cases = [(configs.quartic(n_sub=6), 300), (configs.inverted_quartic(n_sub=4), 1300), (configs.inverted_harmonic(n_sub=5), 1500),
+             (configs.quartic_sweep(2501, n_sub=2), 5)]
+    for params, B in cases:
+        psi0 = initial_states(params, min(B, 64), 1)
+        psi0 = np.tile(psi0, ((B + psi0.shape[0] - 1) // psi0.shape[0], 1))[:B]
+        act = np.random.default_rng(1).integers(0, params["n_levels"], B).astype(np.int32)
+        a = BatchedSim(params, batch=B, seed=5); a.set_state(psi0)
+        b = BatchedSim(params, batch=B, seed=5); b.set_state(psi0)
+        c = BatchedSim(params, batch=B, seed=5); c.set_state(psi0)
+        mom_p = torch.full((B, a.K), float("nan"), dtype=torch.float64).pin_memory()
+        aux_p = torch.full((B, L.QC_AUX_COUNT), float("nan"), dtype=torch.float64).pin_memory()
+        flg_p = torch.full((B,), 255, dtype=torch.uint8).pin_memory()
+        for _ in range(2):
+            a.step_host(act, moments=mom_p, aux=aux_p, flags=flg_p)
+            mom, aux, flags = b.step_host(act)
+            mom_c, aux_c, flg_c = c.step_host(act, aux=aux_p.clone().pin_memory())            # mixed: only aux pinned
+            assert np.array_equal(mom_p.numpy(), mom) and np.array_equal(aux_p.numpy(), aux) and np.array_equal(flg_p.numpy(), flags), a.kernel_info()
+            assert np.array_equal(mom_c, mom) and np.array_equal(aux_c.numpy(), aux) and np.array_equal(flg_c, flags)
+        assert np.array_equal(a.get_state(), b.get_state())
 
 
 def test_fail_and_escape_flags():
