@@ -273,9 +273,11 @@ def measure_extra(task, params, B, steps, warmup, rank, world, local_rank, flush
     ach = B / (ms * 1e-3) * fpu / 1e12
     traffic = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_static.json"))).get(task, {})
-        if B == 8192 and not tag.startswith("BASELINE configs[4]"):
-            traffic = prof.get("dram_bytes_per_launch")
+        static = json.load(open(os.path.join(ROOT, "profiles", "roofline_static.json")))
+        if tag.startswith("BASELINE configs[4]"):              # sweep points: captured per (N, batch)
+            traffic = static.get("sweep_N%d_B%d" % (n, B), {}).get("dram_bytes_per_launch")
+        elif B == 8192:
+            traffic = static.get(task, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
     rec = {"workload": workload_name(task, B, n, params["n_sub"]) + (" [%s]" % tag if tag else ""), "value": world * B / (ms * 1e-3), "unit": "traj-control-steps/s",
