@@ -10,7 +10,7 @@ points, 80 substeps per control step); N>1 = the same per-GPU batch on every ran
 data-path collective plus the exchange of the moment/reward block (stored by the SSE kernel into every rank's peer memory).
 Inside the same driver-timed run the line also carries, under "extra", the other BASELINE configurations measured the same way
 (CUDA events, L2 flushed between steps, max over ranks): config3 (inverted harmonic, 8192 trajectories/GPU), config4 (inverted
-quartic, 8192 trajectories/GPU = 65,536 on 8 GPUs, with its own roofline) and, at N=1, three points of the grid-size sweep.
+quartic, 8192 trajectories/GPU = 65,536 on 8 GPUs, with its own roofline) and five points of the grid-size sweep (N = 257 ... 8193).
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -480,9 +480,10 @@ def main():
                                          "BASELINE configs[2]; herm_mode 0 = literal HERMITIAN/UPPER application of C (I:23,551); mode 1 differs by < 1e-7 after 5 substeps at F_max, which of the two MKL computes is unpinned")
         extra["config4"] = measure_extra("inverted_quartic", configs.inverted_quartic(), 8192, xs, xw, rank, world, local_rank, flush_buf, fp64_peak,
                                          "BASELINE configs[3]: 65,536 trajectories on 8 GPUs = 8192 per GPU")
-        if world == 1:
-            extra["sweep"] = [measure_extra("inverted_quartic", configs.quartic_sweep(npts), Bs, 3, 2, rank, world, local_rank, flush_buf, fp64_peak,
-                                            "BASELINE configs[4], x_max 13, dt ~ h^2") for npts, Bs in ((257, 4096), (1025, 2048), (4097, 296))]
+        # grid-size sweep (BASELINE configs[4]): every rank steps its own batch of each size (weak scaling like the headline), so the 1/2/4/8-GPU
+        # runs of the driver carry it too; ~0.3 s of device time per rank for all five sizes
+        extra["sweep"] = [measure_extra("inverted_quartic", configs.quartic_sweep(npts), Bs, 3, 2, rank, world, local_rank, flush_buf, fp64_peak,
+                                        "BASELINE configs[4], x_max 13, dt ~ h^2") for npts, Bs in ((257, 4096), (1025, 2048), (2049, 1024), (4097, 296), (8193, 148))]
 
     if rank != 0:
         if world > 1:
