@@ -6,11 +6,12 @@
 // more than the shorter recurrence gains (N = 769 / 1025 / 1281: 7.5 -> 8.2, 8.6 -> 9.3, 10.2 -> 10.8 ms).
 #include "qc_pipe_impl.cuh"
 namespace qc {
+const PipeEntry* qc_find_pipe_wide_smem(int var, int L, int G, int ne);
 static const PipeEntry k_pipe[] = { QC_PE_TABG_NSW(QC_QUARTIC, 6, 352, 1, 2), QC_PE_TABG_NSW(QC_QUARTIC, 6, 320, 1, 2), QC_PE_TABG_NSW(QC_QUARTIC, 6, 288, 1, 2),
                                     QC_PE_TABG(QC_QUARTIC, 6, 352, 1), QC_PE_TABG(QC_QUARTIC, 6, 320, 1), QC_PE_TABG(QC_QUARTIC, 6, 288, 1),
                                     QC_PE_TABG(QC_QUARTIC, 6, 256, 1), QC_PE_TABG(QC_QUARTIC, 6, 224, 1), QC_PE_TABG(QC_QUARTIC, 6, 192, 1), QC_PE_TABG(QC_QUARTIC, 6, 160, 1), QC_PE_TABG(QC_QUARTIC, 6, 128, 1) };
 const PipeEntry* qc_find_pipe_wide(int var, int L, int G, int ne) {
     for (const PipeEntry& e : k_pipe) if (e.var == var && e.L == L && e.gc == G && (ne <= 0 || e.ne == ne)) return &e;
-    return nullptr;
+    return qc_find_pipe_wide_smem(var, L, G, ne);
 }
 }  // namespace qc

@@ -21,6 +21,7 @@ const KernEntry* qc_entries_fock_ih2(int* count);
 
 struct PipeEntry { int var, L, gc, ne, threads; kern_t fn; size_t (*smem)(int n_sub); };
 const PipeEntry* qc_find_pipe(int var, int L, int G, int ne);
+const PipeEntry* qc_find_pipe_wide_smem(int var, int L, int G, int ne);
 struct ClusterEntry { int L, gsl, c, threads; kern_t fn; size_t (*smem)(int n_sub); };
 const ClusterEntry* qc_find_cluster(int L, int cols);
 
@@ -111,9 +112,14 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
         const int L = env_int("QCART_PIPE_L", (var == QC_QUARTIC) ? 6 : 3), cols = (n + L - 1) / L, G = (cols + 31) / 32 * 32, W = (W_needed + L - 1) / L * L;
         const int want_ne = env_int("QCART_PIPE_NE", (var == QC_HARMONIC) ? 24 /* NE = 8, two solver warps per set */ : ((var == QC_INV_HARMONIC) ? 4 : (G >= 288 ? 17 /* NE = 1, two solver warps per trajectory */ : (G >= 128 ? 1 : 0))));
         const PipeEntry* pe = qc_find_pipe(var, L, G, want_ne);
+        // single-group CTAs: the instance with the factor table in shared memory when table + lines fit (QCART_PIPE_TABS=0: table in L2)
+        if (var == QC_QUARTIC && want_ne == 1 && env_int("QCART_PIPE_TABS", 1)) {
+            const PipeEntry* ps = qc_find_pipe_wide_smem(var, L, G, 1 + 64);
+            if (ps && (int)ps->smem(n_sub) <= smem_max) pe = ps;
+        }
         const int GUc = (G == 32) ? 10 : ((var == QC_QUARTIC) ? 5 : 12);
         if (pe && W <= (GUc - 1) * L && (int)pe->smem(n_sub) <= smem_max) {
-            const int ne = pe->ne & 15, nsw = (pe->ne >> 4) + 1;           // instance id: NE + 16 (NSW - 1), see qc_pipe_impl.cuh
+            const int ne = pe->ne & 15, nsw = ((pe->ne >> 4) & 3) + 1;          // (+64: single-group instance with the table in shared memory)           // instance id: NE + 16 (NSW - 1), see qc_pipe_impl.cuh
             const int TT = 2 * ne, cpt = (ne == 1) ? 32 * nsw : 32 / (ne / nsw), GU = GUc;       // ne == 1: the nsw solver warps split the chunks of one trajectory
             int mult = (cols + cpt - 1) / cpt;
             if (nsw == 1 || ne == 1) mult |= 1; else mult = (mult + 1) & ~1;
@@ -131,8 +137,8 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
                 memset(&plan, 0, sizeof(plan));
                 plan.L = L; plan.T = TT; plan.G = G; plan.P = cpt; plan.chunk = mult * L; plan.W = W; plan.NP = G * L; plan.threads = pe->threads;
                 plan.smem_bytes = (int)pe->smem(n_sub); plan.tstride = 0; plan.maxt = pe->threads; plan.gc = G; plan.tabs = true; plan.binned = 1; plan.pipe = pe->ne;
-                snprintf(plan.info, sizeof(plan.info), "sse_pipe_kernel<var=%d,L=%d,G=%d,NE=%d,NSW=%d> traj/CTA=%d chunks/traj=%d chunk=%d W=%d bin=1 threads=%d smem=%d regs=%d lmem=%d",
-                         var, L, G, ne, nsw, plan.T, cpt, plan.chunk, W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
+                snprintf(plan.info, sizeof(plan.info), "sse_pipe_kernel<var=%d,L=%d,G=%d,NE=%d,NSW=%d%s> traj/CTA=%d chunks/traj=%d chunk=%d W=%d bin=1 threads=%d smem=%d regs=%d lmem=%d",
+                         var, L, G, ne, nsw, (pe->ne & 64) ? ",tab=smem" : "", plan.T, cpt, plan.chunk, W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
                 return QC_OK;
             }
         }
