@@ -58,6 +58,8 @@ struct qc_sim {
     int g_world = 0, g_rank = 0; uint64_t g_seq = 0;
     double* g_peer[QC_MAX_PEERS] = {}; unsigned long long* g_flag[QC_MAX_PEERS] = {};
     unsigned int* d_gdone = nullptr; unsigned int* d_gerr = nullptr;
+    // chunk-transposed factor table of the current pipeline plan (LaunchPlan::tabt): rebuilt when the plan geometry or any slot changes
+    double2* d_fac_t = nullptr; size_t fac_t_cap = 0; int fac_t_chunk = 0, fac_t_W = 0, fac_t_nch = 0, fac_t_L = 0; bool fac_t_dirty = true;
     double* mir_mom = nullptr; double* mir_aux = nullptr; unsigned char* mir_flags = nullptr;   // set by qc_step_host around run(): StepParams::h_*
     std::vector<uint64_t> slot_stamp; uint64_t call_id = 0;      // LRU of the on-demand factor slots (qc_step_forces / qc_step1)
 };
@@ -126,6 +128,7 @@ static int add_slot(qc_sim* s, double F, int* slot_out) {
     QC_CUDA(cudaMemcpy(s->d_fac + row * idx, tab.data(), sizeof(zc) * row, cudaMemcpyHostToDevice));
     QC_CUDA(cudaMemcpy(s->d_slot_force + idx, &F, sizeof(double), cudaMemcpyHostToDevice));
     if (s->d_herm) { std::vector<double> ht; m.herm_table(F, ht); QC_CUDA(cudaMemcpy(s->d_herm + (size_t)m.n * 11 * idx, ht.data(), sizeof(double) * ht.size(), cudaMemcpyHostToDevice)); }
+    s->fac_t_dirty = true;
     if (idx == s->n_slots) { s->slot_force.push_back(F); s->slot_stamp.push_back(s->call_id); s->n_slots++; }
     else { s->slot_force[idx] = F; s->slot_stamp[idx] = s->call_id; }
     *slot_out = idx;
@@ -181,7 +184,7 @@ extern "C" int qc_create(const qc_config* cfg, qc_sim** out) {
 extern "C" int qc_destroy(qc_sim* s) {
     if (!s) return QC_OK;
     cudaSetDevice(s->device);
-    cudaFree(s->raw_x); cudaFree(s->raw_hd); cudaFree(s->raw_h2); cudaFree(s->d_fac); cudaFree(s->d_slot_force); cudaFree(s->d_herm); cudaFree(s->d_tmp1);
+    cudaFree(s->raw_x); cudaFree(s->raw_hd); cudaFree(s->raw_h2); cudaFree(s->d_fac); cudaFree(s->d_slot_force); cudaFree(s->d_herm); cudaFree(s->d_tmp1); cudaFree(s->d_fac_t);
     cudaFree(s->batch.psi); cudaFree(s->batch.step); cudaFree(s->batch.flags);
     cudaFree(s->d_gdone); cudaFree(s->d_vglobal); cudaFree(s->d_order); cudaFree(s->d_order_count); cudaFree(s->d_action); cudaFree(s->d_noise); cudaFree(s->d_mom); cudaFree(s->d_aux); cudaFree(s->d_flagout);
     cudaFree(s->one.psi); cudaFree(s->one.step); cudaFree(s->one.flags); cudaFree(s->d_slot1); cudaFree(s->d_noise1); cudaFree(s->d_out1); cudaFree(s->d_flag1);
@@ -386,6 +389,22 @@ static int run(qc_sim* s, BatchView& b, const int32_t* slot_dev, const double* n
     p.fac = s->d_fac; p.slot_force = s->d_slot_force; p.slot = slot_dev; p.n_slots = s->n_slots; p.herm_tab = s->d_herm;
     p.psi = b.psi; p.noise = noise; p.seed = s->seed; p.traj_offset = s->traj_offset; p.step_count = b.step; p.nsub_traj = nsub_traj;
     p.moments = moments; p.aux = aux; p.flags_out = flags; p.flags_latch = b.flags; p.q_out = q_out; p.xmean_out = xmean_out;
+    if (pl.tabt) {          // single-group pipeline instance with the table in global memory: chunk-transposed copy for coalesced solver loads
+        const int rows = pl.chunk + pl.W + 2 * QC_TABT_SLACK(pl.L);
+        const size_t stride = (size_t)rows * (2 * m.ba + 1) * pl.P, need = stride * s->cap_slots;
+        if (s->fac_t_cap < need) {
+            QC_CUDA(cudaDeviceSynchronize()); cudaFree(s->d_fac_t); s->d_fac_t = nullptr; s->fac_t_cap = 0;
+            QC_CUDA(cudaMalloc(&s->d_fac_t, sizeof(double2) * need)); s->fac_t_cap = need; s->fac_t_dirty = true;
+        }
+        if (s->fac_t_dirty || s->fac_t_chunk != pl.chunk || s->fac_t_W != pl.W || s->fac_t_nch != pl.P || s->fac_t_L != pl.L) {
+            // (stream order: behind every launch that still reads the previous layout on this stream; other streams: a plan or slot change
+            //  already implies a host-side synchronisation point in add_slot / qc_set_batch)
+            if (launch_fac_transpose(s->d_fac, s->d_fac_t, m.n, m.ba, s->n_slots, pl.chunk, pl.W, pl.L, pl.P, stream)) return fail(QC_ERR_CUDA, "factor-table transpose launch failed");
+            s->launches++;
+            s->fac_t_dirty = false; s->fac_t_chunk = pl.chunk; s->fac_t_W = pl.W; s->fac_t_nch = pl.P; s->fac_t_L = pl.L;
+        }
+        p.fac_t = s->d_fac_t; p.fac_t_stride = (long long)stride;
+    }
     p.h_moments = s->mir_mom; p.h_aux = s->mir_aux; p.h_flags = s->mir_flags;
     p.moments_only = moments_only; p.stagger = pl.stagger; p.jacobi = pl.jacobi; p.xfer = pl.xfer; p.herm_smem = pl.herm_smem;
     if (s->g_world > 0 && &b == &s->batch && !moments_only) {          // fused result exchange: rows + sequence flag to every rank

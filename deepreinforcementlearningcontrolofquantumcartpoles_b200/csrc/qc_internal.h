@@ -64,6 +64,9 @@ struct StepParams {
     const double* hdiag;     // [n + 16] same padding
     const double* h2;        // [n + 16] inverted harmonic, same padding (else null)
     const double2* fac;      // [slots][n][ba+1]
+    const double2* fac_t;    // chunk-transposed copy of `fac` for the single-group pipeline instances that keep the table in global memory
+                             // (qc_kernels.cu: fac_transpose_kernel); [slots][fac_t_stride], null = not built
+    long long fac_t_stride;  // double2 per slot
     const double* slot_force;// [slots]
     const int32_t* slot;     // [B] slot per trajectory
     const int32_t* order;    // binned work list: trajectory id or -1 per position (null = identity)
@@ -102,7 +105,7 @@ struct StepParams {
 
 struct LaunchPlan {
     int L, T, G, P, chunk, W, NP, threads, smem_bytes, tstride, maxt, gc;
-    bool tabs; int jacobi; int xfer; int binned; int smem_cta_extra; int vglobal; long long vglobal_elems_per_traj; int herm_smem; int stagger; int pipe; int cluster;
+    bool tabs; int jacobi; int xfer; int binned; int smem_cta_extra; int vglobal; long long vglobal_elems_per_traj; int herm_smem; int stagger; int pipe; int cluster; int tabt;
     char info[240];
 };
 
@@ -116,6 +119,9 @@ int launch_reset_accept(const double2* psi, int B, int n, int variant, int fail_
 int launch_reset_scatter(double2* psi, int B, int n, const unsigned char* mask, const long long* slot, const double2* pool, long long pool_size, unsigned char* flags, void* stream);
 int launch_hdot(const double2* in, double2* out, int n, int variant, const double* hdiag, const double* h2, const double* tk, void* stream);
 int launch_solve_exact(double2* psi, int n, int ba, const double2* fac, void* stream);
+#define QC_TABT_SLACK(L) ((L) + 8)   // rows of slack either side of a chunk's window in the transposed table (look-ahead of the solver's loads)
+// chunk-transposed factor table: see fac_transpose_kernel.  rows = chunk + W + 2 QC_TABT_SLACK(L), stride = rows * (2 ba + 1) * nch double2 per slot.
+int launch_fac_transpose(const double2* fac, double2* out, int n, int ba, int n_slots, int chunk, int W, int L, int nch, void* stream);
 int launch_gather_wait(const unsigned long long* flags, int world, unsigned long long seq, unsigned int* err_flag, void* stream);
 int measure_fp64_peak(int device, double* flops);
 int measure_smem_peak(int device, double* bps);

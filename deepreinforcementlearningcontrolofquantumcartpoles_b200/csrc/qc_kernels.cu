@@ -19,7 +19,7 @@ const KernEntry* qc_entries_fock_h(int* count);
 const KernEntry* qc_entries_fock_ih(int* count);
 const KernEntry* qc_entries_fock_ih2(int* count);
 
-struct PipeEntry { int var, L, gc, ne, threads; kern_t fn; size_t (*smem)(int n_sub); };
+struct PipeEntry { int var, L, gc, ne, threads; kern_t fn; size_t (*smem)(int n_sub); int tabg; };
 const PipeEntry* qc_find_pipe(int var, int L, int G, int ne);
 const PipeEntry* qc_find_pipe_wide_smem(int var, int L, int G, int ne);
 struct ClusterEntry { int L, gsl, c, threads; kern_t fn; size_t (*smem)(int n_sub); };
@@ -136,7 +136,7 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
                 if (cudaFuncGetAttributes(&fa, (const void*)pe->fn) != cudaSuccess) { err = std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(cudaGetLastError()); return QC_ERR_CUDA; }
                 memset(&plan, 0, sizeof(plan));
                 plan.L = L; plan.T = TT; plan.G = G; plan.P = cpt; plan.chunk = mult * L; plan.W = W; plan.NP = G * L; plan.threads = pe->threads;
-                plan.smem_bytes = (int)pe->smem(n_sub); plan.tstride = 0; plan.maxt = pe->threads; plan.gc = G; plan.tabs = true; plan.binned = 1; plan.pipe = pe->ne;
+                plan.smem_bytes = (int)pe->smem(n_sub); plan.tstride = 0; plan.maxt = pe->threads; plan.gc = G; plan.tabs = true; plan.binned = 1; plan.pipe = pe->ne; plan.tabt = (pe->tabg && ne == 1 && env_int("QCART_PIPE_TABT", 1)) ? 1 : 0;
                 snprintf(plan.info, sizeof(plan.info), "sse_pipe_kernel<var=%d,L=%d,G=%d,NE=%d,NSW=%d%s> traj/CTA=%d chunks/traj=%d chunk=%d W=%d bin=1 threads=%d smem=%d regs=%d lmem=%d",
                          var, L, G, ne, nsw, (pe->ne & 64) ? ",tab=smem" : "", plan.T, cpt, plan.chunk, W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
                 return QC_OK;
@@ -440,6 +440,38 @@ __global__ void solve_exact_kernel(double2* __restrict__ psi, int n, const doubl
         if (lane < m) psi[i0 + lane] = v[lane];
         __syncwarp();
     }
+}
+// Chunk-transposed factor table for the solver warps of the single-group pipeline instances whose table stays in global memory (N = 1537..2112).
+// There lane c of a solver warp walks the rows of chunk c, i.e. the 32 lanes of a load hit 32 different 128-byte lines of the row-major table:
+// 160 L1 wavefronts per recurrence row, 179 cycles per row against 54 with the table in shared memory (development-build timers).  Here the entry
+// of relative row t of chunk c lies next to that of chunk c + 1:
+//     forward block  [r][k][c], k < ba: l_{k+1} of row i + k + 1 (the "diagonal" the scatter-form forward sweep needs), k = ba: 1 / d_i
+//     backward block [r][k][c], k < ba: l_{k+1} of row i
+// with i = c * chunk - W + (r - S) in the forward block (warm-up below the chunk) and i = c * chunk + (r - S) in the backward block (warm-up above
+// it), r in [0, chunk + W + 2 S), S = QC_TABT_SLACK(L) rows of slack either side for the look-ahead of the solver's loads, zero outside the grid.
+__global__ void fac_transpose_kernel(const double2* __restrict__ fac, double2* __restrict__ out, int n, int ba, int chunk, int W, int L, int nch, int rows) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * nch) return;
+    const int r = idx / nch, c = idx % nch, slot = blockIdx.y;
+    const long long i = (long long)c * chunk - W + (r - QC_TABT_SLACK(L));
+    const double2* __restrict__ src = fac + (size_t)slot * n * (ba + 1);
+    double2* __restrict__ dst = out + (size_t)slot * rows * (2 * ba + 1) * nch;
+    const double2 zero = make_double2(0.0, 0.0);
+    for (int k = 0; k < ba; k++) {
+        const long long ii = i + k + 1;
+        dst[((size_t)r * (ba + 1) + k) * nch + c] = (ii >= 0 && ii < n) ? src[(size_t)ii * (ba + 1) + k] : zero;
+    }
+    dst[((size_t)r * (ba + 1) + ba) * nch + c] = (i >= 0 && i < n) ? src[(size_t)i * (ba + 1) + ba] : zero;
+    // the backward sweep warms up on the rows ABOVE its chunk: its block covers i_b = c * chunk + (r - S)
+    const long long ib = (long long)c * chunk + (r - QC_TABT_SLACK(L));
+    double2* __restrict__ dstb = dst + (size_t)rows * (ba + 1) * nch;
+    for (int k = 0; k < ba; k++) dstb[((size_t)r * ba + k) * nch + c] = (ib >= 0 && ib < n) ? src[(size_t)ib * (ba + 1) + k] : zero;
+}
+int launch_fac_transpose(const double2* fac, double2* out, int n, int ba, int n_slots, int chunk, int W, int L, int nch, void* stream) {
+    const int rows = chunk + W + 2 * QC_TABT_SLACK(L);
+    dim3 grid((rows * nch + 255) / 256, n_slots);
+    fac_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(fac, out, n, ba, chunk, W, L, nch, rows);
+    return cudaGetLastError() == cudaSuccess ? QC_OK : QC_ERR_CUDA;
 }
 int launch_hdot(const double2* in, double2* out, int n, int variant, const double* hdiag, const double* h2, const double* tk, void* stream) {
     hdot_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(in, out, n, variant, hdiag, h2, tk[0], tk[1], tk[2], tk[3]);

@@ -139,6 +139,14 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
         if constexpr (!TABG) return tab[(j * CS + k) * G + min(max(col, 0), G - 1)];
         else { const int i = col * L + j; return (i >= 0 && i < npts) ? __ldg(&tab[(size_t)i * (BA + 1) + k]) : mk2(0.0, 0.0); }
     };
+    // chunk-transposed global table (single-group instances, p.fac_t != null; see fac_transpose_kernel): relative row r = (col - col0 + wb) L + j + L
+    // of this lane's chunk, entries of neighbouring chunks adjacent -> one coalesced 512-byte request per entry and warp
+    const bool tabt = TABG && p.fac_t != nullptr;             // (then `tab` points at this slot's transposed table)
+    constexpr int NCH = Geo::CPT;
+    constexpr int SLK = QC_TABT_SLACK(L);
+    const int rows_t = (wb + mult) * L + 2 * SLK, rbase = (wb - col0) * L + SLK, rbase_b = SLK - col0 * L;
+    const double2* __restrict__ tfw = tab;
+    const double2* __restrict__ tbw = tab + (size_t)rows_t * (BA + 1) * NCH;
     // (factor rows from global memory, TABG: L2 latency instead of shared-memory latency per row -> a deeper ring)
     constexpr int PFW = TABG ? QC_PIPE_PF_TABG : QC_PIPE_PF;
     constexpr int PF = (L % (PFW + 1) == 0) ? PFW : 2, NR = PF + 1;      // the row ring restarts with every column: L must be a multiple of NR
@@ -150,6 +158,12 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
     {
         auto load_fwd = [&](Row& r, int col, int j) {
             r.v = U[j * Gp + GUARD + col];
+            if (TABG && tabt) {
+                const size_t rr = (size_t)(col * L + j + rbase) * (BA + 1);
+#pragma unroll
+                for (int k = 0; k <= BA; k++) r.cf[k] = __ldg(&tfw[(rr + k) * NCH + cc]);
+                return;
+            }
 #pragma unroll
             for (int k = 1; k <= BA; k++) {
                 const int jj = (j + k) % L, dc = (j + k) / L;
@@ -198,6 +212,12 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
         double2 xprev = mk2(0.0, 0.0);                          // Fock: x_{i+1} for <x> = sum 2 xl_i Re(conj(x_i) x_{i+1})
         auto load_row = [&](Row& r, int col, int j, bool) {
             r.v = U[j * Gp + GUARD + col];
+            if (TABG && tabt) {
+                const size_t rr = (size_t)(col * L + j + rbase_b) * BA;
+#pragma unroll
+                for (int k = 0; k < BA; k++) r.cf[k] = __ldg(&tbw[(rr + k) * NCH + cc]);
+                return;
+            }
 #pragma unroll
             for (int k = 0; k < BA; k++) r.cf[k] = tabv(j, k, col);
             if constexpr (VAR != QC_QUARTIC) r.cf[BA] = tabv(j, BA + 1, col);      // (xl_i, 0)
@@ -391,7 +411,7 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG, NSW>::THREADS, 1
                 mbar_wait(&bars[X], s & 1);
                 tm.tick(0);
                 const int tsub = (Geo::CSW > 1) ? 0 : sub * Geo::NES;     // first trajectory of the set served by this warp
-                pipe_solve<Geo, VAR, L, TABG>(p, Uall + (size_t)(X * NE + tsub) * LBU, TABG ? p.fac + (size_t)cta_slot * n * (BA + 1) : tab,
+                pipe_solve<Geo, VAR, L, TABG>(p, Uall + (size_t)(X * NE + tsub) * LBU, TABG ? (p.fac_t ? p.fac_t + (size_t)cta_slot * p.fac_t_stride : p.fac + (size_t)cta_slot * n * (BA + 1)) : tab,
                                               scal_all + (X * NE + tsub) * 16, mult, wb, lane, s, tm, (Geo::CSW > 1) ? sub : 0, 8 + X);
                 mbar_arrive(&bars[2 + X]);
                 tm.tick(3);
@@ -892,10 +912,10 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG, NSW>::THREADS, 1
 
 
 // ne: groups per CTA; instances with NSW solver warps per set carry the id NE + 16 (NSW - 1)
-struct PipeEntry { int var, L, gc, ne, threads; kern_t fn; size_t (*smem)(int n_sub); };
+struct PipeEntry { int var, L, gc, ne, threads; kern_t fn; size_t (*smem)(int n_sub); int tabg; };
 #define QC_PE_NSW(VAR, L, GC, NE, NSW) {VAR, L, GC, NE + 16 * (NSW - 1), PipeGeo<VAR, L, GC, NE, false, NSW>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, false, NSW>, PipeGeo<VAR, L, GC, NE, false, NSW>::smem_bytes}
 #define QC_PE(VAR, L, GC, NE) {VAR, L, GC, NE, PipeGeo<VAR, L, GC, NE>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, false>, PipeGeo<VAR, L, GC, NE>::smem_bytes}
-#define QC_PE_TABG_NSW(VAR, L, GC, NE, NSW) {VAR, L, GC, NE + 16 * (NSW - 1), PipeGeo<VAR, L, GC, NE, true, NSW>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, true, NSW>, PipeGeo<VAR, L, GC, NE, true, NSW>::smem_bytes}
-#define QC_PE_TABG(VAR, L, GC, NE) {VAR, L, GC, NE, PipeGeo<VAR, L, GC, NE, true>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, true>, PipeGeo<VAR, L, GC, NE, true>::smem_bytes}
+#define QC_PE_TABG_NSW(VAR, L, GC, NE, NSW) {VAR, L, GC, NE + 16 * (NSW - 1), PipeGeo<VAR, L, GC, NE, true, NSW>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, true, NSW>, PipeGeo<VAR, L, GC, NE, true, NSW>::smem_bytes, 1}
+#define QC_PE_TABG(VAR, L, GC, NE) {VAR, L, GC, NE, PipeGeo<VAR, L, GC, NE, true>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, true>, PipeGeo<VAR, L, GC, NE, true>::smem_bytes, 1}
 
 }  // namespace qc

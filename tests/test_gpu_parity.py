@@ -580,9 +580,10 @@ def test_one_warp_group_pipeline_variants_match_oracle(task, ne, monkeypatch):
     assert np.array_equal(flags, out0["flags"].cpu().numpy())
 
 
-@pytest.mark.parametrize("npts,B", [(1281, 340), (2049, 340)])
+@pytest.mark.parametrize("npts,B", [(641, 340), (1281, 340), (1409, 340), (1793, 340), (2049, 340)])
 def test_wide_grid_pipeline_matches_oracle(npts, B):
-    """Single-group pipeline instances with the factor table in global memory (N = 577 .. 2112): a subset against the oracle."""
+    """Single-group pipeline instances (N = 577 .. 2112): factor table in shared memory where it fits next to the lines (N <= 1536), else
+    streamed from the chunk-transposed global copy: a subset of the trajectories against the oracle."""
     torch = _torch()
     params = configs.quartic_sweep(npts, n_sub=4)
     rng = np.random.default_rng(9)
@@ -593,7 +594,8 @@ def test_wide_grid_pipeline_matches_oracle(npts, B):
     sim.set_state(psi0)
     out = sim.step(torch.as_tensor(actions, device="cuda"), noise=torch.as_tensor(noise, device="cuda"))
     torch.cuda.synchronize()
-    assert "sse_pipe_kernel" in sim.kernel_info() and "NE=1,NSW=%d" % (2 if npts > 1700 else 1) in sim.kernel_info(), sim.kernel_info()
+    assert "sse_pipe_kernel" in sim.kernel_info() and "NE=1,NSW=%d" % (2 if npts > 1536 else 1) in sim.kernel_info(), sim.kernel_info()
+    assert ("tab=smem" in sim.kernel_info()) == (npts <= 1536), sim.kernel_info()
     pick = np.array([0, 1, B // 2, B - 1])
     orc = oracle_for(params)
     ref, fails, _ = oracle_control_step(orc, params, psi0[pick], actions[pick], noise[pick])
@@ -602,6 +604,35 @@ def test_wide_grid_pipeline_matches_oracle(npts, B):
     for k, b in enumerate(pick):
         m_ref = orc.get_moments(ref[k])
         assert np.max(np.abs(mom[b][:5] - m_ref[:5]) / np.maximum(np.abs(m_ref[:5]), 1e-3)) < 1e-9
+
+
+def test_transposed_factor_table_follows_on_demand_forces():
+    """N = 1793 streams its factor rows from the chunk-transposed copy of the table (fac_transpose_kernel).  Forces outside the 21 levels are
+    factorised on demand (qc_step_forces): the copy must be rebuilt, also when a slot is replaced; checked against the oracle."""
+    torch = _torch()
+    npts, B, n_sub = 1793, 340, 3
+    params = configs.quartic_sweep(npts, n_sub=n_sub)
+    rng = np.random.default_rng(19)
+    psi0 = np.tile(initial_states(params, 4, 5), (B // 4, 1))
+    sim = BatchedSim(params, batch=B)
+    sim.set_state(psi0)
+    ref = psi0[:4].copy()
+    orc = oracle_for(params)
+    pick = np.array([0, 1, 2, 3])
+    for it in range(3):
+        noise = rng.standard_normal((B, n_sub, 2))
+        if it == 1:
+            act = rng.integers(0, 21, B).astype(np.int32)
+            forces = np.array([level_force(params, int(a)) for a in act])
+            sim.step(torch.as_tensor(act, device="cuda"), noise=torch.as_tensor(noise, device="cuda"))
+        else:
+            forces = np.repeat(rng.uniform(-4.0, 4.0, 10), B // 10)      # 10 new force values per call, 34 trajectories each
+            sim.step_forces(forces, noise=torch.as_tensor(noise, device="cuda"))
+        torch.cuda.synchronize()
+        assert "sse_pipe_kernel" in sim.kernel_info() and "tab=smem" not in sim.kernel_info(), sim.kernel_info()
+        for k, b in enumerate(pick):
+            orc.run(ref[k], params["dt"], float(forces[b]), params["gamma"], noise[b])
+        assert rel_err(sim.get_state()[pick], ref) < TOL_STEP * (it + 1)
 
 
 @pytest.mark.parametrize("npts", [2501, 4097])
