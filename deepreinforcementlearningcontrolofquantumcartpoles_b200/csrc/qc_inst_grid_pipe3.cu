@@ -5,7 +5,8 @@
 namespace qc {
 // instance id = NE + 64: told apart from the global-table instance of the same geometry (id NE) when the launch looks the plan's kernel up again
 #define QC_PE_WS(VAR, L, GC, NE) {VAR, L, GC, NE + 64, PipeGeo<VAR, L, GC, NE>::THREADS, sse_pipe_kernel<VAR, L, GC, NE, false>, PipeGeo<VAR, L, GC, NE>::smem_bytes}
-static const PipeEntry k_pipe[] = { QC_PE_WS(QC_QUARTIC, 6, 256, 1), QC_PE_WS(QC_QUARTIC, 6, 224, 1), QC_PE_WS(QC_QUARTIC, 6, 192, 1), QC_PE_WS(QC_QUARTIC, 6, 160, 1), QC_PE_WS(QC_QUARTIC, 6, 128, 1) };
+static const PipeEntry k_pipe[] = { QC_PE_WS(QC_QUARTIC, 6, 256, 1), QC_PE_WS(QC_QUARTIC, 6, 224, 1), QC_PE_WS(QC_QUARTIC, 6, 192, 1), QC_PE_WS(QC_QUARTIC, 6, 160, 1), QC_PE_WS(QC_QUARTIC, 6, 128, 1),
+                                    QC_PE_WS(QC_QUARTIC, 6, 160, 2), QC_PE_WS(QC_QUARTIC, 6, 128, 2) };   // two groups per CTA: four trajectories in flight (N = 577..960)
 const PipeEntry* qc_find_pipe_wide_smem(int var, int L, int G, int ne) {
     for (const PipeEntry& e : k_pipe) if (e.var == var && e.L == L && e.gc == G && (ne <= 0 || e.ne == ne)) return &e;
     return nullptr;

@@ -113,8 +113,10 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
         const int want_ne = env_int("QCART_PIPE_NE", (var == QC_HARMONIC) ? 24 /* NE = 8, two solver warps per set */ : ((var == QC_INV_HARMONIC) ? 4 : (G >= 288 ? 17 /* NE = 1, two solver warps per trajectory */ : (G >= 128 ? 1 : 0))));
         const PipeEntry* pe = qc_find_pipe(var, L, G, want_ne);
         // single-group CTAs: the instance with the factor table in shared memory when table + lines fit (QCART_PIPE_TABS=0: table in L2)
+        // (QCART_PIPE_TABS=3: only the one-group form; 1, default: two groups per CTA where four state lines still fit, N = 577..960)
         if (var == QC_QUARTIC && want_ne == 1 && env_int("QCART_PIPE_TABS", 1)) {
-            const PipeEntry* ps = qc_find_pipe_wide_smem(var, L, G, 1 + 64);
+            const PipeEntry* ps = (env_int("QCART_PIPE_TABS", 1) == 1) ? qc_find_pipe_wide_smem(var, L, G, 2 + 64) : nullptr;
+            if (!ps || (int)ps->smem(n_sub) > smem_max) ps = qc_find_pipe_wide_smem(var, L, G, 1 + 64);
             if (ps && (int)ps->smem(n_sub) <= smem_max) pe = ps;
         }
         const int GUc = (G == 32) ? 10 : ((var == QC_QUARTIC) ? 5 : 12);

@@ -10,7 +10,7 @@ from common import initial_states, oracle_for, oracle_control_step
 from deepreinforcementlearningcontrolofquantumcartpoles_b200 import configs, BatchedSim, measure_peaks, QcartError
 
 fp64_peak, _ = measure_peaks(0)
-for npts, B in ((257, 4096), (513, 4096), (1025, 2048), (2049, 1024), (4097, 296), (8193, 148)):
+for npts, B in ((257, 4096), (513, 4096), (641, 4096), (769, 4096), (1025, 2048), (1281, 2048), (1409, 2048), (1537, 1024), (1793, 1024), (2049, 1024), (2501, 592), (4097, 296), (8193, 148)):
     params = configs.quartic_sweep(npts)
     rec = {"N": npts, "B": B, "dt": params["dt"], "n_sub": params["n_sub"]}
     try:
