@@ -580,7 +580,7 @@ def test_one_warp_group_pipeline_variants_match_oracle(task, ne, monkeypatch):
     assert np.array_equal(flags, out0["flags"].cpu().numpy())
 
 
-@pytest.mark.parametrize("npts,B", [(641, 340), (1281, 340), (1409, 340), (1793, 340), (2049, 340)])
+@pytest.mark.parametrize("npts,B", [(641, 340), (897, 340), (1281, 340), (1409, 340), (1793, 340), (2049, 340)])
 def test_wide_grid_pipeline_matches_oracle(npts, B):
     """Single-group pipeline instances (N = 577 .. 2112): factor table in shared memory where it fits next to the lines (N <= 1536), else
     streamed from the chunk-transposed global copy: a subset of the trajectories against the oracle."""
@@ -594,7 +594,8 @@ def test_wide_grid_pipeline_matches_oracle(npts, B):
     sim.set_state(psi0)
     out = sim.step(torch.as_tensor(actions, device="cuda"), noise=torch.as_tensor(noise, device="cuda"))
     torch.cuda.synchronize()
-    assert "sse_pipe_kernel" in sim.kernel_info() and "NE=1,NSW=%d" % (2 if npts > 1536 else 1) in sim.kernel_info(), sim.kernel_info()
+    # N <= 960: two groups per CTA; above: one group; N > 1536: two solver warps per trajectory
+    assert "sse_pipe_kernel" in sim.kernel_info() and "NE=%d,NSW=%d" % (2 if npts <= 960 else 1, 2 if npts > 1536 else 1) in sim.kernel_info(), sim.kernel_info()
     assert ("tab=smem" in sim.kernel_info()) == (npts <= 1536), sim.kernel_info()
     pick = np.array([0, 1, B // 2, B - 1])
     orc = oracle_for(params)
