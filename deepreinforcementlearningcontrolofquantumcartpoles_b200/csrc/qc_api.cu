@@ -601,7 +601,8 @@ extern "C" int qc_step_host(qc_sim* s, const int32_t* action, const double* nois
     // copied behind the launch.  (With the fused exchange active the rows travel to the peers instead and the copies stay.)
     double* zm = (moments && s->g_world == 0) ? (double*)mapped_alias(moments) : nullptr;
     double* za = (aux && s->g_world == 0) ? (double*)mapped_alias(aux) : nullptr;
-    unsigned char* zf = (flags && s->g_world == 0) ? (unsigned char*)mapped_alias(flags) : nullptr;
+    // (a launch without moments and aux leaves the kernels before their output stage: flags alone are copied)
+    unsigned char* zf = (flags && (moments || aux) && s->g_world == 0) ? (unsigned char*)mapped_alias(flags) : nullptr;
     s->mir_mom = zm; s->mir_aux = za; s->mir_flags = zf;
     rc = run(s, s->batch, s->d_action, dn, n_sub, nullptr, moments ? s->d_mom : nullptr, aux ? s->d_aux : nullptr, flags ? s->d_flagout : nullptr, nullptr, nullptr, 0, st);
     s->mir_mom = nullptr; s->mir_aux = nullptr; s->mir_flags = nullptr;

@@ -7,7 +7,10 @@
 #include "qc_pipe_impl.cuh"
 namespace qc {
 const PipeEntry* qc_find_pipe_wide_smem(int var, int L, int G, int ne);
-static const PipeEntry k_pipe[] = { QC_PE_TABG_NSW(QC_QUARTIC, 6, 352, 1, 2), QC_PE_TABG_NSW(QC_QUARTIC, 6, 320, 1, 2), QC_PE_TABG_NSW(QC_QUARTIC, 6, 288, 1, 2),
+static const PipeEntry k_pipe[] = {
+#if QC_PIPE_SPLIT          // (two solver warps per trajectory need the split layout)
+                                    QC_PE_TABG_NSW(QC_QUARTIC, 6, 352, 1, 2), QC_PE_TABG_NSW(QC_QUARTIC, 6, 320, 1, 2), QC_PE_TABG_NSW(QC_QUARTIC, 6, 288, 1, 2),
+#endif
                                     QC_PE_TABG(QC_QUARTIC, 6, 352, 1), QC_PE_TABG(QC_QUARTIC, 6, 320, 1), QC_PE_TABG(QC_QUARTIC, 6, 288, 1),
                                     QC_PE_TABG(QC_QUARTIC, 6, 256, 1), QC_PE_TABG(QC_QUARTIC, 6, 224, 1), QC_PE_TABG(QC_QUARTIC, 6, 192, 1), QC_PE_TABG(QC_QUARTIC, 6, 160, 1), QC_PE_TABG(QC_QUARTIC, 6, 128, 1) };
 const PipeEntry* qc_find_pipe_wide(int var, int L, int G, int ne) {

@@ -158,6 +158,11 @@ def test_host_entry_point_pinned_buffers_equal_pageable_buffers():
             assert np.array_equal(mom_p.numpy(), mom) and np.array_equal(aux_p.numpy(), aux) and np.array_equal(flg_p.numpy(), flags), a.kernel_info()
             assert np.array_equal(mom_c, mom) and np.array_equal(aux_c.numpy(), aux) and np.array_equal(flg_c, flags)
         assert np.array_equal(a.get_state(), b.get_state())
+        # flags alone (no moments, no aux): the kernels skip their output stage, the pinned flag buffer is filled by a copy
+        flg_only = torch.full((B,), 255, dtype=torch.uint8).pin_memory()
+        L.check(a.lib.qc_step_host(a.h, act.ctypes.data, None, 0, None, None, flg_only.data_ptr()))
+        L.check(b.lib.qc_step_host(b.h, act.ctypes.data, None, 0, None, None, flags.ctypes.data))
+        assert np.array_equal(flg_only.numpy(), flags) and flags.max() < 255
 
 
 def test_fail_and_escape_flags():
