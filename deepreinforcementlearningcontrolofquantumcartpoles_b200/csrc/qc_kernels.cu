@@ -138,7 +138,7 @@ int plan_launch(const Model& m, int n_sub, int B, int W_needed, LaunchPlan& plan
                 if (cudaFuncGetAttributes(&fa, (const void*)pe->fn) != cudaSuccess) { err = std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(cudaGetLastError()); return QC_ERR_CUDA; }
                 memset(&plan, 0, sizeof(plan));
                 plan.L = L; plan.T = TT; plan.G = G; plan.P = cpt; plan.chunk = mult * L; plan.W = W; plan.NP = G * L; plan.threads = pe->threads;
-                plan.smem_bytes = (int)pe->smem(n_sub); plan.tstride = 0; plan.maxt = pe->threads; plan.gc = G; plan.tabs = true; plan.binned = 1; plan.pipe = pe->ne; plan.tabt = (pe->tabg && ne == 1 && env_int("QCART_PIPE_TABT", 1)) ? 1 : 0;
+                plan.smem_bytes = (int)pe->smem(n_sub); plan.tstride = 0; plan.maxt = pe->threads; plan.gc = G; plan.tabs = true; plan.binned = 1; plan.pipe = pe->ne; plan.tabt = (pe->tabg && ne == 1) ? 1 : 0;      // PipeGeo::TABT
                 snprintf(plan.info, sizeof(plan.info), "sse_pipe_kernel<var=%d,L=%d,G=%d,NE=%d,NSW=%d%s> traj/CTA=%d chunks/traj=%d chunk=%d W=%d bin=1 threads=%d smem=%d regs=%d lmem=%d",
                          var, L, G, ne, nsw, (pe->ne & 64) ? ",tab=smem" : "", plan.T, cpt, plan.chunk, W, plan.threads, plan.smem_bytes, fa.numRegs, (int)fa.localSizeBytes);
                 return QC_OK;

@@ -106,6 +106,8 @@ template <int VAR, int L, int GC, int NE, bool TABG = false, int NSW = 1> struct
     static_assert(CSW <= 2, "at most two solver warps per trajectory");
 static constexpr int WARPS = ((LASTW > 7 || !SOLO ? LASTW : 7) + 4) / 4 * 4;   // whole warp quads: the register file is per SM sub-partition, so a partial quad buys no registers (ptxas: 320 threads -> 168, not 200)
     static constexpr int THREADS = WARPS * 32;
+    // single-group instances with the table in global memory read the chunk-transposed copy (StepParams::fac_t, see fac_transpose_kernel)
+    static constexpr bool TABT = TABG && NE == 1;
     static constexpr size_t tab_bytes = TABG ? 0 : (size_t)CS * L * G * 16 + (size_t)HT * L * G * 8;
     static constexpr size_t fixed_bytes = tab_bytes + (size_t)TT * LBU * 16 + (size_t)NE * NS * LBS * 16 + (size_t)TT * 128 /* scal */ +
                                           (size_t)NE * 2 * QC_MAXRED * NWG * 8 /* red */ + (size_t)NE * 128 /* stash */ + 64 /* mbarriers */;
@@ -141,7 +143,7 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
     };
     // chunk-transposed global table (single-group instances, p.fac_t != null; see fac_transpose_kernel): relative row r = (col - col0 + wb) L + j + L
     // of this lane's chunk, entries of neighbouring chunks adjacent -> one coalesced 512-byte request per entry and warp
-    const bool tabt = TABG && p.fac_t != nullptr;             // (then `tab` points at this slot's transposed table)
+    constexpr bool tabt = Geo::TABT;                          // (then `tab` points at this slot's transposed table)
     constexpr int NCH = Geo::CPT;
     constexpr int SLK = QC_TABT_SLACK(L);
     const int rows_t = (wb + mult) * L + 2 * SLK, rbase = (wb - col0) * L + SLK, rbase_b = SLK - col0 * L;
@@ -158,18 +160,18 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
     {
         auto load_fwd = [&](Row& r, int col, int j) {
             r.v = U[j * Gp + GUARD + col];
-            if (TABG && tabt) {
+            if constexpr (tabt) {
                 const size_t rr = (size_t)(col * L + j + rbase) * (BA + 1);
 #pragma unroll
                 for (int k = 0; k <= BA; k++) r.cf[k] = __ldg(&tfw[(rr + k) * NCH + cc]);
-                return;
-            }
+            } else {
 #pragma unroll
-            for (int k = 1; k <= BA; k++) {
-                const int jj = (j + k) % L, dc = (j + k) / L;
-                r.cf[k - 1] = tabv(jj, k - 1, col + dc);
+                for (int k = 1; k <= BA; k++) {
+                    const int jj = (j + k) % L, dc = (j + k) / L;
+                    r.cf[k - 1] = tabv(jj, k - 1, col + dc);
+                }
+                r.cf[BA] = tabv(j, BA, col);
             }
-            r.cf[BA] = tabv(j, BA, col);
         };
         double2 pend[BA];
 #pragma unroll
@@ -212,15 +214,15 @@ __device__ __forceinline__ void pipe_solve(const StepParams& p, double2* __restr
         double2 xprev = mk2(0.0, 0.0);                          // Fock: x_{i+1} for <x> = sum 2 xl_i Re(conj(x_i) x_{i+1})
         auto load_row = [&](Row& r, int col, int j, bool) {
             r.v = U[j * Gp + GUARD + col];
-            if (TABG && tabt) {
+            if constexpr (tabt) {
                 const size_t rr = (size_t)(col * L + j + rbase_b) * BA;
 #pragma unroll
                 for (int k = 0; k < BA; k++) r.cf[k] = __ldg(&tbw[(rr + k) * NCH + cc]);
-                return;
-            }
+            } else {
 #pragma unroll
-            for (int k = 0; k < BA; k++) r.cf[k] = tabv(j, k, col);
-            if constexpr (VAR != QC_QUARTIC) r.cf[BA] = tabv(j, BA + 1, col);      // (xl_i, 0)
+                for (int k = 0; k < BA; k++) r.cf[k] = tabv(j, k, col);
+                if constexpr (VAR != QC_QUARTIC) r.cf[BA] = tabv(j, BA + 1, col);      // (xl_i, 0)
+            }
         };
         Row ring[NR];
         int col = col0 + mult + wb - 1;
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(PipeGeo<VAR, L, GC, NE, TABG, NSW>::THREADS, 1
                 mbar_wait(&bars[X], s & 1);
                 tm.tick(0);
                 const int tsub = (Geo::CSW > 1) ? 0 : sub * Geo::NES;     // first trajectory of the set served by this warp
-                pipe_solve<Geo, VAR, L, TABG>(p, Uall + (size_t)(X * NE + tsub) * LBU, TABG ? (p.fac_t ? p.fac_t + (size_t)cta_slot * p.fac_t_stride : p.fac + (size_t)cta_slot * n * (BA + 1)) : tab,
+                pipe_solve<Geo, VAR, L, TABG>(p, Uall + (size_t)(X * NE + tsub) * LBU, TABG ? (Geo::TABT ? p.fac_t + (size_t)cta_slot * p.fac_t_stride : p.fac + (size_t)cta_slot * n * (BA + 1)) : tab,
                                               scal_all + (X * NE + tsub) * 16, mult, wb, lane, s, tm, (Geo::CSW > 1) ? sub : 0, 8 + X);
                 mbar_arrive(&bars[2 + X]);
                 tm.tick(3);
