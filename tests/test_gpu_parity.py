@@ -607,6 +607,26 @@ def test_wide_grid_pipeline_matches_oracle(npts, B):
         assert np.max(np.abs(mom[b][:5] - m_ref[:5]) / np.maximum(np.abs(m_ref[:5]), 1e-3)) < 1e-9
 
 
+def test_wide_grid_falls_back_to_the_streamed_table_when_shared_memory_is_short():
+    """N = 1409 keeps its factor table in shared memory with 320 bytes to spare at 160 substeps; a longer control step (larger noise block)
+    must select the instance that streams the chunk-transposed table instead -- same results against the oracle."""
+    torch = _torch()
+    npts, B, n_sub = 1409, 340, 200
+    params = configs.quartic_sweep(npts, n_sub=n_sub)
+    rng = np.random.default_rng(23)
+    psi0 = np.tile(initial_states(params, 4, 6), (B // 4, 1))
+    actions = rng.integers(0, 21, B).astype(np.int32)
+    noise = rng.standard_normal((B, n_sub, 2))
+    sim = BatchedSim(params, batch=B)
+    sim.set_state(psi0)
+    sim.step(torch.as_tensor(actions, device="cuda"), noise=torch.as_tensor(noise, device="cuda"))
+    torch.cuda.synchronize()
+    assert "sse_pipe_kernel" in sim.kernel_info() and "G=256,NE=1" in sim.kernel_info() and "tab=smem" not in sim.kernel_info(), sim.kernel_info()
+    pick = np.array([0, B - 1])
+    ref, _, _ = oracle_control_step(oracle_for(params), params, psi0[pick], actions[pick], noise[pick])
+    assert rel_err(sim.get_state()[pick], ref) < TOL_STEP
+
+
 def test_transposed_factor_table_follows_on_demand_forces():
     """N = 1793 streams its factor rows from the chunk-transposed copy of the table (fac_transpose_kernel).  Forces outside the 21 levels are
     factorised on demand (qc_step_forces): the copy must be rebuilt, also when a slot is replaced; checked against the oracle."""
